@@ -1,0 +1,491 @@
+// C ABI of the genetest_b200 engine (see include/genetest_b200.h).
+// Host side: design factorisation (QR of the covariates, full-sample Gram
+// matrix, E matrix in genotype-file order), workspace management, batching,
+// kernel dispatch, timing.  No torch types, no exceptions across the ABI.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "gt_common.cuh"
+#include "gt_host.cuh"
+#include "gt_contract.cuh"
+#include "gt_linear.cuh"
+#include "gt_logistic.cuh"
+#include "gt_cox.cuh"
+
+struct gt_engine {
+    int device = 0;
+    cudaStream_t stream = nullptr, own_stream = nullptr;
+    bool have_design = false;
+    int model = GT_MODEL_LINEAR;
+    GtDesignDev D{};
+    gtk::IterDesignDev T{};           // logistic / coxph design
+    DevBuf dE, dMask, dFF0, dR, dRinv, dTq, dIter;   // design
+    DevBuf dS, dCounts;                        // per-batch workspace
+    DevBuf dGeno, dOut, dIout;                 // staging of the *_host entry points
+    int contract_idx = -1;
+    // timing
+    bool timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
+    size_t events_used = 0;
+    double ms_total = 0.0;
+    int64_t launches = 0, all_launches = 0;
+    std::string dominant;
+};
+
+// ---------------------------------------------------------------------------
+// contraction kernel instantiations
+// ---------------------------------------------------------------------------
+typedef void (*contract_fn)(const uint8_t *, long long, int, const uint8_t *, const double *, int,
+                            double *, int *);
+struct ContractEntry { int NCA, NCB, rows, smem; contract_fn fn; };
+
+template <int NCA, int NCB>
+struct RowsFor {
+    static constexpr int NC = NCA + NCB;
+    static constexpr int value = NC <= 16 ? 4 : (NC <= 24 ? 3 : (NC <= 36 ? 2 : 1));
+};
+template <int NCA, int NCB>
+static constexpr int contract_smem() {
+    using Cfg = gtk::ContractCfg<NCA, NCB, RowsFor<NCA, NCB>::value>;
+    int red = gtk::kWarps * 32 * Cfg::NC * 8 + gtk::kWarps * 32 * 3 * 4;
+    return Cfg::kSmem > red ? Cfg::kSmem : red;
+}
+#define GT_ENTRY(A, B) \
+    { A, B, RowsFor<A, B>::value, contract_smem<A, B>(), gtk::contract_packed_kernel<A, B, RowsFor<A, B>::value> }
+static const ContractEntry kContract[] = {
+    GT_ENTRY(6, 2),  GT_ENTRY(10, 2), GT_ENTRY(14, 2), GT_ENTRY(18, 2), GT_ENTRY(24, 2), GT_ENTRY(32, 2),
+    GT_ENTRY(12, 4), GT_ENTRY(20, 4), GT_ENTRY(28, 4), GT_ENTRY(36, 4), GT_ENTRY(48, 4),
+    GT_ENTRY(18, 6), GT_ENTRY(30, 6), GT_ENTRY(42, 6), GT_ENTRY(54, 6),
+    GT_ENTRY(32, 10), GT_ENTRY(48, 10), GT_ENTRY(64, 10),
+};
+static const int kNumContract = sizeof(kContract) / sizeof(kContract[0]);
+
+static int pick_contract(int NC1, int NC2) {
+    int best = -1;
+    for (int i = 0; i < kNumContract; ++i) {
+        if (kContract[i].NCA >= NC1 && kContract[i].NCB >= NC2) {
+            if (best < 0 || kContract[i].NCA + kContract[i].NCB < kContract[best].NCA + kContract[best].NCB)
+                best = i;
+        }
+    }
+    return best;
+}
+
+// ---------------------------------------------------------------------------
+// small kernels: t quantile table, synthetic .bed rows
+// ---------------------------------------------------------------------------
+__global__ void tq_table_kernel(double *tq, int n) {
+    int df = blockIdx.x * blockDim.x + threadIdx.x;
+    if (df <= n) tq[df] = (df > 0) ? gt_t_ppf975((double)df) : nan("");
+}
+
+__device__ __forceinline__ uint64_t splitmix(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+__device__ __forceinline__ double u01(uint64_t h) { return (double)(h >> 11) * (1.0 / 9007199254740992.0); }
+
+__global__ void synth_packed_kernel(uint8_t *packed, long long pitch, int n_file, int n_snps,
+                                    uint64_t seed, double maf_lo, double maf_hi, double miss) {
+    long long bps = (n_file + 3) / 4;
+    long long total = (long long)n_snps * bps;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        int snp = (int)(t / bps);
+        int byte = (int)(t % bps);
+        double maf = maf_lo + (maf_hi - maf_lo) * u01(splitmix(seed ^ (0xABCDull + (uint64_t)snp * 0x100000001B3ull)));
+        uint8_t v = 0;
+        for (int j = 0; j < 4; ++j) {
+            int s = byte * 4 + j;
+            if (s >= n_file) break;   // PLINK pads the last byte with zero bits
+            uint64_t h = splitmix(seed + ((uint64_t)snp << 32) + (uint64_t)s);
+            uint64_t h2 = splitmix(h);
+            uint64_t h3 = splitmix(h2);
+            int g = (u01(h) < maf) + (u01(h2) < maf);    // copies of the coded allele A1
+            uint8_t code = g == 2 ? 0 : (g == 1 ? 2 : 3);
+            if (u01(h3) < miss) code = 1;
+            v |= code << (2 * j);
+        }
+        packed[(long long)snp * pitch + byte] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------
+extern "C" {
+
+int gt_abi_version(void) { return GT_ABI_VERSION; }
+const char *gt_last_error(void) { return g_err.c_str(); }
+
+int64_t gt_packed_pitch(int32_t n_file) {
+    int64_t bps = ((int64_t)n_file + 3) / 4;
+    return (bps + 127) / 128 * 128;
+}
+
+int gt_engine_create(int device, gt_engine **out) {
+    if (!out) return fail(GT_E_ARG, "gt_engine_create: out is NULL");
+    int count = 0;
+    CK(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) return fail(GT_E_ARG, "gt_engine_create: no CUDA device %d (found %d)", device, count);
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(GT_E_UNSUPPORTED, "gt_engine_create: device %d is sm_%d%d; this library is built for sm_100a only",
+                    device, prop.major, prop.minor);
+    gt_engine *e = new gt_engine();
+    e->device = device;
+    CK(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+    e->stream = e->own_stream;
+    *out = e;
+    return 0;
+}
+
+int gt_engine_destroy(gt_engine *e) {
+    if (!e) return 0;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    for (auto &ev : e->events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    DevBuf *bufs[] = {&e->dE, &e->dMask, &e->dFF0, &e->dR, &e->dRinv, &e->dTq, &e->dIter,
+                      &e->dS, &e->dCounts, &e->dGeno, &e->dOut, &e->dIout};
+    for (DevBuf *b : bufs) b->release();
+    if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    delete e;
+    return 0;
+}
+
+int gt_engine_set_stream(gt_engine *e, void *cuda_stream) {
+    if (!e) return fail(GT_E_ARG, "engine is NULL");
+    e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
+    return 0;
+}
+
+int gt_engine_synchronize(gt_engine *e) {
+    if (!e) return fail(GT_E_ARG, "engine is NULL");
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    for (size_t i = 0; i < e->events_used; ++i) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e->events[i].first, e->events[i].second));
+        e->ms_total += ms;
+    }
+    e->events_used = 0;
+    return 0;
+}
+
+int gt_engine_enable_timing(gt_engine *e, int on) {
+    if (!e) return fail(GT_E_ARG, "engine is NULL");
+    e->timing = on != 0;
+    e->ms_total = 0.0; e->launches = 0; e->all_launches = 0; e->events_used = 0;
+    return 0;
+}
+
+int gt_engine_kernel_time(gt_engine *e, double *ms_total, int64_t *launches, int64_t *all_launches) {
+    if (!e) return fail(GT_E_ARG, "engine is NULL");
+    if (ms_total) *ms_total = e->ms_total;
+    if (launches) *launches = e->launches;
+    if (all_launches) *all_launches = e->all_launches;
+    return 0;
+}
+
+const char *gt_engine_dominant_kernel(const gt_engine *e) { return e ? e->dominant.c_str() : ""; }
+
+int gt_engine_num_params(const gt_engine *e) {
+    if (!e || !e->have_design) return fail(GT_E_STATE, "no design set");
+    return e->model == GT_MODEL_LINEAR ? e->D.p : e->T.p;
+}
+int gt_engine_num_fields(const gt_engine *e) {
+    int p = gt_engine_num_params(e);
+    return p < 0 ? p : GT_F_PARAM0 + 6 * p;
+}
+
+int gt_engine_set_design(gt_engine *e, const gt_design_desc *d) {
+    if (!e || !d) return fail(GT_E_ARG, "gt_engine_set_design: NULL argument");
+    if (d->n <= 0 || d->k < 0 || d->n_inter < 0 || !d->y || (d->k > 0 && !d->C))
+        return fail(GT_E_ARG, "gt_engine_set_design: bad sizes (n=%d k=%d n_inter=%d)", d->n, d->k, d->n_inter);
+    if (d->n_inter > 0 && !d->W) return fail(GT_E_ARG, "gt_engine_set_design: n_inter > 0 but W is NULL");
+    if (d->model == GT_MODEL_COXPH && !d->event) return fail(GT_E_ARG, "gt_engine_set_design: coxph needs event");
+    const int n = d->n, k = d->k, I = d->n_inter;
+    const int n_file = d->sample_pos ? d->n_file : (d->n_file > 0 ? d->n_file : n);
+    if (n_file < n) return fail(GT_E_ARG, "gt_engine_set_design: n_file (%d) < n (%d)", n_file, n);
+    if (k + 1 + I > 32) return fail(GT_E_UNSUPPORTED, "gt_engine_set_design: at most 32 design columns (got %d)", k + 1 + I);
+    CK(cudaSetDevice(e->device));
+    std::vector<int> pos(n);
+    {
+        std::vector<char> seen(n_file, 0);
+        for (int i = 0; i < n; ++i) {
+            int ps = d->sample_pos ? d->sample_pos[i] : i;
+            if (ps < 0 || ps >= n_file || seen[ps])
+                return fail(GT_E_ARG, "gt_engine_set_design: sample_pos[%d]=%d invalid or duplicated", i, ps);
+            seen[ps] = 1;
+            pos[i] = ps;
+        }
+    }
+    e->have_design = false;
+    e->model = d->model;
+    cudaStream_t st = e->stream;
+    const int64_t pitch = gt_packed_pitch(n_file);
+    const int n_chunks = (n_file + gtk::kChunk - 1) / gtk::kChunk;
+    const size_t n_pad = (size_t)n_chunks * gtk::kChunk;
+
+    // mask of the 2-bit pairs that are not design rows (file padding included)
+    std::vector<uint8_t> mask((size_t)pitch, 0xFF);
+    for (int i = 0; i < n; ++i) mask[pos[i] >> 2] &= (uint8_t)~(3u << (2 * (pos[i] & 3)));
+    int rc = upload(e->dMask, mask.data(), mask.size(), st);
+    if (rc) return rc;
+
+    if (d->model == GT_MODEL_LINEAR) {
+        HostDesign H;
+        H.n = n; H.k = k; H.I = I; H.L = k + 2 + I;
+        qr_mgs2(d->C, n, k, H);
+        // explicit constant column (statsmodels k_constant) -> centre y on it
+        for (int j = 0; j < k && H.icpt_col < 0; ++j) {
+            const double *c = d->C + (size_t)j * n;
+            double lo = c[0], hi = c[0];
+            for (int i = 1; i < n; ++i) { lo = std::min(lo, c[i]); hi = std::max(hi, c[i]); }
+            if (lo == hi && lo != 0.0) H.icpt_col = j;
+        }
+        H.has_const = H.icpt_col >= 0;
+        if (!H.has_const && k > 0 && !H.degenerate) {
+            // implicit constant: ones in span(Q)
+            long double res = n;
+            for (int j = 0; j < k; ++j) {
+                long double s = 0;
+                for (int i = 0; i < n; ++i) s += H.Q[(size_t)j * n + i];
+                res -= s * s;
+            }
+            if (res < 1e-9L * n) H.has_const = 1;
+        }
+        long double ysum = 0;
+        for (int i = 0; i < n; ++i) ysum += d->y[i];
+        double ybar = H.icpt_col >= 0 ? (double)(ysum / n) : 0.0;
+        H.icpt_shift = H.icpt_col >= 0 ? ybar / d->C[(size_t)H.icpt_col * n] : 0.0;
+
+        const int L = H.L;
+        const int NC1 = (I + 1) * L, NC2 = (I + 1) * (I + 2) / 2;
+        int ci = pick_contract(NC1, NC2);
+        if (ci < 0) return fail(GT_E_UNSUPPORTED, "gt_engine_set_design: no contraction kernel for %d+%d columns (k=%d, interactions=%d)", NC1, NC2, k, I);
+        const int NCA = kContract[ci].NCA, NCB = kContract[ci].NCB, NCP = NCA + NCB;
+        e->contract_idx = ci;
+
+        std::vector<double> V((size_t)n * L);      // row-major base vectors
+        for (int i = 0; i < n; ++i) {
+            double *v = &V[(size_t)i * L];
+            for (int j = 0; j < k; ++j) v[j] = H.Q[(size_t)j * n + i];
+            v[k] = d->y[i] - ybar;
+            v[k + 1] = 1.0;
+            for (int j = 0; j < I; ++j) v[k + 2 + j] = d->W[(size_t)j * n + i];
+        }
+        std::vector<long double> ff((size_t)L * L, 0.0L);
+        for (int i = 0; i < n; ++i) {
+            const double *v = &V[(size_t)i * L];
+            for (int a = 0; a < L; ++a)
+                for (int b = a; b < L; ++b) ff[(size_t)a * L + b] += (long double)v[a] * v[b];
+        }
+        std::vector<double> FF0((size_t)L * L);
+        for (int a = 0; a < L; ++a)
+            for (int b = a; b < L; ++b) FF0[(size_t)a * L + b] = FF0[(size_t)b * L + a] = (double)ff[(size_t)a * L + b];
+
+        std::vector<double> E(n_pad * NCP, 0.0);
+        for (int i = 0; i < n; ++i) {
+            const double *v = &V[(size_t)i * L];
+            double *er = &E[(size_t)pos[i] * NCP];
+            for (int c = 0; c <= I; ++c) {
+                double m = c == 0 ? 1.0 : v[k + 1 + c];
+                for (int b = 0; b < L; ++b) er[c * L + b] = m * v[b];
+            }
+            int idx = 0;
+            for (int a = 0; a <= I; ++a)
+                for (int b = a; b <= I; ++b) {
+                    double ma = a == 0 ? 1.0 : v[k + 1 + a], mb = b == 0 ? 1.0 : v[k + 1 + b];
+                    er[NCA + idx++] = ma * mb;
+                }
+        }
+        if ((rc = upload(e->dE, E.data(), E.size() * 8, st))) return rc;
+        if ((rc = upload(e->dFF0, FF0.data(), FF0.size() * 8, st))) return rc;
+        if ((rc = upload(e->dR, H.R.data(), H.R.size() * 8, st))) return rc;
+        if ((rc = upload(e->dRinv, H.Rinv.data(), H.Rinv.size() * 8, st))) return rc;
+        if ((rc = e->dTq.reserve(((size_t)n + 1) * 8))) return rc;
+        tq_table_kernel<<<(n + 1 + 127) / 128, 128, 0, st>>>((double *)e->dTq.p, n);
+        CK(cudaGetLastError());
+
+        GtDesignDev &D = e->D;
+        D.n_file = n_file; D.n = n; D.k = k; D.I = I; D.L = L; D.p = k + 1 + I;
+        D.NC1 = NC1; D.NC2 = NC2; D.NCA = NCA; D.NCB = NCB; D.NCP = NCP;
+        D.NPROD = L * (L + 1) / 2;
+        D.n_chunks = n_chunks;
+        D.raw_mode = d->raw_mode; D.has_const = H.has_const; D.icpt_col = H.icpt_col;
+        D.use_maf_t = d->use_maf_t; D.degenerate = H.degenerate ? 1 : 0;
+        D.icpt_shift = H.icpt_shift;
+        D.cond_t = d->condition_value_t; D.eig_t = d->eigenvals_t; D.maf_t = d->maf_t;
+        D.E = (const double *)e->dE.p; D.ormask = (const uint8_t *)e->dMask.p;
+        D.FF0 = (const double *)e->dFF0.p; D.R = (const double *)e->dR.p;
+        D.Rinv = (const double *)e->dRinv.p; D.tq = (const double *)e->dTq.p;
+        e->dominant = "contract_packed_kernel";
+        CK(cudaStreamSynchronize(st));   // host vectors go out of scope
+    } else if (d->model == GT_MODEL_LOGISTIC || d->model == GT_MODEL_COXPH) {
+        rc = gtk::iter_set_design(d, pos, n_file, n_chunks, pitch, (const uint8_t *)e->dMask.p,
+                                  e->dIter, e->T, st, g_err);
+        if (rc) return rc;
+        e->dominant = d->model == GT_MODEL_LOGISTIC ? "logistic_irls_kernel" : "cox_newton_kernel";
+    } else {
+        return fail(GT_E_ARG, "gt_engine_set_design: unknown model %d", d->model);
+    }
+    e->have_design = true;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+static int time_begin(gt_engine *e) {
+    if (!e->timing) return -1;
+    if (e->events_used == e->events.size()) {
+        cudaEvent_t a, b;
+        if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return -1;
+        e->events.emplace_back(a, b);
+    }
+    cudaEventRecord(e->events[e->events_used].first, e->stream);
+    return (int)e->events_used;
+}
+static void time_end(gt_engine *e, int slot) {
+    if (slot < 0) return;
+    cudaEventRecord(e->events[slot].second, e->stream);
+    e->events_used++;
+    e->launches++;
+}
+
+static int e_n_file(const gt_engine *e) { return e->model == GT_MODEL_LINEAR ? e->D.n_file : e->T.n_file; }
+
+static int run_linear(gt_engine *e, const void *geno, int64_t pitch, bool packed, int32_t n_snps,
+                      double *out, int32_t *iout) {
+    const GtDesignDev &D = e->D;
+    const ContractEntry &ce = kContract[e->contract_idx];
+    const int tile = 32 * ce.rows;
+    const int kBatch = 1 << 16;
+    int rc;
+    const int bmax = std::min<int>(n_snps, kBatch);
+    if ((rc = e->dS.reserve((size_t)bmax * D.NCP * 8))) return rc;
+    if ((rc = e->dCounts.reserve((size_t)bmax * 4 * 4))) return rc;
+    CK(cudaFuncSetAttribute((const void *)ce.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ce.smem));
+    gtk::FinishLayout lay = gtk::finish_layout(D.L, D.p, D.I);
+    size_t tab = ((size_t)2 * D.NPROD + 15) & ~(size_t)15;
+    int wpc = 8;
+    while (wpc > 1 && (size_t)wpc * lay.perWarp * 8 + tab > 200 * 1024) wpc >>= 1;
+    size_t fsmem = (size_t)wpc * lay.perWarp * 8 + tab;
+    if (fsmem > 220 * 1024) return fail(GT_E_UNSUPPORTED, "design too wide for the finish kernel (%zu B shared)", fsmem);
+    if (packed) CK(cudaFuncSetAttribute((const void *)gtk::linear_finish_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+    else CK(cudaFuncSetAttribute((const void *)gtk::linear_finish_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+
+    for (int s0 = 0; s0 < n_snps; s0 += kBatch) {
+        int nb = std::min<int>(kBatch, n_snps - s0);
+        double *S = (double *)e->dS.p;
+        int *cnt = (int *)e->dCounts.p;
+        if (packed) {
+            const uint8_t *g = (const uint8_t *)geno + (int64_t)s0 * pitch;
+            int slot = time_begin(e);
+            ce.fn<<<(nb + tile - 1) / tile, gtk::kThreads, ce.smem, e->stream>>>(
+                g, pitch, nb, D.ormask, D.E, D.n_chunks, S, cnt);
+            time_end(e, slot);
+            CK(cudaGetLastError());
+            gtk::linear_finish_kernel<true><<<(nb + wpc - 1) / wpc, wpc * 32, fsmem, e->stream>>>(
+                D, g, pitch, nb, S, cnt, out + s0, iout + s0, (long long)n_snps, wpc);
+            CK(cudaGetLastError());
+        } else {
+            const double *g = (const double *)geno + (int64_t)s0 * pitch;
+            gtk::contract_dosage_kernel<<<(nb + 7) / 8, 256, 0, e->stream>>>(
+                g, pitch, nb, D.n, D.E, D.NCA, D.NCB, D.NC1, D.NC2, S, cnt);
+            CK(cudaGetLastError());
+            gtk::linear_finish_kernel<false><<<(nb + wpc - 1) / wpc, wpc * 32, fsmem, e->stream>>>(
+                D, g, pitch, nb, S, cnt, out + s0, iout + s0, (long long)n_snps, wpc);
+            CK(cudaGetLastError());
+        }
+        e->all_launches += 2;
+    }
+    return 0;
+}
+
+static int run_any(gt_engine *e, const void *geno, int64_t pitch, bool packed, int32_t n_snps,
+                   double *out, int32_t *iout) {
+    if (!e || !e->have_design) return fail(GT_E_STATE, "no design set");
+    if (n_snps < 0 || !out || !iout || (n_snps > 0 && !geno)) return fail(GT_E_ARG, "run: bad arguments");
+    if (n_snps == 0) return 0;
+    CK(cudaSetDevice(e->device));
+    if (packed) {
+        if (pitch % 16 != 0 || pitch < ((int64_t)e_n_file(e) + 3) / 4)
+            return fail(GT_E_ARG, "run: pitch %lld must be a multiple of 16 and >= ceil(n_file/4)", (long long)pitch);
+    }
+    if (e->model == GT_MODEL_LINEAR) return run_linear(e, geno, pitch, packed, n_snps, out, iout);
+    return gtk::iter_run(e->T, e->model, geno, pitch, packed, n_snps, out, iout, e->stream, e->timing,
+                         [&]() { return time_begin(e); }, [&](int s) { time_end(e, s); },
+                         e->all_launches, g_err);
+}
+
+
+int gt_run_packed_dev(gt_engine *e, const uint8_t *packed_dev, int64_t pitch, int32_t n_snps,
+                      double *out_dev, int32_t *iout_dev) {
+    return run_any(e, packed_dev, pitch, true, n_snps, out_dev, iout_dev);
+}
+
+int gt_run_dosage_dev(gt_engine *e, const double *dosage_dev, int64_t ld, int32_t n_snps,
+                      double *out_dev, int32_t *iout_dev) {
+    if (e && e->have_design && ld < (e->model == GT_MODEL_LINEAR ? e->D.n : e->T.n))
+        return fail(GT_E_ARG, "gt_run_dosage: ld (%lld) < n", (long long)ld);
+    return run_any(e, dosage_dev, ld, false, n_snps, out_dev, iout_dev);
+}
+
+static int run_host(gt_engine *e, const void *src, int64_t src_pitch_bytes, int64_t dev_pitch_bytes,
+                    int64_t width_bytes, int64_t dev_pitch_arg, bool packed, int32_t n_snps,
+                    double *out_host, int32_t *iout_host) {
+    if (!e || !e->have_design) return fail(GT_E_STATE, "no design set");
+    if (n_snps <= 0) return n_snps == 0 ? 0 : fail(GT_E_ARG, "n_snps < 0");
+    CK(cudaSetDevice(e->device));
+    int nf = gt_engine_num_fields(e);
+    int rc;
+    if ((rc = e->dGeno.reserve((size_t)dev_pitch_bytes * n_snps))) return rc;
+    if ((rc = e->dOut.reserve((size_t)nf * n_snps * 8))) return rc;
+    if ((rc = e->dIout.reserve((size_t)GT_NUM_IFIELDS * n_snps * 4))) return rc;
+    CK(cudaMemcpy2DAsync(e->dGeno.p, dev_pitch_bytes, src, src_pitch_bytes, width_bytes, n_snps,
+                         cudaMemcpyHostToDevice, e->stream));
+    rc = run_any(e, e->dGeno.p, dev_pitch_arg, packed, n_snps, (double *)e->dOut.p, (int32_t *)e->dIout.p);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out_host, e->dOut.p, (size_t)nf * n_snps * 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(iout_host, e->dIout.p, (size_t)GT_NUM_IFIELDS * n_snps * 4, cudaMemcpyDeviceToHost, e->stream));
+    return gt_engine_synchronize(e);
+}
+
+int gt_run_packed_host(gt_engine *e, const uint8_t *packed_host, int64_t row_bytes, int32_t n_snps,
+                       double *out_host, int32_t *iout_host) {
+    if (!e || !e->have_design) return fail(GT_E_STATE, "no design set");
+    int64_t bps = ((int64_t)e_n_file(e) + 3) / 4;
+    if (row_bytes < bps) return fail(GT_E_ARG, "gt_run_packed_host: row_bytes %lld < ceil(n_file/4)=%lld", (long long)row_bytes, (long long)bps);
+    int64_t pitch = gt_packed_pitch(e_n_file(e));
+    return run_host(e, packed_host, row_bytes, pitch, bps, pitch, true, n_snps, out_host, iout_host);
+}
+
+int gt_run_dosage_host(gt_engine *e, const double *dosage_host, int64_t ld, int32_t n_snps,
+                       double *out_host, int32_t *iout_host) {
+    if (!e || !e->have_design) return fail(GT_E_STATE, "no design set");
+    int n = e->model == GT_MODEL_LINEAR ? e->D.n : e->T.n;
+    if (ld < n) return fail(GT_E_ARG, "gt_run_dosage_host: ld (%lld) < n (%d)", (long long)ld, n);
+    return run_host(e, dosage_host, ld * 8, (int64_t)n * 8, (int64_t)n * 8, n, false, n_snps, out_host, iout_host);
+}
+
+int gt_synth_packed_dev(gt_engine *e, uint8_t *packed_dev, int64_t pitch, int32_t n_file,
+                        int32_t n_snps, uint64_t seed, double maf_lo, double maf_hi,
+                        double missing_rate) {
+    if (!e || !packed_dev) return fail(GT_E_ARG, "gt_synth_packed_dev: NULL argument");
+    if (pitch < ((int64_t)n_file + 3) / 4) return fail(GT_E_ARG, "gt_synth_packed_dev: pitch too small");
+    CK(cudaSetDevice(e->device));
+    CK(cudaMemsetAsync(packed_dev, 0xFF, (size_t)pitch * n_snps, e->stream));
+    synth_packed_kernel<<<148 * 16, 256, 0, e->stream>>>(packed_dev, pitch, n_file, n_snps, seed,
+                                                         maf_lo, maf_hi, missing_rate);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,260 @@
+// Shared device/host helpers for the genetest_b200 kernels (sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/genetest_b200.h"
+
+#define GT_FULL 0xffffffffu
+#define GT_HD __host__ __device__ __forceinline__
+
+// ---------------------------------------------------------------------------
+// Device-resident description of one design (filled by gt_engine_set_design).
+// Base vector of sample i:  v_i = [q_i (k) | y_i | 1 | w_i1 .. w_iI],  L = k+2+I
+//   q = row of the orthonormal factor of the covariates (C = Q R)
+//   y = outcome (centred when the design has an explicit constant column)
+// E row of sample i (file order, NCP doubles):
+//   [ m_c * v_i  for c = 0..I ]  (NC1 = (I+1) L, padded to NCA)   weighted by g
+//   [ m_a * m_b  for a <= b   ]  (NC2 = (I+1)(I+2)/2, padded NCB) weighted by g^2
+//   with multipliers m_0 = 1, m_j = w_ij.
+// ---------------------------------------------------------------------------
+struct GtDesignDev {
+    int n_file;        // samples per packed genotype row
+    int n;             // design rows
+    int k, I, L, p;    // covariates, interactions, base length, parameters
+    int NC1, NC2;      // live contraction columns
+    int NCA, NCB;      // padded column blocks (kernel instantiation)
+    int NCP;           // E row stride = NCA + NCB
+    int NPROD;         // L (L + 1) / 2
+    int n_chunks;      // ceil(n_file / 256)
+    int raw_mode;
+    int has_const;     // design spans a constant (k_constant of statsmodels)
+    int icpt_col;      // explicit constant column of C (or -1)
+    int use_maf_t;
+    int degenerate;    // covariates alone are rank deficient
+    double icpt_shift; // ybar / value of the constant column
+    double cond_t, eig_t, maf_t;
+    const double *E;        // [n_chunks*256][NCP]
+    const uint8_t *ormask;  // [pitch] 2-bit pairs: 11 = sample not in design
+    const double *FF0;      // [L*L]   sum over design rows of v v'
+    const double *R;        // [k*k]   row-major upper triangular
+    const double *Rinv;     // [k*k]
+    const double *tq;       // [n+1]   t.ppf(0.975, df)
+};
+
+// ---------------------------------------------------------------------------
+// Student t / normal tails
+// ---------------------------------------------------------------------------
+GT_HD double gt_stirling_tail(double z) {
+    double z2 = z * z;
+    return (1.0 / 12 - (1.0 / 360 - (1.0 / 1260 - (1.0 / 1680 -
+            (1.0 / 1188) / z2) / z2) / z2) / z2) / z;
+}
+
+// lgamma(a + 1/2) - lgamma(a), without the cancellation of the direct form
+GT_HD double gt_lgamma_half_diff(double a) {
+    if (a < 20.0) return lgamma(a + 0.5) - lgamma(a);
+    return a * log1p(0.5 / a) - 0.5 + 0.5 * log(a) +
+           gt_stirling_tail(a + 0.5) - gt_stirling_tail(a);
+}
+
+// Continued fraction of the incomplete beta function (modified Lentz).
+GT_HD double gt_betacf(double a, double b, double x) {
+    const double tiny = 1e-300;
+    double qab = a + b, qap = a + 1.0, qam = a - 1.0;
+    double c = 1.0, d = 1.0 - qab * x / qap;
+    if (fabs(d) < tiny) d = tiny;
+    d = 1.0 / d;
+    double h = d;
+    for (int m = 1; m <= 500; ++m) {
+        double m2 = 2.0 * m;
+        double aa = m * (b - m) * x / ((qam + m2) * (a + m2));
+        d = 1.0 + aa * d;
+        if (fabs(d) < tiny) d = tiny;
+        c = 1.0 + aa / c;
+        if (fabs(c) < tiny) c = tiny;
+        d = 1.0 / d;
+        h *= d * c;
+        aa = -(a + m) * (qab + m) * x / ((a + m2) * (qap + m2));
+        d = 1.0 + aa * d;
+        if (fabs(d) < tiny) d = tiny;
+        c = 1.0 + aa / c;
+        if (fabs(c) < tiny) c = tiny;
+        d = 1.0 / d;
+        double del = d * c;
+        h *= del;
+        if (fabs(del - 1.0) < 2e-16) break;
+    }
+    return h;
+}
+
+// log of the t density normaliser: -ln( sqrt(df) B(df/2, 1/2) ) + ...
+GT_HD double gt_lbeta_half(double a) {
+    return 0.5 * log(3.14159265358979323846) - gt_lgamma_half_diff(a);
+}
+
+// Two-sided tail 2 * P(T_df > |t|) = I_x(df/2, 1/2), x = df / (df + t^2).
+GT_HD double gt_t_sf2(double t, double df) {
+    if (!(df > 0.0) || t != t) return nan("");
+    double t2 = t * t;
+    if (t2 == 0.0) return 1.0;
+    if (isinf(t2)) return 0.0;
+    double a = 0.5 * df;
+    double lnpre = -gt_lbeta_half(a) - a * log1p(t2 / df) +
+                   0.5 * (log(t2) - log(df + t2));
+    double x = df / (df + t2);
+    if (x < (a + 1.0) / (a + 2.5))
+        return exp(lnpre) * gt_betacf(a, 0.5, x) / a;
+    return 1.0 - exp(lnpre) * gt_betacf(0.5, a, t2 / (df + t2)) / 0.5;
+}
+
+GT_HD double gt_t_pdf(double t, double df) {
+    double a = 0.5 * df;
+    return exp(-gt_lbeta_half(a) - 0.5 * log(df) - (a + 0.5) * log1p(t * t / df));
+}
+
+// t.ppf(0.975, df): Cornish-Fisher start, Newton on the two-sided tail.
+GT_HD double gt_t_ppf975(double df) {
+    if (!(df > 0.0)) return nan("");
+    const double z = 1.959963984540054;
+    double t;
+    if (df < 1.5) t = 12.706204736174694;
+    else if (df < 2.5) t = 4.302652729749464;
+    else {
+        double z3 = z * z * z, z5 = z3 * z * z, z7 = z5 * z * z;
+        t = z + (z3 + z) / (4 * df) + (5 * z5 + 16 * z3 + 3 * z) / (96 * df * df) +
+            (3 * z7 + 19 * z5 + 17 * z3 - 15 * z) / (384 * df * df * df);
+    }
+    for (int it = 0; it < 12; ++it) {
+        double f = gt_t_sf2(t, df) - 0.05;
+        double step = f / (2.0 * gt_t_pdf(t, df));
+        t += step;
+        if (fabs(step) <= 1e-15 * t) break;
+    }
+    return t;
+}
+
+// 2 * Phi(-|z|)
+GT_HD double gt_norm_sf2(double z) {
+    if (z != z) return nan("");
+    return erfc(fabs(z) * 0.70710678118654752440);
+}
+
+#define GT_Z975 1.959963984540054
+
+// ---------------------------------------------------------------------------
+// Warp helpers
+// ---------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ double gt_warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(GT_FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ int gt_warp_sum_int(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(GT_FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ double gt_warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(GT_FULL, v, o));
+    return v;
+}
+
+// In-place lower Cholesky of the p x p matrix A (leading dimension ld) held
+// in shared memory, executed by one warp.  Returns false when a pivot is not
+// positive (relative to the original diagonal).
+__device__ __forceinline__ bool gt_warp_cholesky(double *A, int ld, int p, int lane) {
+    bool ok = true;
+    for (int j = 0; j < p; ++j) {
+        double d = A[j * ld + j];
+        if (!(d > 0.0)) { ok = false; break; }
+        double s = sqrt(d);
+        double inv = 1.0 / s;
+        __syncwarp();
+        for (int i = j + 1 + lane; i < p; i += 32) A[i * ld + j] *= inv;
+        if (lane == 0) A[j * ld + j] = s;
+        __syncwarp();
+        int m = p - j - 1;
+        for (int t = lane; t < m * m; t += 32) {
+            int i = j + 1 + t / m, c = j + 1 + t % m;
+            if (c <= i) A[i * ld + c] -= A[i * ld + j] * A[c * ld + j];
+        }
+        __syncwarp();
+    }
+    return ok;
+}
+
+// X = (L L')^{-1}: lane c solves column c (forward then backward substitution).
+__device__ __forceinline__ void gt_warp_chol_inverse(const double *Lc, int ld, int p,
+                                                     double *X, int lane) {
+    for (int c = lane; c < p; c += 32) {
+        for (int i = 0; i < p; ++i) {
+            double s = (i == c) ? 1.0 : 0.0;
+            for (int j = 0; j < i; ++j) s -= Lc[i * ld + j] * X[j * ld + c];
+            X[i * ld + c] = s / Lc[i * ld + i];
+        }
+        for (int i = p - 1; i >= 0; --i) {
+            double s = X[i * ld + c];
+            for (int j = i + 1; j < p; ++j) s -= Lc[j * ld + i] * X[j * ld + c];
+            X[i * ld + c] = s / Lc[i * ld + i];
+        }
+    }
+    __syncwarp();
+}
+
+// Cyclic Jacobi eigenvalues of the symmetric p x p matrix G (shared memory,
+// destroyed).  Returns (max, min) of the diagonal after convergence.  A zero
+// row/column stays exactly zero (monomorphic marker -> eigenvalue 0 -> inf).
+__device__ __forceinline__ void gt_warp_jacobi_extremes(double *G, int ld, int p, int lane,
+                                                        double *emax, double *emin) {
+    for (int sweep = 0; sweep < 40; ++sweep) {
+        double off = 0.0, dg = 0.0;
+        for (int t = lane; t < p * p; t += 32) {
+            int i = t / p, j = t % p;
+            double v = G[i * ld + j];
+            if (i == j) dg += v * v; else off += v * v;
+        }
+        off = gt_warp_sum(off);
+        dg = gt_warp_sum(dg);
+        if (off <= 1e-32 * dg || off == 0.0) break;
+        for (int r = 0; r < p - 1; ++r) {
+            for (int c = r + 1; c < p; ++c) {
+                double apq = G[r * ld + c];
+                if (apq == 0.0) continue;
+                double app = G[r * ld + r], aqq = G[c * ld + c];
+                double tau = (aqq - app) / (2.0 * apq);
+                double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                double cs = 1.0 / sqrt(1.0 + t * t), sn = t * cs;
+                __syncwarp();
+                for (int i = lane; i < p; i += 32) {
+                    if (i != r && i != c) {
+                        double gir = G[i * ld + r], gic = G[i * ld + c];
+                        double nr = cs * gir - sn * gic, nc = sn * gir + cs * gic;
+                        G[i * ld + r] = nr; G[r * ld + i] = nr;
+                        G[i * ld + c] = nc; G[c * ld + i] = nc;
+                    }
+                }
+                if (lane == 0) {
+                    G[r * ld + r] = app - t * apq;
+                    G[c * ld + c] = aqq + t * apq;
+                    G[r * ld + c] = 0.0;
+                    G[c * ld + r] = 0.0;
+                }
+                __syncwarp();
+            }
+        }
+    }
+    double mx = -INFINITY, mn = INFINITY;
+    for (int i = lane; i < p; i += 32) {
+        double v = G[i * ld + i];
+        mx = fmax(mx, v); mn = fmin(mn, v);
+    }
+    mx = gt_warp_max(mx);
+    mn = -gt_warp_max(-mn);
+    *emax = mx; *emin = mn;
+}
+#endif  // __CUDACC__

@@ -1,0 +1,372 @@
+// K3: per-SNP masked normal-equation finish of the linear model, one warp per
+// SNP.  Restates what sm.OLS(y, X).fit() + StatsLinear._results_handler
+// (genetest/statistics/models/linear.py:46-104) compute for the complete
+// cases of each marker (analysis.py:119,172), after _gwas_worker's MAF /
+// flip / interaction steps (analysis.py:127-166):
+//   * re-scan the marker's row for missing samples and subtract their
+//     v v' contributions from the full-sample Gram matrix (exact
+//     complete-case sums),
+//   * MAF on the complete cases, flip (g -> 2 - g) applied algebraically,
+//   * p x p normal equations in the orthonormal covariate basis (Cholesky),
+//     mapped back through R^-1 to the reference's parameterisation,
+//   * condition-number / eigenvalue gates (certified trace bound first,
+//     Jacobi eigenvalues only when the bound cannot decide),
+//   * t statistics, two-sided p-values, 95 % CI, adjusted R^2, log-lik.
+#pragma once
+
+#include "gt_common.cuh"
+
+namespace gtk {
+
+struct FinishLayout {
+    int perWarp;   // doubles per warp
+    int oS0, oMo, oMc, oMi, oStage, oVec, oQueue;
+    int queueInts;
+};
+
+__host__ __device__ inline FinishLayout finish_layout(int L, int p, int I) {
+    FinishLayout f;
+    int o = 0;
+    f.oS0 = o; o += L * L;
+    f.oMo = o; o += p * p;
+    f.oMc = o; o += p * p;
+    f.oMi = o; o += p * p;
+    f.oStage = o; o += 32 * L;
+    f.oVec = o; o += 6 * p + (I + 1) * L + (I + 1) * (I + 1) + 8;
+    f.oQueue = o;
+    f.queueInts = 32 + 512 + 32;
+    o += (f.queueInts + 1) / 2;
+    f.perWarp = (o + 1) & ~1;
+    return f;
+}
+
+__device__ __forceinline__ void finish_write_fail(double *out, int *iout, long long n_snps, int snp,
+                                                  int nf, int status, int nobs, int flip,
+                                                  double maf, double aux, int lane) {
+    for (int f = lane; f < nf; f += 32) {
+        double v = nan("");
+        if (f == GT_F_MAF) v = maf;
+        if (f == GT_F_AUX) v = aux;
+        out[(long long)f * n_snps + snp] = v;
+    }
+    if (lane == 0) {
+        iout[(long long)GT_I_STATUS * n_snps + snp] = status;
+        iout[(long long)GT_I_NOBS * n_snps + snp] = nobs;
+        iout[(long long)GT_I_FLIP * n_snps + snp] = flip;
+        iout[(long long)GT_I_NITER * n_snps + snp] = 0;
+    }
+}
+
+// Subtract sum over the missing samples of v v' from S0 (one warp).
+// PACKED: row = 2-bit codes OR-ed with the design mask; else doubles with NaN.
+template <bool PACKED>
+__device__ __forceinline__ void subtract_missing(const GtDesignDev &D, const void *rowp,
+                                                 double *S0, double *stage, int *queue,
+                                                 const unsigned char *pa, const unsigned char *pb,
+                                                 int lane) {
+    const int L = D.L;
+    int qn = 0;
+    auto process = [&](const int *q, int count) {
+        int idx = (lane < count) ? q[lane] : -1;
+        for (int c = 0; c < L; ++c)
+            stage[lane * L + c] = (idx >= 0) ? D.E[(long long)idx * D.NCP + c] : 0.0;
+        __syncwarp();
+        for (int t = lane; t < D.NPROD; t += 32) {
+            int a = pa[t], b = pb[t];
+            double acc = 0.0;
+#pragma unroll 8
+            for (int e = 0; e < 32; ++e) acc = fma(stage[e * L + a], stage[e * L + b], acc);
+            S0[a * L + b] -= acc;
+            if (a != b) S0[b * L + a] -= acc;
+        }
+        __syncwarp();
+    };
+    auto drain = [&]() {
+        int head = 0;
+        while (qn - head >= 32) { process(queue + head, 32); head += 32; }
+        if (head > 0) {
+            int v = (lane < qn - head) ? queue[head + lane] : 0;
+            __syncwarp();
+            if (lane < qn - head) queue[lane] = v;
+            qn -= head;
+            __syncwarp();
+        }
+    };
+    const int nblocks = PACKED ? ((D.n_file + 15) / 16 + 31) / 32 : (D.n + 31) / 32;
+    for (int blk = 0; blk < nblocks; ++blk) {
+        int c;
+        uint32_t miss = 0;
+        int first = 0;
+        if (PACKED) {
+            int wi = blk * 32 + lane;
+            uint32_t w = 0xFFFFFFFFu;
+            if (wi < (D.n_file + 15) / 16)
+                w = ((const uint32_t *)rowp)[wi] | ((const uint32_t *)D.ormask)[wi];
+            miss = w & ~(w >> 1) & 0x55555555u;
+            c = __popc(miss);
+            first = wi * 16;
+        } else {
+            int i = blk * 32 + lane;
+            double g = (i < D.n) ? ((const double *)rowp)[i] : 0.0;
+            c = (g != g) ? 1 : 0;
+            first = i;
+        }
+        unsigned any = __ballot_sync(GT_FULL, c > 0);
+        if (!any) continue;
+        int off = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(GT_FULL, off, o);
+            if (lane >= o) off += t;
+        }
+        int total = __shfl_sync(GT_FULL, off, 31);
+        off -= c;
+        if (PACKED) {
+            while (miss) {
+                int b = __ffs(miss) - 1;
+                queue[qn + off++] = first + (b >> 1);
+                miss &= miss - 1;
+            }
+        } else if (c) {
+            queue[qn + off] = first;
+        }
+        qn += total;
+        __syncwarp();
+        drain();
+    }
+    if (qn > 0) process(queue, qn);
+}
+
+template <bool PACKED>
+__global__ void __launch_bounds__(256)
+linear_finish_kernel(GtDesignDev D, const void *__restrict__ geno, long long pitch, int n_snps,
+                     const double *__restrict__ S, const int *__restrict__ counts,
+                     double *__restrict__ out, int *__restrict__ iout, long long ostride,
+                     int wpc) {
+    extern __shared__ __align__(16) double sm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int k = D.k, I = D.I, L = D.L, p = D.p;
+    const int iy = k, i1 = k + 1;
+    const int nf = GT_F_PARAM0 + 6 * p;
+    const FinishLayout lay = finish_layout(L, p, I);
+
+    // product index table (shared by the CTA)
+    unsigned char *pa = (unsigned char *)(sm + (size_t)wpc * lay.perWarp);
+    unsigned char *pb = pa + D.NPROD;
+    for (int a = threadIdx.x; a < L; a += blockDim.x) {
+        int base = a * L - a * (a - 1) / 2;   // products (a, a..L-1)
+        for (int b = a; b < L; ++b) { pa[base + b - a] = (unsigned char)a; pb[base + b - a] = (unsigned char)b; }
+    }
+    __syncthreads();
+
+    const int snp = blockIdx.x * wpc + warp;
+    if (warp >= wpc || snp >= n_snps) return;
+
+    double *W = sm + (size_t)warp * lay.perWarp;
+    double *S0 = W + lay.oS0, *Mo = W + lay.oMo, *Mc = W + lay.oMc, *Mi = W + lay.oMi;
+    double *stage = W + lay.oStage;
+    double *rhs = W + lay.oVec, *bq = rhs + p, *beta = bq + p, *var = beta + p,
+           *gdiag = var + p, *tmpv = gdiag + p;
+    double *S1 = tmpv + p;                  // [(I+1)][L]
+    double *S2 = S1 + (I + 1) * L;          // [(I+1)][(I+1)]
+    int *queue = (int *)(W + lay.oQueue);
+
+    for (int t = lane; t < L * L; t += 32) S0[t] = D.FF0[t];
+    __syncwarp();
+
+    const int n_het = counts[(long long)snp * 4 + 0];
+    const int n_hom = counts[(long long)snp * 4 + 1];
+    const int n_miss = counts[(long long)snp * 4 + 2];
+    if (n_miss > 0) {
+        const void *rowp = PACKED ? (const void *)((const uint8_t *)geno + (long long)snp * pitch)
+                                  : (const void *)((const double *)geno + (long long)snp * pitch);
+        subtract_missing<PACKED>(D, rowp, S0, stage, queue, pa, pb, lane);
+    }
+    __syncwarp();
+
+    const double *Ssnp = S + (long long)snp * D.NCP;
+    for (int t = lane; t < (I + 1) * L; t += 32) S1[t] = Ssnp[t];
+    for (int t = lane; t < (I + 1) * (I + 1); t += 32) {
+        int a = t / (I + 1), b = t % (I + 1);
+        int lo = a < b ? a : b, hi = a < b ? b : a;
+        int idx = lo * (I + 1) - lo * (lo - 1) / 2 + (hi - lo);
+        S2[t] = Ssnp[D.NCA + idx];
+    }
+    __syncwarp();
+
+    const int nj = D.n - n_miss;
+    if (nj <= 0) {
+        finish_write_fail(out, iout, ostride, snp, nf, GT_ALL_MISSING, 0, 0, nan(""), nan(""), lane);
+        return;
+    }
+    // MAF on the complete cases (descriptive.py:43): nanmean(g) / 2
+    double maf = nan("");
+    int flip = 0;
+    if (!D.raw_mode) {
+        double sum_g = PACKED ? (double)(n_het + 2 * n_hom) : S1[i1];
+        maf = (sum_g / (double)nj) / 2.0;
+        if (maf > 0.5) { maf = 1.0 - maf; flip = 1; }
+        if (D.use_maf_t && maf < D.maf_t) {
+            finish_write_fail(out, iout, ostride, snp, nf, GT_MAF_BELOW, nj, flip, maf, maf, lane);
+            return;
+        }
+    }
+    if (flip) {   // g -> 2 - g on the complete cases (analysis.py:156-157)
+        for (int t = lane; t < (I + 1) * (I + 1); t += 32) {
+            int a = t / (I + 1), b = t % (I + 1);
+            int ca = a == 0 ? i1 : k + 1 + a, cb = b == 0 ? i1 : k + 1 + b;
+            stage[t] = 4.0 * S0[ca * L + cb] - 4.0 * S1[a * L + cb] + S2[t];
+        }
+        __syncwarp();
+        bool all_zero = (stage[0] == 0.0);
+        for (int t = lane; t < (I + 1) * L; t += 32) {
+            int c = t / L, b = t % L;
+            int cc = c == 0 ? i1 : k + 1 + c;
+            S1[t] = all_zero ? 0.0 : 2.0 * S0[cc * L + b] - S1[t];
+        }
+        __syncwarp();
+        for (int t = lane; t < (I + 1) * (I + 1); t += 32) S2[t] = all_zero ? 0.0 : stage[t];
+        __syncwarp();
+    }
+
+    // normal equations in the [Q | g | g w] basis
+    for (int t = lane; t < p * p; t += 32) {
+        int i = t / p, j = t % p;
+        double v;
+        if (i < k && j < k) v = S0[i * L + j];
+        else if (i < k) v = S1[(j - k) * L + i];
+        else if (j < k) v = S1[(i - k) * L + j];
+        else v = S2[(i - k) * (I + 1) + (j - k)];
+        Mo[t] = v; Mc[t] = v;
+    }
+    for (int i = lane; i < p; i += 32) rhs[i] = (i < k) ? S0[i * L + iy] : S1[(i - k) * L + iy];
+    const double yy = S0[iy * L + iy], sy = S0[iy * L + i1];
+    __syncwarp();
+
+    bool chol_ok = !D.degenerate && gt_warp_cholesky(Mc, p, p, lane);
+    bool need_jacobi = !chol_ok;
+    double ssr = 0.0;
+    if (chol_ok) {
+        gt_warp_chol_inverse(Mc, p, p, Mi, lane);
+        for (int i = lane; i < p; i += 32) {
+            double s = 0.0;
+            for (int j = 0; j < p; ++j) s = fma(Mi[i * p + j], rhs[j], s);
+            bq[i] = s;
+        }
+        __syncwarp();
+        double part = 0.0;
+        for (int i = lane; i < p; i += 32) part = fma(rhs[i], bq[i], part);
+        ssr = yy - gt_warp_sum(part);
+        // back to the reference's parameterisation: beta = T bq, cov = T Mi T'
+        for (int i = lane; i < p; i += 32) {
+            double b = 0.0, v = 0.0, gd = 0.0;
+            if (i < k) {
+                for (int a = i; a < k; ++a) {
+                    double ria = D.Rinv[i * k + a];
+                    b = fma(ria, bq[a], b);
+                    double s = 0.0;
+                    for (int c = i; c < k; ++c) s = fma(Mi[a * p + c], D.Rinv[i * k + c], s);
+                    v = fma(ria, s, v);
+                }
+                for (int a = 0; a <= i; ++a) {
+                    double rai = D.R[a * k + i];
+                    double s = 0.0;
+                    for (int c = 0; c <= i; ++c) s = fma(Mo[a * p + c], D.R[c * k + i], s);
+                    gd = fma(rai, s, gd);
+                }
+            } else {
+                b = bq[i]; v = Mi[i * p + i]; gd = Mo[i * p + i];
+            }
+            beta[i] = b; var[i] = v; gdiag[i] = gd;
+        }
+        __syncwarp();
+        double tv = 0.0, tg = 0.0;
+        for (int i = lane; i < p; i += 32) { tv += var[i]; tg += gdiag[i]; }
+        tv = gt_warp_sum(tv); tg = gt_warp_sum(tg);
+        // cond^2 <= trace(G) trace(G^-1),  lambda_min >= 1 / trace(G^-1)
+        bool cond_safe = tg * tv <= D.cond_t * D.cond_t * (1.0 - 1e-9);
+        bool eig_safe = 1.0 / tv >= D.eig_t * (1.0 + 1e-9);
+        need_jacobi = !(cond_safe && eig_safe);
+    }
+    if (need_jacobi) {
+        // G = Ti' Mo Ti with Ti = blockdiag(R, I): Gram matrix of the original columns
+        double *tmp = stage, *G = S0;
+        for (int t = lane; t < p * p; t += 32) {
+            int i = t / p, j = t % p;
+            double s;
+            if (j < k) { s = 0.0; for (int a = 0; a <= j; ++a) s = fma(Mo[i * p + a], D.R[a * k + j], s); }
+            else s = Mo[i * p + j];
+            tmp[t] = s;
+        }
+        __syncwarp();
+        for (int t = lane; t < p * p; t += 32) {
+            int i = t / p, j = t % p;
+            double s;
+            if (i < k) { s = 0.0; for (int a = 0; a <= i; ++a) s = fma(D.R[a * k + i], tmp[a * p + j], s); }
+            else s = tmp[i * p + j];
+            G[i * p + j] = s;
+        }
+        __syncwarp();
+        // symmetrise (rounding) so a zero column stays exactly zero on both sides
+        for (int t = lane; t < p * p; t += 32) {
+            int i = t / p, j = t % p;
+            if (i < j) { double v = G[j * p + i]; G[i * p + j] = v; }
+        }
+        __syncwarp();
+        double emax, emin;
+        gt_warp_jacobi_extremes(G, p, p, lane, &emax, &emin);
+        double cond = (emin > 0.0) ? sqrt(emax / emin) : INFINITY;
+        if (D.degenerate) cond = INFINITY;
+        if (cond > D.cond_t) {
+            finish_write_fail(out, iout, ostride, snp, nf, GT_COND_LARGE, nj, flip, maf, cond, lane);
+            return;
+        }
+        if (emin < D.eig_t) {
+            finish_write_fail(out, iout, ostride, snp, nf, GT_EIG_SMALL, nj, flip, maf, emin, lane);
+            return;
+        }
+        if (!chol_ok) {
+            finish_write_fail(out, iout, ostride, snp, nf, GT_COND_LARGE, nj, flip, maf, INFINITY, lane);
+            return;
+        }
+    }
+
+    const int df = nj - p;
+    const double scale = (df > 0) ? ssr / (double)df : nan("");
+    const double q975 = (df > 0) ? D.tq[df] : nan("");
+    double pv_snp = 0.0;
+    double my[6];
+    for (int j = lane; j < p; j += 32) {
+        double coef = beta[j] + ((j == D.icpt_col) ? D.icpt_shift : 0.0);
+        double se = sqrt(scale * var[j]);
+        double tval = coef / se;
+        double pval = (df > 0) ? gt_t_sf2(tval, (double)df) : nan("");
+        my[0] = coef; my[1] = se; my[2] = coef - q975 * se; my[3] = coef + q975 * se;
+        my[4] = tval; my[5] = pval;
+#pragma unroll
+        for (int f = 0; f < 6; ++f)
+            out[(long long)(GT_F_PARAM0 + 6 * j + f) * ostride + snp] = my[f];
+        if (j == k) pv_snp = pval;
+    }
+    pv_snp = __shfl_sync(GT_FULL, pv_snp, k & 31);
+    int status = GT_OK;
+    if (!D.raw_mode && pv_snp != pv_snp) status = GT_NAN_PVALUE;
+    if (lane == 0) {
+        double dn = (double)nj;
+        double tss = D.has_const ? (yy - sy * sy / dn) : yy;
+        double r2 = 1.0 - ssr / tss;
+        double r2a = 1.0 - ((dn - (double)D.has_const) / (double)df) * (1.0 - r2);
+        double llf = -0.5 * dn * log(2.0 * 3.14159265358979323846) -
+                     0.5 * dn * log(ssr / dn) - 0.5 * dn;
+        out[(long long)GT_F_MAF * ostride + snp] = maf;
+        out[(long long)GT_F_AUX * ostride + snp] = nan("");
+        out[(long long)GT_F_STAT * ostride + snp] = r2a;
+        out[(long long)GT_F_LLF * ostride + snp] = llf;
+        iout[(long long)GT_I_STATUS * ostride + snp] = status;
+        iout[(long long)GT_I_NOBS * ostride + snp] = nj;
+        iout[(long long)GT_I_FLIP * ostride + snp] = flip;
+        iout[(long long)GT_I_NITER * ostride + snp] = need_jacobi ? 1 : 0;
+    }
+}
+
+}  // namespace gtk

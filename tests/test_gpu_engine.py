@@ -1,0 +1,252 @@
+"""GPU parity tests of the C-ABI engine against the CPU oracle.
+
+Everything here calls ``libgenetest_b200.so`` through ctypes (the drop-in
+boundary) and compares with ``oracle/`` on the same seeded inputs.
+Tolerances: linear 1e-8, logistic 1e-6 (BASELINE.json north_star);
+indices / nobs / flip / MAF / status bit-exact.
+"""
+
+import numpy as np
+import pytest
+
+from genetest_b200.genotypes import pack_rows, unpack_rows
+
+from gpu_support import (compare, run_oracle, synth_design, synth_genotypes)
+
+pytestmark = pytest.mark.gpu
+
+LIN_TOL = 1e-8
+LOGIT_TOL = 1e-6
+
+
+@pytest.fixture(scope="module")
+def engine():
+    from genetest_b200.engine import Engine
+    eng = Engine(0)
+    yield eng
+    eng.close()
+
+
+def _linear_y(rng, C, G=None):
+    y = 0.1 * C[:, 0] + rng.normal(size=C.shape[0]) + 3.0
+    if G is not None:
+        g = np.nan_to_num(G[0])
+        y = y + 0.05 * g
+    return y
+
+
+def test_linear_config1_packed(engine):
+    """BASELINE config 1: 1,000 SNPs x 1,000 samples, age + sex."""
+    rng = np.random.default_rng(20261019)
+    n, n_snps = 1000, 1000
+    C, names = synth_design(rng, n)
+    G = synth_genotypes(rng, n_snps, n)
+    y = _linear_y(rng, C, G)
+    engine.set_design("linear", y, C)
+    res = engine.run_packed_host(pack_rows(G))
+    oracle = run_oracle("linear", y[:, None], C, names, G)
+    problems, worst, n_ok = compare("linear", res, oracle, names, rtol=LIN_TOL)
+    assert not problems, problems[:10]
+    assert n_ok == n_snps
+    print("linear config1 worst rel err", worst)
+
+
+def test_linear_missing_subset_permuted(engine):
+    """1 % missing, samples a permuted subset of the genotype file, edge
+    markers: monomorphic, all-missing, MAF > 0.5 (flip), MAF threshold."""
+    rng = np.random.default_rng(7)
+    n_file, n, n_snps = 1003, 901, 300
+    C, names = synth_design(rng, n, k_extra=3)
+    pos = rng.permutation(n_file)[:n].astype(np.int32)
+    Gfile = synth_genotypes(rng, n_snps, n_file, missing=0.02, maf_lo=0.02,
+                            maf_hi=0.98)
+    Gfile[0] = 0.0                      # monomorphic -> cond inf
+    Gfile[1] = np.nan                   # all missing
+    Gfile[2] = 2.0                      # monomorphic after flip
+    Gfile[3] = 1.0                      # all heterozygous: collinear with 1
+    Gfile[4, pos] = np.nan              # missing for every design sample
+    Gfile[5] = 0.0
+    Gfile[5, pos[:3]] = 1.0             # MAF below threshold
+    y = _linear_y(rng, C)
+    G = Gfile[:, pos]
+    engine.set_design("linear", y, C, sample_pos=pos, n_file=n_file)
+    res = engine.run_packed_host(pack_rows(Gfile))
+    oracle = run_oracle("linear", y[:, None], C, names, G)
+    problems, worst, n_ok = compare("linear", res, oracle, names, rtol=LIN_TOL)
+    assert not problems, problems[:10]
+    assert res.status[0] == 3 and np.isinf(res.aux[0])
+    assert res.status[1] == 1 and res.status[4] == 1
+    assert res.status[2] == 3 and np.isinf(res.aux[2])
+    assert res.status[3] == 3
+    assert n_ok > 250
+    print("linear missing/subset worst rel err", worst)
+    # same batch with a MAF threshold (analysis.py:151-153)
+    engine.set_design("linear", y, C, sample_pos=pos, n_file=n_file,
+                      maf_t=0.01)
+    res = engine.run_packed_host(pack_rows(Gfile))
+    oracle = run_oracle("linear", y[:, None], C, names, G, maf_t=0.01)
+    problems, worst, n_ok = compare("linear", res, oracle, names, rtol=LIN_TOL)
+    assert not problems, problems[:10]
+    assert res.status[5] == 2 and res.status[0] == 2
+
+
+def test_linear_device_resident_matches_host_path(engine):
+    import torch
+    rng = np.random.default_rng(11)
+    n, n_snps = 777, 130
+    C, names = synth_design(rng, n, k_extra=8)
+    G = synth_genotypes(rng, n_snps, n, missing=0.01)
+    y = _linear_y(rng, C)
+    engine.set_design("linear", y, C)
+    host = engine.run_packed_host(pack_rows(G))
+    pitch = engine.packed_pitch()
+    buf = np.zeros((n_snps, pitch), dtype=np.uint8)
+    packed = pack_rows(G)
+    buf[:, :packed.shape[1]] = packed
+    dev = torch.from_numpy(buf).cuda()
+    out, iout = engine.run_packed_dev(dev, n_snps)
+    res = engine.fetch(out, iout)
+    np.testing.assert_array_equal(res.iout, host.iout)
+    np.testing.assert_array_equal(np.nan_to_num(res.out),
+                                  np.nan_to_num(host.out))
+    oracle = run_oracle("linear", y[:, None], C, names, G)
+    problems, worst, _ = compare("linear", res, oracle, names, rtol=LIN_TOL)
+    assert not problems, problems[:10]
+
+
+@pytest.mark.parametrize("n_inter", [1, 2])
+def test_linear_interaction(engine, n_inter):
+    """SNP x covariate interaction columns (analysis.py:159-166)."""
+    rng = np.random.default_rng(100 + n_inter)
+    n, n_snps = 1500, 120
+    C, names = synth_design(rng, n, k_extra=2)
+    G = synth_genotypes(rng, n_snps, n, missing=0.01, maf_lo=0.05,
+                        maf_hi=0.95)
+    y = _linear_y(rng, C)
+    inter = {"I:age": ["age"]}
+    W = [C[:, 0]]
+    if n_inter == 2:
+        inter["I:sexc0"] = ["sex", "c0"]
+        W.append(C[:, 1] * C[:, 2])
+    engine.set_design("linear", y, C, W=np.column_stack(W),
+                      condition_value_t=1e6)
+    res = engine.run_packed_host(pack_rows(G))
+    oracle = run_oracle("linear", y[:, None], C, names, G, interaction=inter,
+                        model_kwargs={"condition_value_t": 1e6})
+    problems, worst, n_ok = compare("linear", res, oracle, names,
+                                    inter_keys=list(inter), rtol=LIN_TOL)
+    assert not problems, problems[:10]
+    assert n_ok == n_snps
+    print("linear interaction", n_inter, "worst rel err", worst)
+
+
+def test_linear_dosage(engine):
+    """Real-valued dosages with NaN (impute2 / bgen / dataframe readers)."""
+    rng = np.random.default_rng(5)
+    n, n_snps = 400, 64
+    C, names = synth_design(rng, n, k_extra=1)
+    G = np.clip(synth_genotypes(rng, n_snps, n) +
+                rng.normal(0, 0.05, (n_snps, n)), 0, 2)
+    G[rng.random(G.shape) < 0.03] = np.nan
+    y = _linear_y(rng, C)
+    engine.set_design("linear", y, C)
+    res = engine.run_dosage_host(G)
+    oracle = run_oracle("linear", y[:, None], C, names, G)
+    # dosage MAF is a float sum: compare to 1e-14, not bit-exact
+    for j, (st, o) in enumerate(oracle):
+        assert st == "ok"
+        assert abs(res.maf[j] - o["SNPs"]["maf"]) < 1e-14
+        o["SNPs"]["maf"] = res.maf[j]
+    problems, worst, n_ok = compare("linear", res, oracle, names, rtol=LIN_TOL)
+    assert not problems, problems[:10]
+
+
+def test_linear_condition_gate_uses_jacobi(engine):
+    """Raw age gives cond ~ 700.  A gate just above the largest condition
+    number cannot be decided by the trace bound -> Jacobi eigenvalues, every
+    marker passes; a gate just below the smallest makes every marker fail
+    with the reference's message and value (linear.py:50-53)."""
+    from oracle import sm_port
+    rng = np.random.default_rng(3)
+    n, n_snps = 600, 40
+    C, names = synth_design(rng, n, standardise=False)
+    G = synth_genotypes(rng, n_snps, n, missing=0.01)
+    y = _linear_y(rng, C)
+    conds = []
+    for j in range(n_snps):
+        ok = ~np.isnan(G[j])
+        conds.append(sm_port.ols_pinv(
+            y[ok], np.column_stack((C[ok], G[j, ok])))["condition_number"])
+    conds = np.array(conds)
+    hi = float(conds.max() * 1.01)
+    engine.set_design("linear", y, C, condition_value_t=hi)
+    res = engine.run_packed_host(pack_rows(G))
+    oracle = run_oracle("linear", y[:, None], C, names, G,
+                        model_kwargs={"condition_value_t": hi})
+    problems, worst, n_ok = compare("linear", res, oracle, names, rtol=LIN_TOL)
+    assert not problems, problems[:10]
+    assert n_ok == n_snps and res.niter.min() == 1    # Jacobi path taken
+    lo = float(conds.min() * 0.99)
+    engine.set_design("linear", y, C, condition_value_t=lo)
+    res = engine.run_packed_host(pack_rows(G))
+    assert (res.status == 3).all()
+    np.testing.assert_allclose(res.aux, conds, rtol=1e-9)
+
+
+def test_logistic_packed(engine):
+    rng = np.random.default_rng(21)
+    n, n_snps = 2000, 200
+    C, names = synth_design(rng, n, k_extra=4)
+    G = synth_genotypes(rng, n_snps, n, missing=0.01, maf_lo=0.05,
+                        maf_hi=0.95)
+    eta = -0.5 + 0.2 * C[:, 0] + 0.3 * np.nan_to_num(G[0])
+    y = (rng.random(n) < 1 / (1 + np.exp(-eta))).astype(float)
+    engine.set_design("logistic", y, C)
+    res = engine.run_packed_host(pack_rows(G))
+    oracle = run_oracle("logistic", y[:, None], C, names, G)
+    problems, worst, n_ok = compare("logistic", res, oracle, names,
+                                    rtol=LOGIT_TOL)
+    assert not problems, problems[:10]
+    assert n_ok == n_snps
+    print("logistic worst rel err", worst)
+
+
+def test_logistic_interaction_subset_and_separation(engine):
+    rng = np.random.default_rng(22)
+    n_file, n, n_snps = 1200, 1000, 60
+    C, names = synth_design(rng, n, k_extra=1)
+    pos = np.sort(rng.permutation(n_file)[:n]).astype(np.int32)
+    Gfile = synth_genotypes(rng, n_snps, n_file, missing=0.02)
+    eta = -0.3 + 0.4 * C[:, 0]
+    y = (rng.random(n) < 1 / (1 + np.exp(-eta))).astype(float)
+    # marker 0 separates the outcome perfectly; marker 1 is monomorphic
+    Gfile[0, pos] = 2.0 * y
+    Gfile[1] = 0.0
+    inter = {"I:age": ["age"]}
+    engine.set_design("logistic", y, C, W=C[:, [0]], sample_pos=pos,
+                      n_file=n_file)
+    res = engine.run_packed_host(pack_rows(Gfile))
+    G = Gfile[:, pos]
+    oracle = run_oracle("logistic", y[:, None], C, names, G, interaction=inter)
+    problems, worst, n_ok = compare("logistic", res, oracle, names,
+                                    inter_keys=list(inter), rtol=LOGIT_TOL)
+    assert not problems, problems[:10]
+    assert res.status[0] == 6
+    print("logistic interaction worst rel err", worst, "ok", n_ok)
+
+
+def test_synthetic_generator_roundtrip(engine):
+    """The device-side .bed generator: decoded rows feed the oracle."""
+    rng = np.random.default_rng(9)
+    n, n_snps = 515, 96
+    C, names = synth_design(rng, n, k_extra=2)
+    y = _linear_y(rng, C)
+    engine.set_design("linear", y, C)
+    dev = engine.synth_packed(n, n_snps, seed=123, missing_rate=0.01)
+    out, iout = engine.run_packed_dev(dev, n_snps)
+    res = engine.fetch(out, iout)
+    G = unpack_rows(dev.cpu().numpy()[:, :(n + 3) // 4], n)
+    assert 0.002 < np.isnan(G).mean() < 0.03
+    oracle = run_oracle("linear", y[:, None], C, names, G)
+    problems, worst, n_ok = compare("linear", res, oracle, names, rtol=LIN_TOL)
+    assert not problems, problems[:10]
