@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""Benchmark of the per-SNP association hot path (SNP-tests/s).
+
+    python bench.py --gpus N --steps K --warmup W [--model linear|logistic]
+    python bench.py --impl reference ...      # CPU restatement of the reference
+
+One step = one pass of the hot path over one shard of synthetic PLINK rows
+that are already resident in HBM (SURVEY.md section 8d: BASELINE config 2 for
+``linear`` -- 100,000 samples, 10 covariates + intercept, 1 % missing
+genotypes, 500,000 SNPs per GPU by default; config 3 for ``logistic``).
+Under torchrun every rank owns its own SNP shard (weak scaling, no data-path
+collective) and rank 0 gathers the fixed-size result blocks over NCCL.
+Prints ONE JSON line on rank 0.
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 20261019
+WORKLOADS = {
+    # model: (samples, covariates w/o intercept, SNPs per GPU per step, missing)
+    "linear": dict(n=100000, k_cov=10, snps=500000, missing=0.01,
+                   name="config2: linear GWAS 500k SNPs x 100k samples, 10 "
+                        "covariates + intercept, 1% missing genotypes"),
+    "logistic": dict(n=50000, k_cov=10, snps=20000, missing=0.0,
+                     name="config3: logistic GWAS 50k samples, 10 covariates "
+                          "+ intercept (batched IRLS), SNP shard per step"),
+}
+
+
+def make_design(model, n, k_cov, rng):
+    """SURVEY.md 8(d): age ~ N(50,10) standardised, sex ~ Bernoulli(.5),
+    remaining covariates iid N(0,1), intercept last."""
+    age = rng.normal(50, 10, n)
+    age = (age - age.mean()) / age.std()
+    sex = rng.integers(0, 2, n).astype(float)
+    cols = [age, sex] + [rng.normal(size=n) for _ in range(k_cov - 2)]
+    C = np.column_stack(cols + [np.ones(n)])
+    names = ["age", "sex"] + ["c{}".format(i) for i in range(k_cov - 2)]
+    names.append("intercept")
+    if model == "linear":
+        y = 0.1 * age + rng.normal(size=n)
+    else:
+        y = (rng.random(n) < 1 / (1 + np.exp(0.5 - 0.2 * age))).astype(float)
+    return y, C, names
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,"
+         "clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm, smax, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                 "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                smax = max(smax, float(r[2]))
+                for nm, v in zip(names, r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except (ValueError, IndexError):
+                continue
+        # samples under load: the upper half of the observed clocks
+        sm.sort()
+        load = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": float(np.median(load)) if load else None,
+                "sm_max_mhz": smax or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------
+# CPU arm: the oracle (restated reference path) on the host cores
+# --------------------------------------------------------------------------
+_CPU = {}
+
+
+def _cpu_init(model, y, C, names):
+    os.environ["OMP_NUM_THREADS"] = "1"
+    os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    os.environ["MKL_NUM_THREADS"] = "1"
+    try:
+        from threadpoolctl import threadpool_limits
+        _CPU["limit"] = threadpool_limits(1)
+    except Exception:
+        pass
+    from oracle import gwas as og
+    _CPU.update(model=model, y=y, C=C, names=names, og=og)
+
+
+def _cpu_work(args):
+    seed, count = args
+    og = _CPU["og"]
+    rng = np.random.default_rng(seed)
+    n = _CPU["C"].shape[0]
+    done = 0
+    for _ in range(count):
+        maf = rng.uniform(0.05, 0.5)
+        g = rng.binomial(2, maf, n).astype(float)
+        g[rng.random(n) < 0.01] = np.nan
+        og.gwas_one(_CPU["model"], _CPU["y"][:, None], _CPU["C"],
+                    _CPU["names"], g)
+        done += 1
+    return done
+
+
+def cpu_throughput(model, y, C, names, n_snps, cores, pool=None):
+    """SNP-tests/s of the restated reference path on ``cores`` processes."""
+    import multiprocessing as mp
+    own = pool is None
+    if own:
+        pool = mp.get_context("spawn").Pool(cores, _cpu_init,
+                                           (model, y, C, names))
+    per = max(1, n_snps // cores)
+    jobs = [(SEED + 17 * i, per) for i in range(cores)]
+    t0 = time.perf_counter()
+    done = sum(pool.map(_cpu_work, jobs))
+    dt = time.perf_counter() - t0
+    if own:
+        pool.close()
+    return done / dt, done, dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    w = WORKLOADS[args.model]
+    rng = np.random.default_rng(SEED)
+    y, C, names = make_design(args.model, w["n"], w["k_cov"], rng)
+    cores = os.cpu_count() or 1
+    per_step = args.ref_snps or (cores * (48 if args.model == "linear" else 12))
+    import multiprocessing as mp
+    pool = mp.get_context("spawn").Pool(cores, _cpu_init,
+                                       (args.model, y, C, names))
+    for _ in range(args.warmup):
+        cpu_throughput(args.model, y, C, names, max(cores, per_step // 4),
+                       cores, pool)
+    t0 = time.perf_counter()
+    total = 0
+    for _ in range(args.steps):
+        _, done, _ = cpu_throughput(args.model, y, C, names, per_step, cores,
+                                    pool)
+        total += done
+    dt = time.perf_counter() - t0
+    pool.close()
+    value = total / dt
+    sample = ("{} SNPs per step of the same synthetic workload, oracle port "
+              "(statsmodels restated in numpy), {} processes x 1 BLAS thread"
+              .format(per_step, cores))
+    line = {
+        "impl": "reference", "metric": "SNP-tests/sec", "value": value,
+        "unit": "SNP-tests/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": w["name"], "model": args.model,
+                   "samples": w["n"], "covariates": w["k_cov"] + 1},
+        "cpu_baseline": {"value": value, "unit": "SNP-tests/s",
+                         "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "SNP-tests/s",
+                "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from genetest_b200.engine import Engine
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    w = WORKLOADS[args.model]
+    n = args.samples or w["n"]
+    snps = args.snps or w["snps"]
+    rng = np.random.default_rng(SEED)
+    y, C, names = make_design(args.model, n, w["k_cov"], rng)
+
+    eng = Engine(local_rank)
+    eng.use_torch_stream()
+    # sample ids in a random permutation relative to the phenotype table
+    pos = np.random.default_rng(SEED + 1).permutation(n).astype(np.int32)
+    eng.set_design(args.model, y, C, sample_pos=pos, n_file=n)
+    packed = eng.synth_packed(n, snps, seed=SEED + 1000 * rank,
+                              missing_rate=w["missing"])
+    pitch = packed.stride(0)
+    out, iout = eng.alloc_results(snps)
+    gathered = None
+    if world > 1 and rank == 0:
+        gathered = [torch.empty_like(out) for _ in range(world)]
+        gathered_i = [torch.empty_like(iout) for _ in range(world)]
+    torch.cuda.synchronize()
+
+    def step():
+        eng.run_packed_dev(packed, snps, pitch, out, iout)
+        if world > 1:
+            # the only collective: fixed-size result blocks -> rank 0
+            dist.gather(out, gathered if rank == 0 else None, dst=0)
+            dist.gather(iout, gathered_i if rank == 0 else None, dst=0)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    eng.enable_timing(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    eng.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    kms, klaunches, all_launches = eng.kernel_time()
+    eng.enable_timing(False)
+    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    status = iout[0]
+    n_tested = int(status.numel())
+    n_ok = int((status == 0).sum().item())
+
+    # ---- end to end through the C ABI with HOST buffers (H2D + D2H inside) ----
+    e2e_snps = min(snps, args.e2e_snps)
+    host_packed = torch.empty((e2e_snps, (n + 3) // 4), dtype=torch.uint8).pin_memory()
+    host_packed.copy_(packed[:e2e_snps, :(n + 3) // 4].cpu())
+    host_out = torch.empty((eng.n_fields, e2e_snps), dtype=torch.float64).pin_memory()
+    host_iout = torch.empty((4, e2e_snps), dtype=torch.int32).pin_memory()
+    hp, ho, hi = host_packed.numpy(), host_out.numpy(), host_iout.numpy()
+    eng.run_packed_host(hp, ho, hi)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 5))
+    for _ in range(e2e_steps):
+        eng.run_packed_host(hp, ho, hi)
+    e2e_dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_dt = float(t.item())
+    e2e_value = world * e2e_snps * e2e_steps / e2e_dt
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured" if "hbm_gbs" in peaks else "fallback"
+    p = eng.n_params
+    bytes_per_snp = (n + 3) // 4 + 8 * (6 * p + 5) + 8       # SURVEY 8(d)
+    per_launch_snps = snps * args.steps / max(1, klaunches)
+    kernel_ms = kms / max(1, klaunches)
+    achieved = per_launch_snps * bytes_per_snp / (kernel_ms * 1e-3) / 1e9
+    fp64_peak = eng.fp64_peak_tflops()
+    dmma_peak = eng.dmma_peak_tflops()
+    if args.model == "linear":
+        flop_per_snp = 2.0 * n * (p + 2)          # contraction columns (k+2) + g^2
+    else:
+        flop_per_snp = float("nan")
+    fp64_achieved = per_launch_snps * flop_per_snp / (kernel_ms * 1e-3) / 1e12
+
+    # ---- CPU baseline: restated reference path on the host cores ----
+    cores = os.cpu_count() or 1
+    cpu_snps = args.cpu_snps or (cores * (200 if args.model == "linear" else 50))
+    cpu_value, cpu_done, cpu_dt = cpu_throughput(args.model, y, C, names,
+                                                 cpu_snps, cores)
+    value = world * snps * args.steps / (ms * 1e-3)
+    line = {
+        "metric": "SNP-tests/sec", "value": value, "unit": "SNP-tests/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": w["name"], "model": args.model, "samples": n,
+                   "covariates": w["k_cov"] + 1, "params": p,
+                   "snps_per_gpu_per_step": snps,
+                   "l2": "inputs ({:.1f} GB packed per GPU) larger than L2"
+                         .format(snps * pitch / 1e9),
+                   "parallelism": "snp-shard x{}".format(world),
+                   "ok_markers_last_step": n_ok, "markers_last_step": n_tested},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak,
+                     "unit": "GB/s", "frac": achieved / hbm_peak,
+                     "traffic": None, "peak_source": peak_src,
+                     "kernel": eng.dominant_kernel(),
+                     "kernel_ms_per_launch": kernel_ms,
+                     "kernel_share_of_step": kms / ms,
+                     "algorithmic_bytes_per_snp": bytes_per_snp,
+                     "fp64": {"achieved_tflops": fp64_achieved,
+                              "peak_tflops_measured": fp64_peak,
+                              "dmma_peak_tflops_measured": dmma_peak,
+                              "frac": fp64_achieved / fp64_peak
+                              if fp64_peak else None,
+                              "flop_per_snp": flop_per_snp}},
+        "cpu_baseline": {"value": cpu_value, "unit": "SNP-tests/s",
+                         "cores": cores, "kind": "port",
+                         "sample": "{} SNPs of the same synthetic workload in "
+                                   "{:.1f} s, oracle port, {} processes x 1 "
+                                   "BLAS thread".format(cpu_done, cpu_dt, cores)},
+        "e2e": {"value": e2e_value, "unit": "SNP-tests/s",
+                "h2d_bytes_per_step": int(hp.nbytes),
+                "d2h_bytes_per_step": int(ho.nbytes + hi.nbytes),
+                "snps_per_step": e2e_snps, "steps": e2e_steps,
+                "call": "gt_run_packed_host (pinned host buffers)"},
+        "gpu_launches": int(all_launches),
+        "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="linear", choices=sorted(WORKLOADS))
+    ap.add_argument("--snps", type=int, default=0, help="SNPs per GPU per step")
+    ap.add_argument("--samples", type=int, default=0)
+    ap.add_argument("--e2e-snps", type=int, default=65536)
+    ap.add_argument("--cpu-snps", type=int, default=0)
+    ap.add_argument("--ref-snps", type=int, default=0)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -117,6 +117,33 @@ __global__ void synth_packed_kernel(uint8_t *packed, long long pitch, int n_file
     }
 }
 
+// FP64 FMA peak probe (roofline denominator for the FP64-bound kernels;
+// MEASURED_PEAKS.json has no FP64 figure).
+__global__ void fp64_peak_kernel(double *sink, int iters, double b, double c) {
+    double a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
+           a6 = a0 + 6, a7 = a0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+    }
+    double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 123.456) sink[0] = s;
+}
+
+__global__ void dmma_peak_kernel(double *sink, int iters, double a, double b) {
+    double c[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { c[i][0] = threadIdx.x + i; c[i][1] = i; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) gtk::dmma884(c[i][0], c[i][1], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+    if (s == 123.456) sink[0] = s;
+}
+
 // ---------------------------------------------------------------------------
 extern "C" {
 
@@ -162,6 +189,8 @@ int gt_engine_destroy(gt_engine *e) {
 
 int gt_engine_set_stream(gt_engine *e, void *cuda_stream) {
     if (!e) return fail(GT_E_ARG, "engine is NULL");
+    // NULL selects the engine's own stream; pass cudaStreamLegacy (0x1) or
+    // cudaStreamPerThread (0x2) to run on a default stream.
     e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
     return 0;
 }
@@ -485,6 +514,55 @@ int gt_synth_packed_dev(gt_engine *e, uint8_t *packed_dev, int64_t pitch, int32_
     synth_packed_kernel<<<148 * 16, 256, 0, e->stream>>>(packed_dev, pitch, n_file, n_snps, seed,
                                                          maf_lo, maf_hi, missing_rate);
     CK(cudaGetLastError());
+    return 0;
+}
+
+int gt_measure_fp64_peak(gt_engine *e, double *tflops) {
+    if (!e || !tflops) return fail(GT_E_ARG, "gt_measure_fp64_peak: NULL argument");
+    CK(cudaSetDevice(e->device));
+    int rc = e->dS.reserve(64);
+    if (rc) return rc;
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    const int blocks = 148 * 8, threads = 256, iters = 1 << 15;
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        CK(cudaEventRecord(a, e->stream));
+        fp64_peak_kernel<<<blocks, threads, 0, e->stream>>>((double *)e->dS.p, iters, 0.999999, 1e-9);
+        CK(cudaEventRecord(b, e->stream));
+        CK(cudaEventSynchronize(b));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, a, b));
+        double tf = 2.0 * blocks * threads * 8.0 * iters / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    *tflops = best;
+    return 0;
+}
+
+int gt_measure_dmma_peak(gt_engine *e, double *tflops) {
+    if (!e || !tflops) return fail(GT_E_ARG, "gt_measure_dmma_peak: NULL argument");
+    CK(cudaSetDevice(e->device));
+    int rc = e->dS.reserve(64);
+    if (rc) return rc;
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    const int blocks = 148 * 8, threads = 256, iters = 1 << 12;
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        CK(cudaEventRecord(a, e->stream));
+        dmma_peak_kernel<<<blocks, threads, 0, e->stream>>>((double *)e->dS.p, iters, 0.5, 0.25);
+        CK(cudaEventRecord(b, e->stream));
+        CK(cudaEventSynchronize(b));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, a, b));
+        // one m8n8k4 MMA = 256 FMA = 512 FLOP per warp
+        double tf = 512.0 * blocks * (threads / 32) * 8.0 * iters / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    *tflops = best;
     return 0;
 }
 

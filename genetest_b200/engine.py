@@ -33,7 +33,8 @@ ABI_SYMBOLS = [
     "gt_packed_pitch", "gt_run_packed_dev", "gt_run_packed_host",
     "gt_run_dosage_dev", "gt_run_dosage_host", "gt_synth_packed_dev",
     "gt_engine_enable_timing", "gt_engine_kernel_time",
-    "gt_engine_dominant_kernel",
+    "gt_engine_dominant_kernel", "gt_measure_fp64_peak",
+    "gt_measure_dmma_peak",
 ]
 
 
@@ -98,6 +99,8 @@ def load_library():
                                           c.POINTER(i64), c.POINTER(i64)]
     lib.gt_engine_dominant_kernel.argtypes = [vp]
     lib.gt_engine_dominant_kernel.restype = c.c_char_p
+    lib.gt_measure_fp64_peak.argtypes = [vp, c.POINTER(dbl)]
+    lib.gt_measure_dmma_peak.argtypes = [vp, c.POINTER(dbl)]
     for name in ABI_SYMBOLS:
         getattr(lib, name)
     _LIB = lib
@@ -194,6 +197,8 @@ class Engine(object):
     def use_torch_stream(self):
         """Launch on torch's current stream (so torch.cuda.Event times it)."""
         s = self._torch.cuda.current_stream(self.device).cuda_stream
+        if s == 0:
+            s = 1       # cudaStreamLegacy: torch's default stream
         self._check(self.lib.gt_engine_set_stream(self._h, ctypes.c_void_p(s)))
 
     def synchronize(self):
@@ -333,6 +338,16 @@ class Engine(object):
         self._check(self.lib.gt_engine_kernel_time(
             self._h, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(a)))
         return ms.value, n.value, a.value
+
+    def fp64_peak_tflops(self):
+        v = ctypes.c_double()
+        self._check(self.lib.gt_measure_fp64_peak(self._h, ctypes.byref(v)))
+        return v.value
+
+    def dmma_peak_tflops(self):
+        v = ctypes.c_double()
+        self._check(self.lib.gt_measure_dmma_peak(self._h, ctypes.byref(v)))
+        return v.value
 
     def dominant_kernel(self):
         return self.lib.gt_engine_dominant_kernel(self._h).decode()

@@ -66,7 +66,8 @@ enum {
                           coef, std_err, lower_ci, upper_ci, t(z)_value,
                           p_value                                            */
 };
-/* integer block: int32 iout[3][n_snps] = status, nobs, flip               */
+/* integer block: int32 iout[GT_NUM_IFIELDS][n_snps] = status, nobs, flip,
+ * iterations (IRLS / Newton steps; linear: 1 when the Jacobi gate ran)   */
 enum { GT_I_STATUS = 0, GT_I_NOBS = 1, GT_I_FLIP = 2, GT_I_NITER = 3,
        GT_NUM_IFIELDS = 4 };
 
@@ -103,7 +104,8 @@ const char *gt_last_error(void);
 
 int gt_engine_create(int device, gt_engine **out);
 int gt_engine_destroy(gt_engine *e);
-/* cudaStream_t to launch on (NULL = the engine's own stream). */
+/* cudaStream_t to launch on.  NULL = the engine's own non-blocking stream;
+ * use cudaStreamLegacy / cudaStreamPerThread for a default stream. */
 int gt_engine_set_stream(gt_engine *e, void *cuda_stream);
 int gt_engine_synchronize(gt_engine *e);
 
@@ -148,6 +150,11 @@ int gt_engine_enable_timing(gt_engine *e, int on);
 int gt_engine_kernel_time(gt_engine *e, double *ms_total, int64_t *launches,
                           int64_t *all_launches);
 const char *gt_engine_dominant_kernel(const gt_engine *e);
+/* FP64 FMA throughput of the device (TFLOP/s), measured with a register-only
+ * FMA kernel: the roofline denominator of the FP64-bound kernels. */
+int gt_measure_fp64_peak(gt_engine *e, double *tflops);
+/* same for the FP64 tensor-core path (mma.sync m8n8k4 f64). */
+int gt_measure_dmma_peak(gt_engine *e, double *tflops);
 
 #ifdef __cplusplus
 }
