@@ -25,7 +25,7 @@ struct gt_engine {
     GtDesignDev D{};
     gtk::IterDesignDev T{};           // logistic / coxph design
     DevBuf dE, dMask, dFF0, dR, dRinv, dTq, dIter;   // design
-    DevBuf dS, dCounts;                        // per-batch workspace
+    DevBuf dS, dCounts, dGsum;                 // per-batch workspace
     DevBuf dGeno, dOut, dIout;                 // staging of the *_host entry points
     int contract_idx = -1;
     // timing
@@ -41,34 +41,34 @@ struct gt_engine {
 // contraction kernel instantiations
 // ---------------------------------------------------------------------------
 typedef void (*contract_fn)(const uint8_t *, long long, int, const uint8_t *, const double *, int,
-                            double *, int *);
-struct ContractEntry { int NCA, NCB, rows, smem; contract_fn fn; };
+                            double *, int *, double *);
+struct ContractEntry { int NCA, NCB, rows, warps, smem; contract_fn fn; };
 
-template <int NCA, int NCB>
-struct RowsFor {
-    static constexpr int NC = NCA + NCB;
-    static constexpr int value = NC <= 16 ? 4 : (NC <= 24 ? 3 : (NC <= 36 ? 2 : 1));
-};
-template <int NCA, int NCB>
-static constexpr int contract_smem() {
-    using Cfg = gtk::ContractCfg<NCA, NCB, RowsFor<NCA, NCB>::value>;
-    int red = gtk::kWarps * 32 * Cfg::NC * 8 + gtk::kWarps * 32 * 3 * 4;
-    return Cfg::kSmem > red ? Cfg::kSmem : red;
-}
-#define GT_ENTRY(A, B) \
-    { A, B, RowsFor<A, B>::value, contract_smem<A, B>(), gtk::contract_packed_kernel<A, B, RowsFor<A, B>::value> }
+// (NCA, NCB, ROWS, WARPS, MINB): register tile ROWS x (NCA + NCB) doubles per
+// thread; small tiles run 128-thread CTAs, three per SM.
+#define GT_ENTRY(A, B, R, W, M)                                              \
+    { A, B, R, W, gtk::ContractCfg<A, B, R, W>::kSmem,                        \
+      gtk::contract_packed_kernel<A, B, R, W, M> }
 static const ContractEntry kContract[] = {
-    GT_ENTRY(6, 2),  GT_ENTRY(10, 2), GT_ENTRY(14, 2), GT_ENTRY(18, 2), GT_ENTRY(24, 2), GT_ENTRY(32, 2),
-    GT_ENTRY(12, 4), GT_ENTRY(20, 4), GT_ENTRY(28, 4), GT_ENTRY(36, 4), GT_ENTRY(48, 4),
-    GT_ENTRY(18, 6), GT_ENTRY(30, 6), GT_ENTRY(42, 6), GT_ENTRY(54, 6),
-    GT_ENTRY(32, 10), GT_ENTRY(48, 10), GT_ENTRY(64, 10),
+    // lean designs (no interaction): E = [q | y]
+    GT_ENTRY(4, 0, 4, 4, 3),  GT_ENTRY(6, 0, 4, 4, 3),  GT_ENTRY(8, 0, 4, 4, 3),
+    GT_ENTRY(10, 0, 4, 4, 3), GT_ENTRY(12, 0, 4, 4, 3), GT_ENTRY(14, 0, 4, 4, 2),
+    GT_ENTRY(16, 0, 4, 4, 2), GT_ENTRY(20, 0, 3, 4, 2), GT_ENTRY(24, 0, 2, 4, 3),
+    GT_ENTRY(28, 0, 2, 4, 2), GT_ENTRY(32, 0, 2, 4, 2),
+    // one interaction
+    GT_ENTRY(12, 4, 4, 4, 2), GT_ENTRY(20, 4, 3, 4, 2), GT_ENTRY(28, 4, 2, 4, 2),
+    GT_ENTRY(36, 4, 1, 4, 3), GT_ENTRY(48, 4, 1, 4, 2),
+    // two / three interactions
+    GT_ENTRY(18, 6, 3, 4, 2), GT_ENTRY(30, 6, 2, 4, 2), GT_ENTRY(42, 6, 1, 4, 2),
+    GT_ENTRY(54, 6, 1, 4, 2),
+    GT_ENTRY(32, 10, 1, 4, 2), GT_ENTRY(48, 10, 1, 4, 2), GT_ENTRY(64, 10, 1, 4, 1),
 };
 static const int kNumContract = sizeof(kContract) / sizeof(kContract[0]);
 
 static int pick_contract(int NC1, int NC2) {
     int best = -1;
     for (int i = 0; i < kNumContract; ++i) {
-        if (kContract[i].NCA >= NC1 && kContract[i].NCB >= NC2) {
+        if (kContract[i].NCA >= NC1 && kContract[i].NCB >= NC2 && (kContract[i].NCB == 0) == (NC2 == 0)) {
             if (best < 0 || kContract[i].NCA + kContract[i].NCB < kContract[best].NCA + kContract[best].NCB)
                 best = i;
         }
@@ -180,7 +180,7 @@ int gt_engine_destroy(gt_engine *e) {
     cudaStreamSynchronize(e->stream);
     for (auto &ev : e->events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     DevBuf *bufs[] = {&e->dE, &e->dMask, &e->dFF0, &e->dR, &e->dRinv, &e->dTq, &e->dIter,
-                      &e->dS, &e->dCounts, &e->dGeno, &e->dOut, &e->dIout};
+                      &e->dS, &e->dCounts, &e->dGsum, &e->dGeno, &e->dOut, &e->dIout};
     for (DevBuf *b : bufs) b->release();
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
@@ -297,7 +297,8 @@ int gt_engine_set_design(gt_engine *e, const gt_design_desc *d) {
         H.icpt_shift = H.icpt_col >= 0 ? ybar / d->C[(size_t)H.icpt_col * n] : 0.0;
 
         const int L = H.L;
-        const int NC1 = (I + 1) * L, NC2 = (I + 1) * (I + 2) / 2;
+        const bool lean = (I == 0);
+        const int NC1 = lean ? k + 1 : (I + 1) * L, NC2 = lean ? 0 : (I + 1) * (I + 2) / 2;
         int ci = pick_contract(NC1, NC2);
         if (ci < 0) return fail(GT_E_UNSUPPORTED, "gt_engine_set_design: no contraction kernel for %d+%d columns (k=%d, interactions=%d)", NC1, NC2, k, I);
         const int NCA = kContract[ci].NCA, NCB = kContract[ci].NCB, NCP = NCA + NCB;
@@ -325,6 +326,10 @@ int gt_engine_set_design(gt_engine *e, const gt_design_desc *d) {
         for (int i = 0; i < n; ++i) {
             const double *v = &V[(size_t)i * L];
             double *er = &E[(size_t)pos[i] * NCP];
+            if (lean) {
+                for (int b = 0; b <= k; ++b) er[b] = v[b];
+                continue;
+            }
             for (int c = 0; c <= I; ++c) {
                 double m = c == 0 ? 1.0 : v[k + 1 + c];
                 for (int b = 0; b < L; ++b) er[c * L + b] = m * v[b];
@@ -351,6 +356,7 @@ int gt_engine_set_design(gt_engine *e, const gt_design_desc *d) {
         D.n_chunks = n_chunks;
         D.raw_mode = d->raw_mode; D.has_const = H.has_const; D.icpt_col = H.icpt_col;
         D.use_maf_t = d->use_maf_t; D.degenerate = H.degenerate ? 1 : 0;
+        D.lean = lean ? 1 : 0;
         D.icpt_shift = H.icpt_shift;
         D.cond_t = d->condition_value_t; D.eig_t = d->eigenvals_t; D.maf_t = d->maf_t;
         D.E = (const double *)e->dE.p; D.ormask = (const uint8_t *)e->dMask.p;
@@ -369,6 +375,8 @@ int gt_engine_set_design(gt_engine *e, const gt_design_desc *d) {
     e->have_design = true;
     return 0;
 }
+
+}  // extern "C"
 
 // ---------------------------------------------------------------------------
 static int time_begin(gt_engine *e) {
@@ -390,6 +398,30 @@ static void time_end(gt_engine *e, int slot) {
 
 static int e_n_file(const gt_engine *e) { return e->model == GT_MODEL_LINEAR ? e->D.n_file : e->T.n_file; }
 
+template <bool PACKED>
+static int launch_finish(gt_engine *e, int NT2, int grid, int threads, size_t smem,
+                         const void *g, int64_t pitch, int nb, double *out, int32_t *iout,
+                         long long stride, int wpc) {
+    const GtDesignDev &D = e->D;
+    const double *S = (const double *)e->dS.p;
+    const int *cnt = (const int *)e->dCounts.p;
+    const double *gs = (const double *)e->dGsum.p;
+#define GT_FIN(N)                                                                            \
+    case N:                                                                                  \
+        CK(cudaFuncSetAttribute((const void *)gtk::linear_finish_kernel<PACKED, N>,          \
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+        gtk::linear_finish_kernel<PACKED, N><<<grid, threads, smem, e->stream>>>(            \
+            D, g, pitch, nb, S, cnt, gs, out, iout, stride, wpc);                            \
+        break;
+    switch (NT2) {
+        GT_FIN(1) GT_FIN(2) GT_FIN(3) GT_FIN(4) GT_FIN(5)
+        default: return fail(GT_E_UNSUPPORTED, "finish kernel: design too wide");
+    }
+#undef GT_FIN
+    CK(cudaGetLastError());
+    return 0;
+}
+
 static int run_linear(gt_engine *e, const void *geno, int64_t pitch, bool packed, int32_t n_snps,
                       double *out, int32_t *iout) {
     const GtDesignDev &D = e->D;
@@ -400,38 +432,37 @@ static int run_linear(gt_engine *e, const void *geno, int64_t pitch, bool packed
     const int bmax = std::min<int>(n_snps, kBatch);
     if ((rc = e->dS.reserve((size_t)bmax * D.NCP * 8))) return rc;
     if ((rc = e->dCounts.reserve((size_t)bmax * 4 * 4))) return rc;
+    if ((rc = e->dGsum.reserve((size_t)bmax * 2 * 8))) return rc;
     CK(cudaFuncSetAttribute((const void *)ce.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ce.smem));
     gtk::FinishLayout lay = gtk::finish_layout(D.L, D.p, D.I);
-    size_t tab = ((size_t)2 * D.NPROD + 15) & ~(size_t)15;
+    const int NT2 = (D.L + 7) / 8;
     int wpc = 8;
-    while (wpc > 1 && (size_t)wpc * lay.perWarp * 8 + tab > 200 * 1024) wpc >>= 1;
-    size_t fsmem = (size_t)wpc * lay.perWarp * 8 + tab;
+    while (wpc > 1 && (size_t)wpc * lay.perWarp * 8 > 100 * 1024) wpc >>= 1;
+    size_t fsmem = (size_t)wpc * lay.perWarp * 8;
     if (fsmem > 220 * 1024) return fail(GT_E_UNSUPPORTED, "design too wide for the finish kernel (%zu B shared)", fsmem);
-    if (packed) CK(cudaFuncSetAttribute((const void *)gtk::linear_finish_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-    else CK(cudaFuncSetAttribute((const void *)gtk::linear_finish_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
 
     for (int s0 = 0; s0 < n_snps; s0 += kBatch) {
         int nb = std::min<int>(kBatch, n_snps - s0);
         double *S = (double *)e->dS.p;
         int *cnt = (int *)e->dCounts.p;
+        double *gs = (double *)e->dGsum.p;
+        int grid = (nb + wpc - 1) / wpc;
         if (packed) {
             const uint8_t *g = (const uint8_t *)geno + (int64_t)s0 * pitch;
             int slot = time_begin(e);
-            ce.fn<<<(nb + tile - 1) / tile, gtk::kThreads, ce.smem, e->stream>>>(
-                g, pitch, nb, D.ormask, D.E, D.n_chunks, S, cnt);
+            ce.fn<<<(nb + tile - 1) / tile, 32 * ce.warps, ce.smem, e->stream>>>(
+                g, pitch, nb, D.ormask, D.E, D.n_chunks, S, cnt, gs);
             time_end(e, slot);
             CK(cudaGetLastError());
-            gtk::linear_finish_kernel<true><<<(nb + wpc - 1) / wpc, wpc * 32, fsmem, e->stream>>>(
-                D, g, pitch, nb, S, cnt, out + s0, iout + s0, (long long)n_snps, wpc);
-            CK(cudaGetLastError());
+            if ((rc = launch_finish<true>(e, NT2, grid, wpc * 32, fsmem, g, pitch, nb, out + s0,
+                                          iout + s0, (long long)n_snps, wpc))) return rc;
         } else {
             const double *g = (const double *)geno + (int64_t)s0 * pitch;
             gtk::contract_dosage_kernel<<<(nb + 7) / 8, 256, 0, e->stream>>>(
-                g, pitch, nb, D.n, D.E, D.NCA, D.NCB, D.NC1, D.NC2, S, cnt);
+                g, pitch, nb, D.n, D.E, D.NCA, D.NCB, D.NC1, D.NC2, S, cnt, gs);
             CK(cudaGetLastError());
-            gtk::linear_finish_kernel<false><<<(nb + wpc - 1) / wpc, wpc * 32, fsmem, e->stream>>>(
-                D, g, pitch, nb, S, cnt, out + s0, iout + s0, (long long)n_snps, wpc);
-            CK(cudaGetLastError());
+            if ((rc = launch_finish<false>(e, NT2, grid, wpc * 32, fsmem, g, pitch, nb, out + s0,
+                                           iout + s0, (long long)n_snps, wpc))) return rc;
         }
         e->all_launches += 2;
     }
@@ -454,6 +485,8 @@ static int run_any(gt_engine *e, const void *geno, int64_t pitch, bool packed, i
                          e->all_launches, g_err);
 }
 
+
+extern "C" {
 
 int gt_run_packed_dev(gt_engine *e, const uint8_t *packed_dev, int64_t pitch, int32_t n_snps,
                       double *out_dev, int32_t *iout_dev) {

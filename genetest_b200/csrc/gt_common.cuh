@@ -34,6 +34,7 @@ struct GtDesignDev {
     int icpt_col;      // explicit constant column of C (or -1)
     int use_maf_t;
     int degenerate;    // covariates alone are rank deficient
+    int lean;          // no interaction: E rows are [q | y] only (NC1 = k + 1, NC2 = 0)
     double icpt_shift; // ybar / value of the constant column
     double cond_t, eig_t, maf_t;
     const double *E;        // [n_chunks*256][NCP]
@@ -60,34 +61,29 @@ GT_HD double gt_lgamma_half_diff(double a) {
            gt_stirling_tail(a + 0.5) - gt_stirling_tail(a);
 }
 
-// Continued fraction of the incomplete beta function (modified Lentz).
+// Continued fraction of the incomplete beta function, 1/(1+ d1/(1+ d2/(1+ ...))),
+// evaluated with Steed's forward algorithm: one reciprocal per partial
+// quotient, and the two coefficients of a step share one more.
 GT_HD double gt_betacf(double a, double b, double x) {
-    const double tiny = 1e-300;
-    double qab = a + b, qap = a + 1.0, qam = a - 1.0;
-    double c = 1.0, d = 1.0 - qab * x / qap;
-    if (fabs(d) < tiny) d = tiny;
-    d = 1.0 / d;
-    double h = d;
-    for (int m = 1; m <= 500; ++m) {
-        double m2 = 2.0 * m;
-        double aa = m * (b - m) * x / ((qam + m2) * (a + m2));
-        d = 1.0 + aa * d;
-        if (fabs(d) < tiny) d = tiny;
-        c = 1.0 + aa / c;
-        if (fabs(c) < tiny) c = tiny;
-        d = 1.0 / d;
-        h *= d * c;
-        aa = -(a + m) * (qab + m) * x / ((a + m2) * (qap + m2));
-        d = 1.0 + aa * d;
-        if (fabs(d) < tiny) d = tiny;
-        c = 1.0 + aa / c;
-        if (fabs(c) < tiny) c = tiny;
-        d = 1.0 / d;
-        double del = d * c;
-        h *= del;
-        if (fabs(del - 1.0) < 2e-16) break;
+    const double qab = a + b, qap = a + 1.0, qam = a - 1.0;
+    double D = 1.0 / (1.0 - qab * x / qap);
+    double delta = D - 1.0;
+    double f = 1.0 + delta;
+    for (int m = 1; m <= 300; ++m) {
+        const double m2 = 2.0 * m;
+        const double q1 = qam + m2, q2 = a + m2, q3 = qap + m2;
+        const double r = 1.0 / (q1 * q2 * q3);
+        const double aa1 = m * (b - m) * x * q3 * r;
+        const double aa2 = -(a + m) * (qab + m) * x * q1 * r;
+        D = 1.0 / (1.0 + aa1 * D);
+        delta *= D - 1.0;
+        f += delta;
+        D = 1.0 / (1.0 + aa2 * D);
+        delta *= D - 1.0;
+        f += delta;
+        if (fabs(delta) < 1e-16 * fabs(f)) break;
     }
-    return h;
+    return f;
 }
 
 // log of the t density normaliser: -ln( sqrt(df) B(df/2, 1/2) ) + ...
@@ -105,7 +101,11 @@ GT_HD double gt_t_sf2(double t, double df) {
     double lnpre = -gt_lbeta_half(a) - a * log1p(t2 / df) +
                    0.5 * (log(t2) - log(df + t2));
     double x = df / (df + t2);
-    if (x < (a + 1.0) / (a + 2.5))
+    // direct fraction in the tail; the complement converges faster (and loses
+    // at most ~3 digits) for |t| < 3 once df is not tiny
+    bool direct = x < (a + 1.0) / (a + 2.5);
+    if (direct && t2 < 9.0 && df > 10.0) direct = false;
+    if (direct)
         return exp(lnpre) * gt_betacf(a, 0.5, x) / a;
     return 1.0 - exp(lnpre) * gt_betacf(0.5, a, t2 / (df + t2)) / 0.5;
 }

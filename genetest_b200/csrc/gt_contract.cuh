@@ -1,7 +1,7 @@
 // K1 + K2: stage PLINK 2-bit rows into shared memory with cp.async, decode
 // them to dosages in registers and contract them against the design's E
-// matrix in FP64.  Output per SNP: S[NCP] = sum_i g_i E1_i | sum_i g_i^2 E2_i
-// and the exact integer genotype counts.
+// matrix in FP64.  Output per SNP: S[NCP] = sum_i g_i E1_i | sum_i g_i^2 E2_i,
+// the exact integer genotype counts and (sum g, sum g^2).
 //
 // Replaces (for a tile of 32*ROWS SNPs at once) the per-SNP staging of
 // genetest/analysis.py:109-119 (NaN fill, label-aligned scatter, complete-case
@@ -13,8 +13,6 @@
 
 namespace gtk {
 
-constexpr int kThreads = 256;          // 8 warps; warp w owns samples [32w, 32w+32) of a chunk
-constexpr int kWarps = kThreads / 32;
 constexpr int kChunk = 256;            // samples per pipeline stage
 constexpr int kRowBytes = kChunk / 4;  // 64 packed bytes per SNP row per stage
 constexpr int kRowPitch = kRowBytes + 16;  // shared-memory row pitch (bank spread)
@@ -27,51 +25,52 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-// dosage (and its square) of the 2-bit code at bit position `pos` of word w,
-// built as IEEE doubles with integer ops only: 00 -> 2, 01 (missing) -> 0,
-// 10 -> 1, 11 -> 0.
-__device__ __forceinline__ void decode_pair(uint32_t w, int pos, double &g, double &g2) {
-    uint32_t lo = (w >> pos) & 1u;
-    uint32_t hi = (w >> (pos + 1)) & 1u;
-    // g  : hi=0 -> 2.0 (0x40000000), hi=1 -> 1.0 (0x3FF00000)
-    // g^2: hi=0 -> 4.0 (0x40100000), hi=1 -> 1.0 (0x3FF00000)
-    uint32_t h1 = 0x40000000u - (hi << 20);
-    uint32_t h2 = 0x40100000u - (hi << 21);
-    h1 = lo ? 0u : h1;
-    h2 = lo ? 0u : h2;
-    g = __hiloint2double((int)h1, 0);
-    g2 = __hiloint2double((int)h2, 0);
-}
-
-template <int NCA, int NCB, int ROWS>
+template <int NCA, int NCB, int ROWS, int WARPS>
 struct ContractCfg {
     static constexpr int NC = NCA + NCB;
+    static constexpr int kThreads = 32 * WARPS;
+    static constexpr int kSPW = kChunk / WARPS;                      // samples per warp per stage
     static constexpr int kTile = 32 * ROWS;                          // SNPs per CTA
+    static constexpr int kTabBytes = 64;                             // decode table (4 x double2)
     static constexpr int kGenoBytes = kTile * kRowPitch;
     static constexpr int kEBytes = kChunk * NC * 8;
     static constexpr int kStageBytes = kGenoBytes + kEBytes + kRowBytes;
-    static constexpr int kStages = (2 * kStageBytes <= 200 * 1024) ? 2 : 1;
-    static constexpr int kSmem = kStages * kStageBytes;
+    static constexpr int kStages = (2 * kStageBytes + kTabBytes <= 72 * 1024) ? 2
+                                   : ((2 * kStageBytes + kTabBytes <= 200 * 1024) ? 2 : 1);
+    static constexpr int kRedBytes = WARPS * 32 * NC * 8 + WARPS * 32 * 3 * 4;
+    static constexpr int kMain = kStages * kStageBytes;
+    static constexpr int kSmem = kTabBytes + (kMain > kRedBytes ? kMain : kRedBytes);
 };
 
-template <int NCA, int NCB, int ROWS>
-__global__ void __launch_bounds__(kThreads, 1)
+// Packed kernel.  `lean` designs (no interaction) carry only [q | y] in E:
+// sum g and sum g^2 come from the exact class counts.
+template <int NCA, int NCB, int ROWS, int WARPS, int MINB>
+__global__ void __launch_bounds__(32 * WARPS, MINB)
 contract_packed_kernel(const uint8_t *__restrict__ geno, long long pitch, int n_snps,
                        const uint8_t *__restrict__ ormask, const double *__restrict__ E,
-                       int n_chunks, double *__restrict__ S, int *__restrict__ counts) {
-    using Cfg = ContractCfg<NCA, NCB, ROWS>;
+                       int n_chunks, double *__restrict__ S, int *__restrict__ counts,
+                       double *__restrict__ gsum) {
+    using Cfg = ContractCfg<NCA, NCB, ROWS, WARPS>;
     constexpr int NC = Cfg::NC;
-    extern __shared__ __align__(16) unsigned char smem[];
+    constexpr int kThreads = Cfg::kThreads;
+    constexpr int NW64 = Cfg::kSPW / 32;     // 64-bit words (32 samples) per row per warp
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // code -> (g, g^2): 00 -> 2, 01 (missing) -> 0, 10 -> 1, 11 -> 0
+    double2 *tab = (double2 *)smem_raw;
+    unsigned char *smem = smem_raw + Cfg::kTabBytes;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile0 = blockIdx.x * Cfg::kTile;
+    if (tid < 4) {
+        double g = tid == 0 ? 2.0 : (tid == 2 ? 1.0 : 0.0);
+        tab[tid] = make_double2(g, g * g);
+    }
 
     auto stage_geno = [&](int s) { return smem + s * Cfg::kStageBytes; };
     auto stage_E = [&](int s) { return (double *)(smem + s * Cfg::kStageBytes + Cfg::kGenoBytes); };
     auto stage_mask = [&](int s) { return smem + s * Cfg::kStageBytes + Cfg::kGenoBytes + Cfg::kEBytes; };
 
     auto issue = [&](int chunk, int s) {
-        // packed rows: kTile rows x 64 B  (4 x 16 B per row)
         unsigned char *gs = stage_geno(s);
         for (int t = tid; t < Cfg::kTile * 4; t += kThreads) {
             int row = t >> 2, part = t & 3;
@@ -79,7 +78,6 @@ contract_packed_kernel(const uint8_t *__restrict__ geno, long long pitch, int n_
             cp_async16(gs + row * kRowPitch + part * 16,
                        geno + (long long)snp * pitch + (long long)chunk * kRowBytes + part * 16);
         }
-        // E rows of this chunk: contiguous kChunk * NC doubles
         const double *src = E + (long long)chunk * kChunk * NC;
         double *es = stage_E(s);
         for (int t = tid; t < kChunk * NC / 2; t += kThreads) cp_async16(es + 2 * t, src + 2 * t);
@@ -109,46 +107,60 @@ contract_packed_kernel(const uint8_t *__restrict__ geno, long long pitch, int n_
         __syncthreads();
 
         const unsigned char *gs = stage_geno(s);
-        const double *es = stage_E(s) + warp * 32 * NC;
-        const uint2 mk = *(const uint2 *)(stage_mask(s) + warp * 8);
-        uint2 w[ROWS];
+#pragma unroll 1
+        for (int h = 0; h < 2 * NW64; ++h) {
+            const int sub = warp * NW64 + (h >> 1);           // 32-sample group within the chunk
+            const int half = h & 1;                           // 16-sample half of the group
+            const double *es = stage_E(s) + (sub * 32 + half * 16) * NC;
+            uint32_t w[ROWS];
+            {
+                const uint32_t mk = *(const uint32_t *)(stage_mask(s) + sub * 8 + half * 4);
 #pragma unroll
-        for (int r = 0; r < ROWS; ++r) {
-            w[r] = *(const uint2 *)(gs + (lane + 32 * r) * kRowPitch + warp * 8);
-            w[r].x |= mk.x; w[r].y |= mk.y;
-            // exact class counts from the bit planes (even bit = low bit of the code)
-            uint32_t lox = w[r].x & 0x55555555u, hix = (w[r].x >> 1) & 0x55555555u;
-            uint32_t loy = w[r].y & 0x55555555u, hiy = (w[r].y >> 1) & 0x55555555u;
-            nmis[r] += __popc(lox & ~hix) + __popc(loy & ~hiy);
-            nhet[r] += __popc(hix & ~lox) + __popc(hiy & ~loy);
-            nhom[r] += __popc(~(lox | hix) & 0x55555555u) + __popc(~(loy | hiy) & 0x55555555u);
-        }
-#pragma unroll 4
-        for (int sidx = 0; sidx < 32; ++sidx) {
-            double e[NC];
-            const double2 *ep = (const double2 *)(es + sidx * NC);
-#pragma unroll
-            for (int c = 0; c < NC / 2; ++c) {
-                double2 v = ep[c];
-                e[2 * c] = v.x; e[2 * c + 1] = v.y;
+                for (int r = 0; r < ROWS; ++r) {
+                    uint32_t v = *(const uint32_t *)(gs + (lane + 32 * r) * kRowPitch + sub * 8 + half * 4) | mk;
+                    w[r] = v;
+                    // exact class counts from the bit planes (even bit = low bit of the code)
+                    uint32_t lo = v & 0x55555555u, hi = (v >> 1) & 0x55555555u;
+                    nmis[r] += __popc(lo & ~hi);
+                    nhet[r] += __popc(hi & ~lo);
+                    nhom[r] += __popc(~(lo | hi) & 0x55555555u);
+                }
             }
 #pragma unroll
-            for (int r = 0; r < ROWS; ++r) {
-                uint32_t word = (sidx < 16) ? w[r].x : w[r].y;
-                double g, g2;
-                decode_pair(word, 2 * (sidx & 15), g, g2);
+            for (int sidx = 0; sidx < 16; ++sidx) {
+                double e[NC];
+                const double2 *ep = (const double2 *)(es + sidx * NC);
 #pragma unroll
-                for (int c = 0; c < NCA; ++c) acc[r][c] = fma(g, e[c], acc[r][c]);
+                for (int c = 0; c < NC / 2; ++c) {
+                    double2 v = ep[c];
+                    e[2 * c] = v.x; e[2 * c + 1] = v.y;
+                }
 #pragma unroll
-                for (int c = 0; c < NCB; ++c) acc[r][NCA + c] = fma(g2, e[NCA + c], acc[r][NCA + c]);
+                for (int r = 0; r < ROWS; ++r) {
+                    // byte offset of the table entry: code * 16
+                    uint32_t off = (sidx >= 2) ? ((w[r] >> (2 * sidx - 4)) & 0x30u)
+                                               : ((w[r] << (4 - 2 * sidx)) & 0x30u);
+                    if (NCB > 0) {
+                        double2 gg = *(const double2 *)((const unsigned char *)tab + off);
+#pragma unroll
+                        for (int c = 0; c < NCA; ++c) acc[r][c] = fma(gg.x, e[c], acc[r][c]);
+#pragma unroll
+                        for (int c = 0; c < NCB; ++c)
+                            acc[r][NCA + c] = fma(gg.y, e[NCA + c], acc[r][NCA + c]);
+                    } else {
+                        double g = *(const double *)((const unsigned char *)tab + off);
+#pragma unroll
+                        for (int c = 0; c < NCA; ++c) acc[r][c] = fma(g, e[c], acc[r][c]);
+                    }
+                }
             }
         }
         __syncthreads();
     }
 
     // cross-warp reduction through shared memory, one row set at a time
-    double *red = (double *)smem;                 // [kWarps][32][NC]   (<= one E stage)
-    int *redc = (int *)(smem + kWarps * 32 * NC * 8);   // [kWarps][32][3]
+    double *red = (double *)smem;                        // [WARPS][32][NC]
+    int *redc = (int *)(smem + WARPS * 32 * NC * 8);     // [WARPS][32][3]
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
         double *mine = red + (warp * 32 + lane) * NC;
@@ -160,16 +172,24 @@ contract_packed_kernel(const uint8_t *__restrict__ geno, long long pitch, int n_
         for (int t = tid; t < 32 * NC; t += kThreads) {
             double sum = 0.0;
 #pragma unroll
-            for (int wv = 0; wv < kWarps; ++wv) sum += red[wv * 32 * NC + t];
+            for (int wv = 0; wv < WARPS; ++wv) sum += red[wv * 32 * NC + t];
             int snp = tile0 + 32 * r + t / NC;
             if (snp < n_snps) S[(long long)snp * NC + t % NC] = sum;
         }
-        for (int t = tid; t < 32 * 3; t += kThreads) {
-            int sum = 0;
+        for (int t = tid; t < 32; t += kThreads) {
+            int c3[3] = {0, 0, 0};
 #pragma unroll
-            for (int wv = 0; wv < kWarps; ++wv) sum += redc[wv * 32 * 3 + t];
-            int snp = tile0 + 32 * r + t / 3;
-            if (snp < n_snps) counts[(long long)snp * 4 + t % 3] = sum;
+            for (int wv = 0; wv < WARPS; ++wv)
+#pragma unroll
+                for (int q = 0; q < 3; ++q) c3[q] += redc[(wv * 32 + t) * 3 + q];
+            int snp = tile0 + 32 * r + t;
+            if (snp < n_snps) {
+                counts[(long long)snp * 4 + 0] = c3[0];
+                counts[(long long)snp * 4 + 1] = c3[1];
+                counts[(long long)snp * 4 + 2] = c3[2];
+                gsum[(long long)snp * 2 + 0] = (double)(c3[0] + 2 * c3[1]);
+                gsum[(long long)snp * 2 + 1] = (double)(c3[0] + 4 * c3[1]);
+            }
         }
         __syncthreads();
     }
@@ -181,19 +201,29 @@ contract_packed_kernel(const uint8_t *__restrict__ geno, long long pitch, int n_
 __global__ void __launch_bounds__(256)
 contract_dosage_kernel(const double *__restrict__ dosage, long long ld, int n_snps, int n,
                        const double *__restrict__ E, int NCA, int NCB, int NC1, int NC2,
-                       double *__restrict__ S, int *__restrict__ counts) {
+                       double *__restrict__ S, int *__restrict__ counts,
+                       double *__restrict__ gsum) {
     const int lane = threadIdx.x & 31;
     const int snp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (snp >= n_snps) return;
     const int NC = NCA + NCB;
     const double *row = dosage + (long long)snp * ld;
     int nm = 0;
-    for (int i = lane; i < n; i += 32) nm += (row[i] != row[i]);
+    double sg = 0.0, sg2 = 0.0;
+    for (int i = lane; i < n; i += 32) {
+        double g = row[i];
+        if (g != g) { nm += 1; continue; }
+        sg += g; sg2 = fma(g, g, sg2);
+    }
     nm = gt_warp_sum_int(nm);
+    sg = gt_warp_sum(sg);
+    sg2 = gt_warp_sum(sg2);
     if (lane == 0) {
         counts[(long long)snp * 4 + 0] = -1;
         counts[(long long)snp * 4 + 1] = -1;
         counts[(long long)snp * 4 + 2] = nm;
+        gsum[(long long)snp * 2 + 0] = sg;
+        gsum[(long long)snp * 2 + 1] = sg2;
     }
     for (int c = 0; c < NC; ++c) {
         bool live = (c < NCA) ? (c < NC1) : (c - NCA < NC2);

@@ -18,6 +18,12 @@
 
 namespace gtk {
 
+// stride of the 32-entry staging tile: == 4 (mod 16) doubles -> the MMA
+// fragment loads below are bank-conflict free
+__host__ __device__ constexpr int finish_stage_stride(int NT2) {
+    return NT2 <= 2 ? 20 : (NT2 <= 4 ? 36 : 52);
+}
+
 struct FinishLayout {
     int perWarp;   // doubles per warp
     int oS0, oMo, oMc, oMi, oStage, oVec, oQueue;
@@ -31,10 +37,11 @@ __host__ __device__ inline FinishLayout finish_layout(int L, int p, int I) {
     f.oMo = o; o += p * p;
     f.oMc = o; o += p * p;
     f.oMi = o; o += p * p;
-    f.oStage = o; o += 32 * L;
+    o = (o + 1) & ~1;                      // staging rows are copied 16 B at a time
+    f.oStage = o; o += 32 * finish_stage_stride((L + 7) / 8);
     f.oVec = o; o += 6 * p + (I + 1) * L + (I + 1) * (I + 1) + 8;
     f.oQueue = o;
-    f.queueInts = 32 + 512 + 32;
+    f.queueInts = 64;
     o += (f.queueInts + 1) / 2;
     f.perWarp = (o + 1) & ~1;
     return f;
@@ -57,90 +64,138 @@ __device__ __forceinline__ void finish_write_fail(double *out, int *iout, long l
     }
 }
 
-// Subtract sum over the missing samples of v v' from S0 (one warp).
-// PACKED: row = 2-bit codes OR-ed with the design mask; else doubles with NaN.
-template <bool PACKED>
-__device__ __forceinline__ void subtract_missing(const GtDesignDev &D, const void *rowp,
-                                                 double *S0, double *stage, int *queue,
-                                                 const unsigned char *pa, const unsigned char *pb,
-                                                 int lane) {
-    const int L = D.L;
-    int qn = 0;
-    auto process = [&](const int *q, int count) {
-        int idx = (lane < count) ? q[lane] : -1;
-        for (int c = 0; c < L; ++c)
-            stage[lane * L + c] = (idx >= 0) ? D.E[(long long)idx * D.NCP + c] : 0.0;
-        __syncwarp();
-        for (int t = lane; t < D.NPROD; t += 32) {
-            int a = pa[t], b = pb[t];
-            double acc = 0.0;
-#pragma unroll 8
-            for (int e = 0; e < 32; ++e) acc = fma(stage[e * L + a], stage[e * L + b], acc);
-            S0[a * L + b] -= acc;
-            if (a != b) S0[b * L + a] -= acc;
-        }
-        __syncwarp();
-    };
-    auto drain = [&]() {
-        int head = 0;
-        while (qn - head >= 32) { process(queue + head, 32); head += 32; }
-        if (head > 0) {
-            int v = (lane < qn - head) ? queue[head + lane] : 0;
-            __syncwarp();
-            if (lane < qn - head) queue[lane] = v;
-            qn -= head;
-            __syncwarp();
-        }
-    };
-    const int nblocks = PACKED ? ((D.n_file + 15) / 16 + 31) / 32 : (D.n + 31) / 32;
-    for (int blk = 0; blk < nblocks; ++blk) {
-        int c;
-        uint32_t miss = 0;
-        int first = 0;
-        if (PACKED) {
-            int wi = blk * 32 + lane;
-            uint32_t w = 0xFFFFFFFFu;
-            if (wi < (D.n_file + 15) / 16)
-                w = ((const uint32_t *)rowp)[wi] | ((const uint32_t *)D.ormask)[wi];
-            miss = w & ~(w >> 1) & 0x55555555u;
-            c = __popc(miss);
-            first = wi * 16;
-        } else {
-            int i = blk * 32 + lane;
-            double g = (i < D.n) ? ((const double *)rowp)[i] : 0.0;
-            c = (g != g) ? 1 : 0;
-            first = i;
-        }
-        unsigned any = __ballot_sync(GT_FULL, c > 0);
-        if (!any) continue;
-        int off = c;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            int t = __shfl_up_sync(GT_FULL, off, o);
-            if (lane >= o) off += t;
-        }
-        int total = __shfl_sync(GT_FULL, off, 31);
-        off -= c;
-        if (PACKED) {
-            while (miss) {
-                int b = __ffs(miss) - 1;
-                queue[qn + off++] = first + (b >> 1);
-                miss &= miss - 1;
-            }
-        } else if (c) {
-            queue[qn + off] = first;
-        }
-        qn += total;
-        __syncwarp();
-        drain();
-    }
-    if (qn > 0) process(queue, qn);
+__device__ __forceinline__ void dmma884_lin(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-template <bool PACKED>
+// Subtract sum over the missing samples of v v' from S0 (one warp).
+// PACKED: row = 2-bit codes OR-ed with the design mask; else doubles with NaN.
+// Missing samples are compacted 32 at a time (ballot ranking), their base
+// vectors gathered into a shared staging tile, and the outer products
+// accumulated with FP64 tensor-core MMAs (m8n8k4, upper tiles only).
+template <bool PACKED, int NT2>
+__device__ __forceinline__ void subtract_missing(const GtDesignDev &D, const void *rowp,
+                                                 double *S0, double *stage, int *queue,
+                                                 int lane) {
+    constexpr int LS = finish_stage_stride(NT2);
+    const int L = D.L;
+    const int nlive = D.lean ? D.k + 1 : L;      // columns present in E
+    double acc[NT2][NT2][2];
+#pragma unroll
+    for (int a = 0; a < NT2; ++a)
+#pragma unroll
+        for (int b = 0; b < NT2; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+    int qn = 0;
+    const unsigned lt_mask = (1u << lane) - 1u;
+
+    auto process = [&](int count) {     // entries queue[0 .. count), count <= 32
+        int idx = (lane < count) ? queue[lane] : -1;
+        double *sr = stage + lane * LS;
+        if (idx >= 0) {
+            // E rows are 16 B aligned (NCP even), staging rows too (LS even)
+            const double2 *er = (const double2 *)(D.E + (long long)idx * D.NCP);
+            double2 *s2 = (double2 *)sr;
+            for (int c = 0; c < (nlive + 1) / 2; ++c) s2[c] = er[c];
+            if (!D.lean && (nlive & 1)) sr[nlive] = 0.0;    // keep the padding column zero
+            if (D.lean) sr[D.k + 1] = 1.0;
+        } else {
+            for (int c = 0; c < L; ++c) sr[c] = 0.0;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+            const int e = ks * 4 + (lane & 3), c = lane >> 2;
+            double f[NT2];
+#pragma unroll
+            for (int t = 0; t < NT2; ++t) f[t] = stage[e * LS + t * 8 + c];
+#pragma unroll
+            for (int mt = 0; mt < NT2; ++mt)
+#pragma unroll
+                for (int nt = mt; nt < NT2; ++nt)
+                    dmma884_lin(acc[mt][nt][0], acc[mt][nt][1], f[mt], f[nt]);
+        }
+        __syncwarp();
+    };
+    auto push_round = [&](bool have, int idx) {
+        unsigned has = __ballot_sync(GT_FULL, have);
+        if (have) queue[qn + __popc(has & lt_mask)] = idx;
+        qn += __popc(has);
+        __syncwarp();
+        if (qn >= 32) {
+            process(32);
+            int rem = qn - 32;
+            int v = (lane < rem) ? queue[32 + lane] : 0;
+            __syncwarp();
+            if (lane < rem) queue[lane] = v;
+            qn = rem;
+            __syncwarp();
+        }
+        return has;
+    };
+
+    if (PACKED) {
+        const int nwords = (D.n_file + 15) / 16;         // 32-bit words of 16 samples
+        const int nblocks = (nwords + 127) / 128;        // 4 words (64 samples) per lane
+        const uint4 *row4 = (const uint4 *)rowp;
+        const uint4 *mask4 = (const uint4 *)D.ormask;
+        auto fetch = [&](int blk) {
+            uint4 w = make_uint4(~0u, ~0u, ~0u, ~0u);
+            if (blk < nblocks && (blk * 32 + lane) * 4 < nwords) {   // rows are 16 B padded
+                uint4 r = row4[blk * 32 + lane], m = mask4[blk * 32 + lane];
+                w = make_uint4(r.x | m.x, r.y | m.y, r.z | m.z, r.w | m.w);
+            }
+            return w;
+        };
+        uint4 nxt = fetch(0);
+        for (int blk = 0; blk < nblocks; ++blk) {
+            const uint4 w = nxt;
+            nxt = fetch(blk + 1);                 // prefetch: hides the DRAM latency of the scan
+            unsigned long long lo = (unsigned long long)(w.x & ~(w.x >> 1) & 0x55555555u) |
+                                    ((unsigned long long)(w.y & ~(w.y >> 1) & 0x55555555u) << 32);
+            unsigned long long hi = (unsigned long long)(w.z & ~(w.z >> 1) & 0x55555555u) |
+                                    ((unsigned long long)(w.w & ~(w.w >> 1) & 0x55555555u) << 32);
+            const int base = (blk * 32 + lane) * 64;
+            if (!__any_sync(GT_FULL, (lo | hi) != 0ull)) continue;
+            while (true) {
+                bool have = (lo | hi) != 0ull;
+                int idx = 0;
+                if (lo) { int b = __ffsll((long long)lo) - 1; idx = base + (b >> 1); lo &= lo - 1; }
+                else if (hi) { int b = __ffsll((long long)hi) - 1; idx = base + 32 + (b >> 1); hi &= hi - 1; }
+                if (!push_round(have, idx)) break;
+            }
+        }
+    } else {
+        const int nblocks = (D.n + 31) / 32;
+        for (int blk = 0; blk < nblocks; ++blk) {
+            int i = blk * 32 + lane;
+            double g = (i < D.n) ? ((const double *)rowp)[i] : 0.0;
+            push_round(g != g, i);
+        }
+    }
+    if (qn > 0) process(qn);
+    __syncwarp();
+#pragma unroll
+    for (int mt = 0; mt < NT2; ++mt)
+#pragma unroll
+        for (int nt = mt; nt < NT2; ++nt)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                int r = mt * 8 + (lane >> 2), c = nt * 8 + 2 * (lane & 3) + j;
+                if (r < L && c < L && r <= c) {
+                    double v = acc[mt][nt][j];
+                    S0[r * L + c] -= v;
+                    if (r != c) S0[c * L + r] -= v;
+                }
+            }
+    __syncwarp();
+}
+
+template <bool PACKED, int NT2>
 __global__ void __launch_bounds__(256)
 linear_finish_kernel(GtDesignDev D, const void *__restrict__ geno, long long pitch, int n_snps,
                      const double *__restrict__ S, const int *__restrict__ counts,
+                     const double *__restrict__ gsum,
                      double *__restrict__ out, int *__restrict__ iout, long long ostride,
                      int wpc) {
     extern __shared__ __align__(16) double sm[];
@@ -149,15 +204,6 @@ linear_finish_kernel(GtDesignDev D, const void *__restrict__ geno, long long pit
     const int iy = k, i1 = k + 1;
     const int nf = GT_F_PARAM0 + 6 * p;
     const FinishLayout lay = finish_layout(L, p, I);
-
-    // product index table (shared by the CTA)
-    unsigned char *pa = (unsigned char *)(sm + (size_t)wpc * lay.perWarp);
-    unsigned char *pb = pa + D.NPROD;
-    for (int a = threadIdx.x; a < L; a += blockDim.x) {
-        int base = a * L - a * (a - 1) / 2;   // products (a, a..L-1)
-        for (int b = a; b < L; ++b) { pa[base + b - a] = (unsigned char)a; pb[base + b - a] = (unsigned char)b; }
-    }
-    __syncthreads();
 
     const int snp = blockIdx.x * wpc + warp;
     if (warp >= wpc || snp >= n_snps) return;
@@ -172,6 +218,7 @@ linear_finish_kernel(GtDesignDev D, const void *__restrict__ geno, long long pit
     int *queue = (int *)(W + lay.oQueue);
 
     for (int t = lane; t < L * L; t += 32) S0[t] = D.FF0[t];
+    for (int t = lane; t < 32 * finish_stage_stride(NT2); t += 32) stage[t] = 0.0;
     __syncwarp();
 
     const int n_het = counts[(long long)snp * 4 + 0];
@@ -180,17 +227,23 @@ linear_finish_kernel(GtDesignDev D, const void *__restrict__ geno, long long pit
     if (n_miss > 0) {
         const void *rowp = PACKED ? (const void *)((const uint8_t *)geno + (long long)snp * pitch)
                                   : (const void *)((const double *)geno + (long long)snp * pitch);
-        subtract_missing<PACKED>(D, rowp, S0, stage, queue, pa, pb, lane);
+        subtract_missing<PACKED, NT2>(D, rowp, S0, stage, queue, lane);
     }
     __syncwarp();
 
     const double *Ssnp = S + (long long)snp * D.NCP;
-    for (int t = lane; t < (I + 1) * L; t += 32) S1[t] = Ssnp[t];
-    for (int t = lane; t < (I + 1) * (I + 1); t += 32) {
-        int a = t / (I + 1), b = t % (I + 1);
-        int lo = a < b ? a : b, hi = a < b ? b : a;
-        int idx = lo * (I + 1) - lo * (lo - 1) / 2 + (hi - lo);
-        S2[t] = Ssnp[D.NCA + idx];
+    const double sum_g_all = gsum[(long long)snp * 2], sum_g2_all = gsum[(long long)snp * 2 + 1];
+    if (D.lean) {      // E carries [q | y] only; sum g, sum g^2 come from the counts
+        for (int t = lane; t < L; t += 32) S1[t] = (t <= k) ? Ssnp[t] : sum_g_all;
+        if (lane == 0) S2[0] = sum_g2_all;
+    } else {
+        for (int t = lane; t < (I + 1) * L; t += 32) S1[t] = Ssnp[t];
+        for (int t = lane; t < (I + 1) * (I + 1); t += 32) {
+            int a = t / (I + 1), b = t % (I + 1);
+            int lo = a < b ? a : b, hi = a < b ? b : a;
+            int idx = lo * (I + 1) - lo * (lo - 1) / 2 + (hi - lo);
+            S2[t] = Ssnp[D.NCA + idx];
+        }
     }
     __syncwarp();
 
@@ -203,7 +256,7 @@ linear_finish_kernel(GtDesignDev D, const void *__restrict__ geno, long long pit
     double maf = nan("");
     int flip = 0;
     if (!D.raw_mode) {
-        double sum_g = PACKED ? (double)(n_het + 2 * n_hom) : S1[i1];
+        double sum_g = sum_g_all;
         maf = (sum_g / (double)nj) / 2.0;
         if (maf > 0.5) { maf = 1.0 - maf; flip = 1; }
         if (D.use_maf_t && maf < D.maf_t) {
