@@ -1,0 +1,566 @@
+"""Run a statistical analysis (``genetest/analysis.py``).
+
+``execute`` keeps the reference's entry point and call protocol
+(``analysis.py:230-325``); the GWAS branch (``_execute_gwas``, reference
+``analysis.py:593-728`` + ``_gwas_worker`` ``:68-205``) no longer spawns worker
+processes that refit statsmodels one marker at a time: markers are streamed
+in batches to the B200 engine (``genetest_b200.engine``), which applies the
+complete-case mask, MAF, flip, interaction columns and the fit for every
+marker of the batch, and comes back with fixed-size result blocks that are
+turned into the reference's per-marker dictionaries for the subscribers.
+
+Under ``torchrun`` (one process per GPU) every rank analyses a contiguous
+range of the markers and rank 0 gathers the result blocks (NCCL) and drives
+the subscribers -- there is no other communication.
+"""
+
+import itertools
+import logging
+
+import numpy as np
+import pandas as pd
+
+from . import sharding
+from . import subscribers as subscribers_module
+from .engine import get_engine
+from .modelspec import PheWAS, SNPs, modelspec_from_formula
+from .statistics.core import StatsError
+from .statistics.descriptive import get_maf, get_sex_maf
+from .statistics.models._single import failure_reason
+from .statistics.models.survival import cox_param_dict
+
+logger = logging.getLogger(__name__)
+
+PARAM_FIELDS = ("coef", "std_err", "lower_ci", "upper_ci", "t_value",
+                "p_value")
+
+#: markers per engine call (bounds host staging memory)
+BATCH_SNPS = 65536
+
+
+def _missing(y, X):
+    """Boolean vector of the rows without any missing value."""
+    return ~(y.isnull().any(axis=1) | X.isnull().any(axis=1))
+
+
+def _generate_sample_order(x_samples, geno_samples):
+    """Positions (in the genotype container's sample order) of the samples
+    that are rows of X, and their labels (``analysis.py:43-65``)."""
+    in_x = set(x_samples)
+    geno_order = np.array(
+        [i for i, s in enumerate(geno_samples) if s in in_x], dtype=int)
+    x_order = np.asarray(geno_samples, dtype=object)[geno_order]
+    if pd.Index(x_samples).duplicated().any():
+        raise NotImplementedError(
+            "repeated measurements (duplicated samples) are only used by "
+            "mixedlm, which is outside the B200 hot path")
+    return geno_order, x_order
+
+
+def execute_formula(phenotypes, genotypes, formula, test, test_kwargs=None,
+                    subscribers=None, variant_predicates=None,
+                    output_prefix=None, maf_t=None, cpus=None,
+                    sexual_chromosome=False):
+    modelspec, subgroups = modelspec_from_formula(formula, test, test_kwargs)
+    execute(phenotypes, genotypes, modelspec, subscribers, variant_predicates,
+            output_prefix, subgroups, maf_t, cpus, sexual_chromosome)
+
+
+def execute(phenotypes, genotypes, modelspec, subscribers=None,
+            variant_predicates=None, output_prefix=None, subgroups=None,
+            maf_t=None, cpus=None, sexual_chromosome=False):
+    """Execute an analysis.
+
+    Args:
+        phenotypes: the phenotypes container.
+        genotypes: the genotypes container (geneparse-like reader).
+        modelspec (ModelSpec): the model specification.
+        subscribers (list): result sinks (default: ``Print()``).
+        variant_predicates (list): callables ``f(snp) -> bool``.
+        output_prefix (str): prefix of the failed / skipped marker files.
+        subgroups (list): levels of the stratification variables.
+        maf_t (float): MAF threshold.
+        cpus (int): kept for compatibility; the GPU engine ignores it.
+        sexual_chromosome (bool): sex-aware MAF.
+    """
+    if subscribers is None:
+        subscribers = [subscribers_module.Print()]
+    for subscriber in subscribers:
+        subscriber.init(modelspec)
+    if variant_predicates is None:
+        variant_predicates = []
+
+    if isinstance(modelspec.outcome, PheWAS):
+        raise NotImplementedError(
+            "pheWAS analyses are outside the B200 hot path (per-SNP "
+            "association loop)")
+
+    data = modelspec.create_data_matrix(phenotypes, genotypes)
+    data = data.dropna()            # missing outcome or covariable
+
+    y_cols = tuple(modelspec.outcome.keys())
+    y = data[[modelspec.outcome[col].id for col in y_cols]]
+    X = data.drop(y.columns, axis=1)
+    y.columns = y_cols
+
+    bad_cols = _get_uninformative_factors(X, modelspec)
+    if len(bad_cols):
+        logger.info("After removing missing values, dropping ({}) factor "
+                    "levels that have no variation.".format(len(bad_cols)))
+        X = X.drop(bad_cols, axis=1)
+
+    messages = {"skipped": [], "failed": []}
+
+    sample_sex = None
+    if sexual_chromosome:
+        logger.info("Analysis is performed on a sexual chromosome")
+        sample_sex = phenotypes.get_sex()
+
+    if modelspec.stratify_by is not None:
+        _execute_stratified(genotypes, modelspec, subscribers, y, X,
+                            variant_predicates, subgroups, messages, maf_t,
+                            cpus, sample_sex)
+    elif SNPs in modelspec.predictors:
+        _execute_gwas(genotypes, modelspec, subscribers, y, X,
+                      variant_predicates, messages, maf_t, cpus, sample_sex)
+    else:
+        _execute_simple(modelspec, subscribers, y, X, variant_predicates,
+                        messages)
+
+    for subscriber in subscribers:
+        subscriber.close()
+
+    if not sharding.is_primary():
+        return
+    prefix = (output_prefix + "_") if output_prefix is not None else ""
+    if messages["failed"]:
+        with open(prefix + "failed_snps.txt", "w") as f:
+            for name, reason in messages["failed"]:
+                f.write("{}\t{}\n".format(name, reason))
+    if messages["skipped"]:
+        with open(prefix + "not_analyzed_snps.txt", "w") as f:
+            for name in messages["skipped"]:
+                f.write("{}\n".format(name))
+
+
+def _get_uninformative_factors(df, modelspec):
+    """Factor-level columns that are all zero (no sample has the level)."""
+    factor_ids = [t[2].id for t in modelspec.transformations
+                  if t[0] == "ENCODE_FACTOR"]
+    zero = df.columns[df.sum() == 0]
+    return [c for c in zero if any(c.startswith(f) for f in factor_ids)]
+
+
+def _execute_simple(modelspec, subscribers, y, X, variant_predicates,
+                    messages):
+    """A single fit (no marker loop)."""
+    if len(variant_predicates) != 0:
+        logger.warning("Variant predicates are only used for GWAS analyses.")
+    test = modelspec.test()
+    logger.info("Executing {} - Design matrix has shape: {}".format(
+        test, X.shape))
+    results = test.fit(y, X)
+    for entity in results:
+        if entity in modelspec.variant_metadata:
+            results[entity].update(modelspec.variant_metadata[entity])
+    for subscriber in subscribers:
+        try:
+            subscriber.handle(results)
+        except KeyError as e:
+            return subscribers_module.subscriber_error(e.args[0])
+
+
+def _execute_stratified(genotypes, modelspec, subscribers, y, X,
+                        variant_predicates, subgroups, messages, maf_t=None,
+                        cpus=None, sample_sex=None):
+    """One analysis per combination of the stratification levels."""
+    assert len(modelspec.stratify_by) == len(subgroups)
+    var_levels = []
+    for var, subgroup in zip(modelspec.stratify_by, subgroups):
+        if subgroup is None:
+            var_levels.append(X[var.id].dropna().unique())
+        elif hasattr(subgroup, "__iter__") and type(subgroup) is not str:
+            var_levels.append(subgroup)
+        else:
+            var_levels.append([subgroup])
+
+    gwas_mode = SNPs in modelspec.predictors
+    translations = modelspec.get_translations()
+    strat_ids = [v.id for v in modelspec.stratify_by]
+
+    for levels in itertools.product(*var_levels):
+        current = list(zip(modelspec.stratify_by, levels))
+        idx = np.logical_and.reduce(
+            [X[var.id] == level for var, level in current])
+        subset_info = {translations[var.id]: level for var, level in current}
+        for sub in subscribers:
+            sub._update_current_subset(subset_info)
+
+        this_x = X.loc[idx, :]
+        bad_cols = _get_uninformative_factors(this_x, modelspec)
+        this_x = this_x.drop(bad_cols, axis=1).drop(strat_ids, axis=1)
+        logger.info("Analysing subgroup {}".format(";".join(
+            "{}:{}".format(*kv) for kv in sorted(subset_info.items()))))
+
+        if this_x.shape[0] == 0:
+            observed = {translations[var.id]: list(X[var.id].dropna().unique())
+                        for var in modelspec.stratify_by}
+            raise ValueError(
+                "No samples left in subgroup analysis ({}). Are all requested "
+                "levels valid?\nThe observed levels are: {}".format(
+                    subset_info, observed))
+        if this_x.shape[1] == 0:
+            raise ValueError(
+                "No columns left in subgroup analysis ({}). Maybe there are "
+                "no samples with non-null values in the requested subgroup."
+                .format(subset_info))
+        if len(bad_cols):
+            logger.info("After stratification, dropping factor levels ({}) "
+                        "that have no variation ".format(len(bad_cols)))
+
+        if gwas_mode:
+            _execute_gwas(genotypes, modelspec, subscribers, y.loc[idx, :],
+                          this_x, variant_predicates, messages, maf_t, cpus,
+                          sample_sex)
+        else:
+            _execute_simple(modelspec, subscribers, y.loc[idx, :], this_x,
+                            variant_predicates, messages)
+
+
+# --------------------------------------------------------------------------
+# the GWAS branch
+# --------------------------------------------------------------------------
+class ResultBlock(object):
+    """Result blocks of a batch of markers plus their metadata; turns rows
+    into the reference's result dictionaries on demand."""
+
+    def __init__(self, model, columns, res, meta, maf_t):
+        self.model = model
+        self.columns = columns          # design columns in fit() order
+        self.res = res                  # engine.Results
+        self.meta = meta                # [(name, chrom, pos, coded, reference)]
+        self.maf_t = maf_t
+
+    def __len__(self):
+        return len(self.meta)
+
+    def ok(self, i):
+        return self.res.status[i] == 0
+
+    def reason(self, i):
+        return failure_reason(self.res, i, self.maf_t)
+
+    def to_dict(self, i):
+        """The dictionary ``Stats*.fit`` + ``_gwas_worker`` build for one
+        marker (``linear.py:64-89`` / ``logistic.py:49-72`` /
+        ``survival.py:100-120``, then ``analysis.py:191-195``)."""
+        res = self.res
+        name, chrom, pos, coded, reference = self.meta[i]
+        if self.model == "linear":
+            out = {"MODEL": {"r_squared_adj": float(res.stat[i]),
+                             "log_likelihood": float(res.llf[i]),
+                             "nobs": float(res.nobs[i])}}
+        elif self.model == "logistic":
+            out = {"MODEL": {"log_likelihood": float(res.llf[i]),
+                             "nobs": float(res.nobs[i]),
+                             "nevents": res.stat[i]}}
+        else:
+            out = {"MODEL": {"log_likelihood": float(res.llf[i]),
+                             "nobs": int(res.nobs[i]),
+                             "nevents": res.stat[i]}}
+        for j, col in enumerate(self.columns):
+            vals = res.param(j)[:, i]
+            if self.model == "coxph":
+                out[col] = cox_param_dict(vals)
+            else:
+                out[col] = {f: float(v) for f, v in zip(PARAM_FIELDS, vals)}
+        flip = bool(res.flip[i])
+        out["SNPs"].update({
+            "chrom": str(chrom), "pos": pos,
+            "major": coded if flip else reference,
+            "minor": reference if flip else coded, "name": name,
+        })
+        out["SNPs"]["maf"] = float(res.maf[i])
+        return out
+
+
+def _dispatch_block(block, subscribers, messages):
+    for i in range(len(block)):
+        if not block.ok(i):
+            reason = block.reason(i)
+            name = block.meta[i][0]
+            logger.warning("{}: {}".format(name, reason))
+            if name:
+                messages["failed"].append((name, reason))
+            continue
+        results = block.to_dict(i)
+        for subscriber in subscribers:
+            try:
+                subscriber.handle(results)
+            except KeyError as e:
+                subscribers_module.subscriber_error(e.args[0])
+
+
+def _host_fit_loop(genotypes, test, subscribers, y, X, variant_predicates,
+                   messages, maf_t, gwas_interaction, sample_sex):
+    """Plugin path for user-supplied tests without a batched kernel: the
+    reference's loop body, one ``fit`` call per marker, in this process."""
+    samples = genotypes.get_samples()
+    geno_index, sample_order = _generate_sample_order(X.index, samples)
+    if geno_index.shape[0] == 0:
+        raise RuntimeError("Genotype and phenotype data have "
+                           "non-overlapping indices.")
+    X = X.copy()
+    for snp in genotypes.iter_genotypes():
+        try:
+            if not all([f(snp) for f in variant_predicates]):
+                messages["skipped"].append(snp.variant.name)
+                continue
+        except StopIteration:
+            break
+        X["SNPs"] = np.nan
+        if gwas_interaction:
+            X = X.drop(list(gwas_interaction.keys()), axis=1, errors="ignore")
+        X.loc[sample_order, "SNPs"] = snp.genotypes[geno_index]
+        not_missing = _missing(y, X)
+        if np.sum(not_missing) == 0:
+            messages["failed"].append((snp.variant.name,
+                                       "All genotypes are missing"))
+            continue
+        if sample_sex is None:
+            maf, minor, major, flip = get_maf(
+                X.loc[not_missing, "SNPs"], snp.coded, snp.reference)
+        else:
+            ids = X.index[not_missing]
+            maf, minor, major, flip = get_sex_maf(
+                X.loc[ids, "SNPs"], sample_sex.reindex(ids), snp.coded,
+                snp.reference)
+        if maf_t is not None and maf < maf_t:
+            messages["failed"].append(
+                (snp.variant.name, "MAF: {} < {}".format(maf, maf_t)))
+            continue
+        if flip:
+            X["SNPs"] = 2 - X["SNPs"]
+        if gwas_interaction:
+            for key, cols in gwas_interaction.items():
+                col = X["SNPs"].copy()
+                for c in cols:
+                    col = col * X[c]
+                X[key] = col
+        try:
+            results = test.fit(y[not_missing], X[not_missing])
+        except StatsError as e:
+            logger.warning("{}: {}".format(snp.variant.name, e))
+            if snp.variant.name:
+                messages["failed"].append((snp.variant.name, str(e)))
+            continue
+        results["SNPs"].update({
+            "chrom": str(snp.variant.chrom), "pos": snp.variant.pos,
+            "major": major, "minor": minor, "name": snp.variant.name,
+        })
+        results["SNPs"]["maf"] = maf
+        for subscriber in subscribers:
+            try:
+                subscriber.handle(results)
+            except KeyError as e:
+                subscribers_module.subscriber_error(e.args[0])
+
+
+def _integer_valued(block):
+    ok = ~np.isnan(block)
+    v = block[ok]
+    return bool(np.all((v == 0) | (v == 1) | (v == 2)))
+
+
+def _execute_gwas(genotypes, modelspec, subscribers, y, X, variant_predicates,
+                  messages, maf_t=None, cpus=None, sample_sex=None):
+    gwas_interaction = None
+    if modelspec.has_gwas_interaction:
+        gwas_interaction = modelspec.gwas_interaction
+        for subscriber in subscribers:
+            subscriber._update_gwas_interaction(
+                list(sorted(gwas_interaction.keys())))
+
+    test = modelspec.test()
+    model = getattr(test, "gwas_model", None)
+    if model is None:
+        logger.info("{} has no batched kernel: fitting on the host, one "
+                    "marker at a time".format(test))
+        return _host_fit_loop(genotypes, test, subscribers, y, X,
+                              variant_predicates, messages, maf_t,
+                              gwas_interaction, sample_sex)
+    if sample_sex is not None:
+        raise NotImplementedError(
+            "sexual_chromosome=True (sex-aware MAF) is not implemented on "
+            "the B200 engine yet")
+
+    # ---- sample alignment (analysis.py:43-65, 97-116) ----
+    samples = list(genotypes.get_samples())
+    geno_index, sample_order = _generate_sample_order(X.index, samples)
+    if geno_index.shape[0] == 0:
+        logger.critical("Genotype and phenotype data have non-overlapping "
+                        "indices.")
+        raise RuntimeError("Exception raised in worker processes")
+    # design rows in genotype-file order; phenotype-only samples would be
+    # all-NaN for every marker and never enter a fit
+    Xd = X.loc[sample_order, :]
+    yd = y.loc[sample_order, :]
+    n_file = len(samples)
+
+    columns = list(Xd.columns)
+    W = None
+    inter_keys = []
+    if gwas_interaction:
+        inter_keys = list(gwas_interaction.keys())
+        W = np.column_stack([
+            np.prod(Xd[list(cols)].values.astype(float), axis=1)
+            for cols in gwas_interaction.values()])
+
+    options = dict(test.gwas_options())
+    if model == "coxph":
+        if "strata" in yd.columns:
+            raise NotImplementedError("stratified Cox models are not "
+                                      "supported by the B200 engine")
+        if "intercept" in columns:
+            columns.remove("intercept")
+        C = Xd[columns].values.astype(float)
+        y_main = yd["tte"].values.astype(float)
+        event = yd["event"].values.astype(float)
+    else:
+        C = Xd[columns].values.astype(float)
+        y_main = yd.iloc[:, 0].values.astype(float)
+        event = None
+    fit_columns = columns + ["SNPs"] + inter_keys
+
+    rank, world = sharding.rank_world()
+    eng = get_engine(sharding.local_device())
+    eng.set_design(model, y_main, C, W=W, event=event,
+                   sample_pos=geno_index.astype(np.int32), n_file=n_file,
+                   maf_t=maf_t, **options)
+
+    names_only = all(isinstance(f, _name_filter_type())
+                     for f in variant_predicates)
+    if hasattr(genotypes, "packed") and names_only:
+        blocks = _packed_blocks(genotypes, eng, variant_predicates, messages,
+                                rank, world)
+    else:
+        blocks = _decoded_blocks(genotypes, eng, variant_predicates, messages,
+                                 geno_index, rank, world)
+
+    def consume(res, meta):
+        block = ResultBlock(model, fit_columns, res, meta, maf_t)
+        for s in subscribers:
+            if hasattr(s, "handle_block"):
+                s.handle_block(block)
+        _dispatch_block(
+            block, [s for s in subscribers if not hasattr(s, "handle_block")],
+            messages)
+
+    if world == 1:
+        for res, meta in blocks:            # stream batch by batch
+            if res is not None:
+                consume(res, meta)
+    else:
+        # every rank finishes its range, then ONE gather of the fixed-size
+        # result blocks to rank 0 (the only collective of the analysis)
+        from .engine import Results, NUM_IFIELDS
+        parts = [(r, m) for r, m in blocks if r is not None]
+        meta = [x for _r, m in parts for x in m]
+        if parts:
+            res = Results(np.concatenate([r.out for r, _m in parts], axis=1),
+                          np.concatenate([r.iout for r, _m in parts], axis=1),
+                          eng.n_params)
+        else:
+            res = Results(np.zeros((eng.n_fields, 0)),
+                          np.zeros((NUM_IFIELDS, 0), dtype=np.int32),
+                          eng.n_params)
+        res, meta = sharding.gather_results(res, meta)
+        if sharding.is_primary() and len(meta):
+            consume(res, meta)
+    logger.info("Analysis completed")
+
+
+def _name_filter_type():
+    from .modelspec.predicates import NameFilter
+    return NameFilter
+
+
+def _packed_blocks(reader, eng, predicates, messages, rank, world):
+    """Fast path: the reader exposes SNP-major 2-bit rows (PLINK .bed)."""
+    table = reader.variant_table()
+    keep = np.ones(len(table), dtype=bool)
+    for f in predicates:
+        keep &= np.array([t[0] in f.extract for t in table], dtype=bool)
+    if rank == 0:
+        messages["skipped"].extend(
+            t[0] for t, k in zip(table, keep) if not k)
+    idx = np.flatnonzero(keep)
+    lo, hi = sharding.shard_range(len(idx), world, rank)
+    idx = idx[lo:hi]
+    packed = reader.packed()
+    for s in range(0, len(idx), BATCH_SNPS):
+        sel = idx[s:s + BATCH_SNPS]
+        if len(sel) and sel[-1] - sel[0] + 1 == len(sel):
+            rows = packed[sel[0]:sel[-1] + 1]          # contiguous: no copy
+        else:
+            rows = packed[sel]
+        res = eng.run_packed_host(np.ascontiguousarray(rows))
+        meta = [table[i] for i in sel]
+        yield res, meta
+    if len(idx) == 0:
+        yield None, []
+
+
+def _decoded_blocks(reader, eng, predicates, messages, geno_index, rank,
+                    world):
+    """Generic path: any geneparse-like reader, decoded on the host.
+    Integer-valued batches are re-packed to 2 bits, anything else goes to the
+    engine as FP64 dosages aligned to the design rows."""
+    n_file = len(reader.get_samples())
+    rows, meta = [], []
+
+    def flush():
+        block = np.vstack(rows)
+        if _integer_valued(block):
+            from .genotypes.plink import pack_rows
+            res = eng.run_packed_host(pack_rows(block))
+        else:
+            res = eng.run_dosage_host(
+                np.ascontiguousarray(block[:, geno_index]))
+        out = (res, list(meta))
+        del rows[:], meta[:]
+        return out
+
+    count = -1
+    total = None
+    if world > 1:
+        total = reader.get_number_variants()
+    lo, hi = (0, None) if world == 1 else sharding.shard_range(total, world,
+                                                              rank)
+    any_block = False
+    for snp in reader.iter_genotypes():
+        count += 1
+        try:
+            if not all([f(snp) for f in predicates]):
+                if rank == 0:
+                    messages["skipped"].append(snp.variant.name)
+                continue
+        except StopIteration:
+            break
+        if count < lo or (hi is not None and count >= hi):
+            continue
+        g = np.asarray(snp.genotypes, dtype=float)
+        if g.shape[0] != n_file:
+            raise ValueError("{}: {} genotypes for {} samples".format(
+                snp.variant.name, g.shape[0], n_file))
+        rows.append(g)
+        meta.append((snp.variant.name, snp.variant.chrom, snp.variant.pos,
+                     snp.coded, snp.reference))
+        if len(rows) >= 8192:
+            any_block = True
+            yield flush()
+    if rows:
+        any_block = True
+        yield flush()
+    if not any_block:
+        yield None, []

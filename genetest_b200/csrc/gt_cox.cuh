@@ -9,6 +9,7 @@
 #include "gt_common.cuh"
 #include "gt_host.cuh"
 #include "gt_logistic.cuh"
+#include "gt_coxk.cuh"
 
 namespace gtk {
 
@@ -20,12 +21,9 @@ static int iter_set_design(const gt_design_desc *d, const std::vector<int> &pos,
     const int n = d->n, k = d->k, I = d->n_inter;
     const int p = k + 1 + I;
     if (p > 23) return fail(GT_E_UNSUPPORTED, "iterative models support at most 23 design columns (got %d)", p);
-    if (d->model == GT_MODEL_COXPH)
-        return fail(GT_E_UNSUPPORTED, "coxph kernel not built in this revision");
     HostDesign H;
     H.n = n; H.k = k; H.I = I;
     qr_mgs2(d->C, n, k, H);
-    if (H.degenerate) return fail(GT_E_UNSUPPORTED, "covariates are rank deficient (logistic / coxph need a full-rank design)");
     const size_t n_pad = (size_t)n_chunks * 256;
     const int XS = (k + I + 1) & ~1;
     const int XSs = XS > 0 ? XS : 2;
@@ -39,12 +37,82 @@ static int iter_set_design(const gt_design_desc *d, const std::vector<int> &pos,
         y[pos[i]] = d->y[i];
     }
     for (int t = 0; t < k * k; ++t) Rinv[t] = H.Rinv[t];
+    // coxph: schedule in descending time, tie groups inside 32-slot blocks
+    std::vector<int> slot_pos, slot_info;
+    std::vector<double> Xs;
+    if (d->model == GT_MODEL_COXPH) {
+        std::vector<int> order(n);
+        for (int i = 0; i < n; ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(),
+                         [&](int a, int b) { return d->y[a] > d->y[b]; });
+        int i0 = 0;
+        while (i0 < n) {
+            int i1 = i0;
+            while (i1 + 1 < n && d->y[order[i1 + 1]] == d->y[order[i0]]) ++i1;
+            int size = i1 - i0 + 1;
+            if (size > 32)
+                return fail(GT_E_UNSUPPORTED, "coxph: %d samples share one time; at most 32 tied samples are supported", size);
+            int fill = (int)(slot_pos.size() % 32);
+            if (fill + size > 32)
+                for (; fill < 32; ++fill) {      // pad: singleton empty slots
+                    slot_pos.push_back(-1);
+                    slot_info.push_back(fill | (fill << 5));
+                }
+            int la = (int)(slot_pos.size() % 32), lb = la + size - 1;
+            for (int t = i0; t <= i1; ++t) {
+                int row = order[t];
+                slot_pos.push_back(pos[row]);
+                int ev = d->event[row] != 0.0 ? 1 : 0;
+                slot_info.push_back(la | (lb << 5) | (ev << 10));
+            }
+            i0 = i1 + 1;
+        }
+        for (int fill = (int)(slot_pos.size() % 32); fill != 0 && fill < 32; ++fill) {
+            slot_pos.push_back(-1);
+            slot_info.push_back(fill | (fill << 5));
+        }
+        const size_t ns = slot_pos.size();
+        for (size_t b = 0; b < ns; b += 32) {
+            bool ties = false;
+            for (int t = 0; t < 32; ++t) ties |= ((slot_info[b + t] & 31) != ((slot_info[b + t] >> 5) & 31));
+            if (ties) for (int t = 0; t < 32; ++t) slot_info[b + t] |= 1 << 11;
+        }
+        Xs.assign(ns * XSs, 0.0);
+        // slot -> design row: rebuild from the sorted order
+        size_t s = 0;
+        std::vector<int> row_of_pos(n_file, -1);
+        for (int i = 0; i < n; ++i) row_of_pos[pos[i]] = i;
+        for (s = 0; s < ns; ++s) {
+            if (slot_pos[s] < 0) continue;
+            int row = row_of_pos[slot_pos[s]];
+            for (int j = 0; j < k; ++j) Xs[s * XSs + j] = H.Q[(size_t)j * n + row];
+            for (int j = 0; j < I; ++j) Xs[s * XSs + k + j] = d->W[(size_t)j * n + row];
+        }
+        // append: Xs | slot_pos | slot_info  (ints packed two per double)
+        size_t base = host.size();
+        host.resize(base + Xs.size() + ns + 2, 0.0);
+        std::memcpy(&host[base], Xs.data(), Xs.size() * 8);
+        int *ip = (int *)&host[base + Xs.size()];
+        std::memcpy(ip, slot_pos.data(), ns * 4);
+        std::memcpy(ip + ns, slot_info.data(), ns * 4);
+        // pointers may have moved
+        X = host.data(); y = X + n_pad * XSs; Rinv = y + n_pad;
+        T.n_slots = (int)ns;
+    }
     int rc = upload(buf, host.data(), host.size() * 8, st);
     if (rc) return rc;
     T.n_file = n_file; T.n = n; T.k = k; T.I = I; T.p = p; T.XS = XSs; T.n_pad = (int)n_pad;
     T.raw_mode = d->raw_mode; T.use_maf_t = d->use_maf_t; T.maf_t = d->maf_t;
+    T.degenerate = H.degenerate ? 1 : 0;
     T.X = (const double *)buf.p; T.y = T.X + n_pad * XSs; T.Rinv = T.y + n_pad;
-    T.order = nullptr; T.group_end = nullptr; T.tte = nullptr;
+    if (d->model == GT_MODEL_COXPH) {
+        const double *xs = T.Rinv + (size_t)k * k + 2;
+        T.Xs = xs;
+        T.slot_pos = (const int *)(xs + (size_t)T.n_slots * XSs);
+        T.slot_info = T.slot_pos + T.n_slots;
+    } else {
+        T.n_slots = 0; T.Xs = nullptr; T.slot_pos = nullptr; T.slot_info = nullptr;
+    }
     CK(cudaStreamSynchronize(st));
     return 0;
 }
@@ -63,16 +131,40 @@ static int launch_logistic(const IterDesignDev &T, const void *geno, int64_t pit
     return 0;
 }
 
+template <bool PACKED, int NT>
+static int launch_cox(const IterDesignDev &T, const void *geno, int64_t pitch, int n_snps,
+                      double *out, int32_t *iout, cudaStream_t st) {
+    using Cfg = CoxCfg<NT>;
+    int wpc = 8;
+    while (wpc > 1 && (size_t)wpc * Cfg::perWarp * 8 > 200 * 1024) wpc >>= 1;
+    size_t smem = (size_t)wpc * Cfg::perWarp * 8;
+    CK(cudaFuncSetAttribute((const void *)cox_newton_kernel<PACKED, NT>,
+                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cox_newton_kernel<PACKED, NT><<<(n_snps + wpc - 1) / wpc, wpc * 32, smem, st>>>(
+        T, geno, pitch, n_snps, out, iout, (long long)n_snps);
+    CK(cudaGetLastError());
+    return 0;
+}
+
 static int iter_run(const IterDesignDev &T, int model, const void *geno, int64_t pitch, bool packed,
                     int32_t n_snps, double *out, int32_t *iout, cudaStream_t st, bool timing,
                     const std::function<int()> &tbegin, const std::function<void(int)> &tend,
                     int64_t &all_launches, std::string &err) {
     (void)timing; (void)err;
-    if (model != GT_MODEL_LOGISTIC) return fail(GT_E_UNSUPPORTED, "coxph kernel not built in this revision");
     int NT = (T.p + 1 + 7) / 8;
     int slot = tbegin();
     int rc;
-    if (packed) {
+    if (model == GT_MODEL_COXPH) {
+        if (packed) {
+            rc = NT == 1 ? launch_cox<true, 1>(T, geno, pitch, n_snps, out, iout, st)
+               : NT == 2 ? launch_cox<true, 2>(T, geno, pitch, n_snps, out, iout, st)
+                         : launch_cox<true, 3>(T, geno, pitch, n_snps, out, iout, st);
+        } else {
+            rc = NT == 1 ? launch_cox<false, 1>(T, geno, pitch, n_snps, out, iout, st)
+               : NT == 2 ? launch_cox<false, 2>(T, geno, pitch, n_snps, out, iout, st)
+                         : launch_cox<false, 3>(T, geno, pitch, n_snps, out, iout, st);
+        }
+    } else if (packed) {
         rc = NT == 1 ? launch_logistic<true, 1>(T, geno, pitch, n_snps, out, iout, st)
            : NT == 2 ? launch_logistic<true, 2>(T, geno, pitch, n_snps, out, iout, st)
                      : launch_logistic<true, 3>(T, geno, pitch, n_snps, out, iout, st);

@@ -26,14 +26,18 @@ struct IterDesignDev {
     int XS;                 // row stride of X (doubles): k + I rounded up to even
     int n_pad;
     int raw_mode, use_maf_t;
+    int degenerate;         // covariates alone are rank deficient
     double maf_t;
     const double *X;        // [n_pad][XS]  q (k) | w (I), genotype-file order, zeros when excluded
     const double *y;        // [n_pad]      outcome / event, NaN = sample not in the design
     const double *Rinv;     // [k*k]
-    // coxph only: processing order = descending time
-    const int *order;       // [n] file position of the i-th sample in descending-time order
-    const int *group_end;   // [n] 1 when the tie group (same time) ends at this sample
-    const double *tte;
+    // coxph only: schedule in descending time, 32 slots per block, tie groups
+    // never straddle a block (host pads with empty slots)
+    int n_slots;
+    const int *slot_pos;    // [n_slots] genotype position of the slot's sample, -1 = empty
+    const int *slot_info;   // [n_slots] bits 0-4 first lane of the tie group, 5-9 last lane,
+                            //           bit 10 event, bit 11 block has a tie group
+    const double *Xs;       // [n_slots][XS] q | w in slot order
 };
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
@@ -122,6 +126,10 @@ logistic_irls_kernel(IterDesignDev T, const void *__restrict__ geno, long long p
         if (maf > 0.5) { maf = 1.0 - maf; flip = 1; }
         if (T.use_maf_t && maf < T.maf_t) { write_fail(GT_MAF_BELOW, flip, maf, maf, 0); return; }
     }
+
+    // rank-deficient covariates: statsmodels' pinv gives a zero standard error
+    // for the redundant direction -> NaN inference
+    if (T.degenerate) { write_fail(GT_NAN_PVALUE, flip, maf, nan(""), 0); return; }
 
     for (int t = lane; t < 2 * 32 * PS; t += 32) xs[t] = 0.0;   // xs and wxs (padding stays 0)
     for (int t = lane; t < PH; t += 32) beta[t] = 0.0;

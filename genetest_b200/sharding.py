@@ -1,0 +1,102 @@
+"""SNP-range sharding across the GPUs of one box.
+
+The reference's only parallelism is data parallelism over markers through
+worker processes and queues (``genetest/analysis.py:601-633``).  Here it is
+one process per GPU (``torchrun``); every rank owns a contiguous range of the
+markers, nothing is exchanged while computing, and the fixed-size result
+blocks are gathered on rank 0 at the end (NCCL on GPUs; gloo in the CPU
+tests).  No statistic spans markers, so no other collective exists.
+"""
+
+import os
+
+import numpy as np
+
+__all__ = ["rank_world", "is_primary", "local_device", "shard_range",
+           "gather_results", "gather_arrays"]
+
+
+def _dist():
+    try:
+        import torch.distributed as dist
+    except ImportError:         # pragma: no cover
+        return None
+    if dist.is_available() and dist.is_initialized():
+        return dist
+    return None
+
+
+def rank_world():
+    dist = _dist()
+    if dist is None:
+        return 0, 1
+    return dist.get_rank(), dist.get_world_size()
+
+
+def is_primary():
+    return rank_world()[0] == 0
+
+
+def local_device():
+    return int(os.environ.get("LOCAL_RANK", "0")) if _dist() else 0
+
+
+def shard_range(n, world, rank):
+    """Contiguous range [lo, hi) of ``n`` markers owned by ``rank``:
+    ``ceil(n / world)`` markers per rank, the last ranks may own fewer."""
+    per = -(-n // world) if world > 0 else n
+    lo = min(n, rank * per)
+    hi = min(n, lo + per)
+    return lo, hi
+
+
+def gather_arrays(arrays):
+    """Gather a list of ``[fields, n_local]`` numpy arrays on rank 0.
+
+    Every rank passes arrays with the same leading dimensions and dtypes;
+    ``n_local`` may differ.  Returns, on rank 0, the list of arrays
+    concatenated over ranks along the last axis (rank order), elsewhere None.
+    """
+    dist = _dist()
+    if dist is None:
+        return arrays
+    import torch
+    rank, world = dist.get_rank(), dist.get_world_size()
+    nccl = dist.get_backend() == "nccl"
+    dev = torch.device("cuda", local_device()) if nccl else torch.device("cpu")
+    n_local = arrays[0].shape[-1]
+    sizes = torch.zeros(world, dtype=torch.int64, device=dev)
+    sizes[rank] = n_local
+    dist.all_reduce(sizes)
+    sizes = [int(s) for s in sizes.cpu()]
+    n_max = max(sizes)
+    out = []
+    for a in arrays:
+        t = torch.zeros(a.shape[:-1] + (n_max,),
+                        dtype=torch.from_numpy(a[..., :0]).dtype, device=dev)
+        if n_local:
+            t[..., :n_local] = torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        bucket = [torch.empty_like(t) for _ in range(world)] \
+            if rank == 0 else None
+        dist.gather(t, bucket, dst=0)
+        if rank == 0:
+            out.append(np.concatenate(
+                [b[..., :s].cpu().numpy() for b, s in zip(bucket, sizes)],
+                axis=-1))
+    return out if rank == 0 else None
+
+
+def gather_results(res, meta):
+    """Result blocks + marker metadata of every rank -> rank 0."""
+    dist = _dist()
+    if dist is None:
+        return res, meta
+    from .engine import Results
+    rank, world = dist.get_rank(), dist.get_world_size()
+    gathered = gather_arrays([res.out, res.iout])
+    metas = [None] * world if rank == 0 else None
+    dist.gather_object(meta, metas, dst=0)
+    if rank != 0:
+        return None, None
+    return (Results(gathered[0], gathered[1], res.n_params),
+            [m for part in metas for m in part])

@@ -32,17 +32,33 @@ def failure_reason(res, i, maf_t=None):
 
 
 def fit_single(model, y_cols, X, options, device=0):
-    """Returns the engine Results for a one-marker raw-mode batch."""
-    cols = list(X.columns)
-    Xv = X.values.astype(float)
+    """One-marker raw-mode batch.  Returns ``(results, order)`` where
+    ``order[j]`` is the engine parameter index of column ``j`` of ``X``.
+
+    The column handed to the engine as "the marker" is the last
+    non-constant one, so that an intercept stays among the covariates (the
+    engine detects the constant there, as statsmodels' ``k_constant`` does).
+    """
+    Xv = np.ascontiguousarray(X.values, dtype=float)
+    p = Xv.shape[1]
+    marker = p - 1
+    for j in range(p - 1, -1, -1):
+        if Xv.shape[0] and np.ptp(Xv[:, j]) != 0:
+            marker = j
+            break
+    rest = [j for j in range(p) if j != marker]
+    order = [0] * p
+    for pos, j in enumerate(rest):
+        order[j] = pos
+    order[marker] = p - 1
     eng = get_engine(device)
     kwargs = dict(options)
     if model == "coxph":
-        eng.set_design(model, y_cols[0], Xv[:, :-1], event=y_cols[1],
+        eng.set_design(model, y_cols[0], Xv[:, rest], event=y_cols[1],
                        raw_mode=True, **kwargs)
     else:
-        eng.set_design(model, y_cols[0], Xv[:, :-1], raw_mode=True, **kwargs)
-    res = eng.run_dosage_host(np.ascontiguousarray(Xv[:, -1][None, :]))
+        eng.set_design(model, y_cols[0], Xv[:, rest], raw_mode=True, **kwargs)
+    res = eng.run_dosage_host(np.ascontiguousarray(Xv[:, marker][None, :]))
     if res.status[0] != 0:
         raise StatsError(failure_reason(res, 0))
-    return res, cols
+    return res, order

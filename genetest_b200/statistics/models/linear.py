@@ -32,13 +32,13 @@ class StatsLinear(StatsModels, BatchedGWAS):
     def fit(self, y, X):
         """Fit ``y ~ X`` on the GPU engine; same dict as the reference
         (``linear.py:64-89``)."""
-        res, cols = fit_single("linear", [y.iloc[:, 0].values.astype(float)],
+        res, order = fit_single("linear", [y.iloc[:, 0].values.astype(float)],
                                X, self.gwas_options())
         out = {"MODEL": {"r_squared_adj": float(res.stat[0]),
                          "log_likelihood": float(res.llf[0]),
                          "nobs": float(res.nobs[0])}}
-        for j, col in enumerate(cols):
-            vals = res.param(j)[:, 0]
+        for j, col in enumerate(X.columns):
+            vals = res.param(order[j])[:, 0]
             if col == "SNPs" and np.isnan(vals[5]):
                 raise StatsError("Inference did not converge.")
             out[col] = {f: float(v) for f, v in zip(PARAM_FIELDS, vals)}

@@ -17,13 +17,13 @@ class StatsLogistic(StatsModels, BatchedGWAS):
         """Same dict as the reference (``logistic.py:49-72``); the
         ``t_value`` is a z statistic."""
         yv = y.iloc[:, 0].values.astype(float)
-        res, cols = fit_single("logistic", [yv], X, {})
+        res, order = fit_single("logistic", [yv], X, {})
         out = {"MODEL": {"log_likelihood": float(res.llf[0]),
                          "nobs": float(res.nobs[0]),
                          "nevents": np.sum(y.y) if "y" in y.columns
                          else float(yv.sum())}}
-        for j, col in enumerate(cols):
-            vals = res.param(j)[:, 0]
+        for j, col in enumerate(X.columns):
+            vals = res.param(order[j])[:, 0]
             if col == "SNPs" and np.isnan(vals[5]):
                 raise StatsError("Inference did not converge.")
             out[col] = {f: float(v) for f, v in zip(PARAM_FIELDS, vals)}

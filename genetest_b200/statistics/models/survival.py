@@ -47,13 +47,13 @@ class StatsCoxPH(StatsModels, BatchedGWAS):
 
     def fit(self, y, X):
         tte, event, X = self._prepare_data(y, X)
-        res, cols = fit_single(
+        res, order = fit_single(
             "coxph", [tte.values.astype(float), event.values.astype(float)],
             X, {})
         out = {"MODEL": {"log_likelihood": float(res.llf[0]),
                          "nobs": X.shape[0], "nevents": np.sum(event)}}
-        for j, col in enumerate(cols):
-            vals = res.param(j)[:, 0]
+        for j, col in enumerate(X.columns):
+            vals = res.param(order[j])[:, 0]
             if col == "SNPs" and np.isnan(vals[5]):
                 raise StatsError("Inference did not converge.")
             out[col] = cox_param_dict(vals)

@@ -250,3 +250,71 @@ def test_synthetic_generator_roundtrip(engine):
     oracle = run_oracle("linear", y[:, None], C, names, G)
     problems, worst, n_ok = compare("linear", res, oracle, names, rtol=LIN_TOL)
     assert not problems, problems[:10]
+
+
+def _cox_data(rng, n, C, ties=False):
+    """tte ~ Exp(rate = exp(0.1 z(age))), censoring Exp(0.5)."""
+    t_event = rng.exponential(1.0 / np.exp(0.1 * C[:, 0]))
+    t_cens = rng.exponential(2.0, n)
+    tte = np.minimum(t_event, t_cens)
+    event = (t_event <= t_cens).astype(float)
+    if ties:
+        tte = np.ceil(tte * 120) / 120        # heavy ties (Efron correction)
+    return tte, event
+
+
+@pytest.mark.parametrize("ties", [False, True])
+def test_coxph_packed(engine, ties):
+    rng = np.random.default_rng(31 + ties)
+    n, n_snps = 1500, 120
+    C, names = synth_design(rng, n, k_extra=3)
+    C, names = C[:, :-1], names[:-1]          # StatsCoxPH drops the intercept
+    G = synth_genotypes(rng, n_snps, n, missing=0.01, maf_lo=0.05,
+                        maf_hi=0.95)
+    G[0] = 0.0                                # monomorphic -> Singular matrix
+    tte, event = _cox_data(rng, n, C, ties)
+    if ties:
+        # the engine keeps at most 32 tied samples in a block
+        _, counts = np.unique(tte, return_counts=True)
+        assert counts.max() <= 32 and counts.max() > 3
+    engine.set_design("coxph", tte, C, event=event)
+    res = engine.run_packed_host(pack_rows(G))
+    oracle = run_oracle("coxph", np.column_stack((tte, event)), C, names, G)
+    problems, worst, n_ok = compare("coxph", res, oracle, names,
+                                    rtol=LOGIT_TOL)
+    assert not problems, problems[:10]
+    assert res.status[0] == 7 and n_ok == n_snps - 1
+    print("coxph ties={} worst rel err {}".format(ties, worst))
+
+
+def test_coxph_interaction_subset_dosage(engine):
+    rng = np.random.default_rng(41)
+    n_file, n, n_snps = 900, 800, 40
+    C, names = synth_design(rng, n, k_extra=1)
+    C, names = C[:, :-1], names[:-1]
+    pos = rng.permutation(n_file)[:n].astype(np.int32)
+    Gfile = synth_genotypes(rng, n_snps, n_file, missing=0.02)
+    tte, event = _cox_data(rng, n, C)
+    inter = {"I:age": ["age"]}
+    engine.set_design("coxph", tte, C, event=event, W=C[:, [0]],
+                      sample_pos=pos, n_file=n_file)
+    res = engine.run_packed_host(pack_rows(Gfile))
+    G = Gfile[:, pos]
+    oracle = run_oracle("coxph", np.column_stack((tte, event)), C, names, G,
+                        interaction=inter)
+    problems, worst, n_ok = compare("coxph", res, oracle, names,
+                                    inter_keys=list(inter), rtol=LOGIT_TOL)
+    assert not problems, problems[:10]
+    # real-valued dosages, aligned to the design rows
+    D = np.clip(G + rng.normal(0, 0.03, G.shape), 0, 2)
+    engine.set_design("coxph", tte, C, event=event, W=C[:, [0]])
+    res = engine.run_dosage_host(D)
+    oracle = run_oracle("coxph", np.column_stack((tte, event)), C, names, D,
+                        interaction=inter)
+    for j, (st, o) in enumerate(oracle):
+        if st == "ok":
+            assert abs(res.maf[j] - o["SNPs"]["maf"]) < 1e-14
+            o["SNPs"]["maf"] = res.maf[j]
+    problems, worst, n_ok = compare("coxph", res, oracle, names,
+                                    inter_keys=list(inter), rtol=LOGIT_TOL)
+    assert not problems, problems[:10]

@@ -1,0 +1,275 @@
+"""Replay the reference's known-answer tests through ``analysis.execute``.
+
+Same fixtures and assertions as genetest/tests/test_linear.py,
+test_logistic.py, test_coxph.py and test_gwaswriter.py (numbers from
+``tests/golden/expected.json``): PLINK files written with a permuted sample
+order, phenotype rows AND columns re-permuted before every case, so that
+alignment is proven to be by label; results come out of the CUDA engine.
+"""
+
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from genetest_b200 import analysis, subscribers
+from genetest_b200 import modelspec as spec
+from genetest_b200.genotypes import DataFrameReader, PlinkReader, PlinkWriter
+from genetest_b200.phenotypes import _DummyPhenotypes
+from genetest_b200.statistics.core import StatsError
+from genetest_b200.statistics.models.linear import StatsLinear
+from genetest_b200.subscribers import GWASWriter
+
+from golden_support import (CASES, EXPECTED, MARKERS, NSNPS, OUTCOME,
+                            case_ids, check_record, load_table)
+
+pytestmark = pytest.mark.gpu
+
+
+def _phenotypes(df, model, rng):
+    ph = _DummyPhenotypes()
+    data = df.drop([c for c in df.columns if c.startswith("snp")], axis=1)
+    ph.data = data.iloc[rng.permutation(data.shape[0]),
+                        rng.permutation(data.shape[1])]
+    return ph
+
+
+def _plink(df, prefix, order, snps):
+    with PlinkWriter(prefix) as w:
+        for s in snps:
+            w.write_genotypes(df.loc[order, s].fillna(-1).values)
+        w.write_bim([(MARKERS[s][0], s, MARKERS[s][1], MARKERS[s][2],
+                      MARKERS[s][3]) for s in snps])
+        w.write_fam(order)
+    return PlinkReader(prefix)
+
+
+def _dataframe_reader(df, order, snps):
+    info = pd.DataFrame(
+        {"chrom": [MARKERS[s][0] for s in snps],
+         "pos": [MARKERS[s][1] for s in snps],
+         "a1": [MARKERS[s][2] for s in snps],
+         "a2": [MARKERS[s][3] for s in snps]}, index=snps)
+    return DataFrameReader(df.loc[order, snps].copy(), info)
+
+
+def _build_modelspec(case):
+    spec._reset()
+    model = case["model"]
+    gender = spec.factor(spec.phenotypes.gender)
+    if model == "coxph":
+        outcome = dict(tte=spec.phenotypes.tte, event=spec.phenotypes.event)
+    else:
+        outcome = spec.phenotypes[OUTCOME[model][0]]
+    inter = None
+    if case["mode"] == "gwas":
+        first = spec.SNPs
+        if case["inter"] == "var1":
+            inter = spec.gwas_interaction(spec.phenotypes.var1)
+        elif case["inter"] == "gender":
+            inter = spec.gwas_interaction(gender)
+    else:
+        first = spec.genotypes[case["snp"]]
+        other = spec.genotypes[case.get("inter_snp", case["snp"])]
+        if case["inter"] == "var1":
+            inter = spec.interaction(spec.phenotypes.var1, other)
+        elif case["inter"] == "gender":
+            inter = spec.interaction(gender, other)
+    predictors = [first, spec.phenotypes.age, spec.phenotypes.var1, gender]
+    if inter is not None:
+        predictors.append(inter)
+    if model == "linear" and case["kwargs"]:
+        test = lambda: StatsLinear(**case["kwargs"])    # noqa: E731
+    else:
+        test = model
+    return spec.ModelSpec(outcome=outcome, predictors=predictors,
+                          test=test), inter
+
+
+@pytest.mark.parametrize("model", ["linear", "logistic", "coxph"])
+def test_reference_goldens_through_execute(model, tmp_path):
+    rng = np.random.default_rng(12345)
+    snps = ["snp{}".format(i + 1) for i in range(NSNPS[model])]
+    readers = {}
+    for name in case_ids(model):
+        case = CASES[model][name]
+        rec = EXPECTED[model][name]
+        df = load_table(case["data"])
+        if case["data"] not in readers:
+            order = rng.permutation(df.index.values)
+            if model == "linear":
+                readers[case["data"]] = _plink(
+                    df, str(tmp_path / case["data"]), order, snps)
+            else:
+                readers[case["data"]] = _dataframe_reader(df, order, snps)
+        genotypes = readers[case["data"]]
+        phenotypes = _phenotypes(df, model, rng)
+        modelspec, inter = _build_modelspec(case)
+        sub = subscribers.ResultsMemory()
+        prefix = str(tmp_path / (name + "_results"))
+
+        def key(entity):
+            return entity.replace("INTER", inter.id) if inter else entity
+
+        if "raises" in rec:
+            with pytest.raises(StatsError) as err:
+                analysis.execute(phenotypes, genotypes, modelspec,
+                                 subscribers=[sub])
+            assert str(err.value) == rec["raises"], name
+            continue
+        analysis.execute(phenotypes, genotypes, modelspec, subscribers=[sub],
+                         output_prefix=prefix)
+        if case["mode"] == "gwas":
+            results = sub._get_gwas_results()
+            assert len(results) == rec["n_results"], name
+            with open(prefix + "_failed_snps.txt") as f:
+                failed = [line.split("\t") for line in f.read().splitlines()]
+            assert failed == rec["failed"], name
+            problems = check_record(
+                rec, lambda snp, ent, fld: results[snp][key(ent)][fld])
+        else:
+            res = sub.results[0]
+            problems = check_record(
+                rec, lambda snp, ent, fld: res[key(ent)][fld])
+        assert not problems, (name, problems)
+
+
+@pytest.fixture()
+def factors(tmp_path):
+    df = load_table("factors")
+    rng = np.random.default_rng(99)
+    order = rng.permutation(df.index.values)
+    prefix = str(tmp_path / "input")
+    with PlinkWriter(prefix) as w:
+        for s in ("snp1", "snp2", "snp3"):
+            w.write_genotypes(df.loc[order, s].values)
+        w.write_bim([(1, "snp{}".format(i), i, "B", "A") for i in (1, 2, 3)])
+        w.write_fam(order)
+    ph = _DummyPhenotypes()
+    data = df.drop(["snp1", "snp2", "snp3"], axis=1)
+    ph.data = data.iloc[rng.permutation(data.shape[0]),
+                        rng.permutation(data.shape[1])]
+    spec._reset()
+    out = str(tmp_path / "output.txt")
+    writer = GWASWriter(out, "linear")
+    yield ph, PlinkReader(prefix), writer, out
+    writer.close()
+
+
+COMMON = {"snp", "chr", "pos", "major", "minor", "maf", "n", "ll", "adj_r2"}
+STATS = ("coef", "se", "lower", "upper", "t", "p")
+
+
+def _table(path):
+    df = pd.read_csv(path, sep="\t")
+    return df.set_index("snp", drop=False).loc[["snp1", "snp2", "snp3"], :]
+
+
+def test_gwaswriter_normal(factors):
+    """test_gwaswriter.py:101-134."""
+    ph, geno, writer, out = factors
+    analysis.execute_formula(
+        ph, geno, "pheno ~ SNPs + var1 + var2 + factor(var3) + factor(var4) "
+        "+ factor(var5)", "linear", subscribers=[writer], output_prefix="")
+    df = _table(out)
+    assert set(df.columns) == COMMON | set(STATS)
+    np.testing.assert_array_almost_equal(
+        df.coef.values,
+        [6.48616317675085, 4.29701960321627, -1.44891512389655])
+
+
+def test_gwaswriter_subgroups(factors):
+    """test_gwaswriter.py:136-177."""
+    ph, geno, writer, out = factors
+    analysis.execute_formula(
+        ph, geno, "pheno | var4 ~ SNPs + var1 + var2 + factor(var3) + "
+        "factor(var5)", "linear", subscribers=[writer], output_prefix="")
+    df = _table(out)
+    assert set(df.columns) == COMMON | set(STATS) | {"subgroup"}
+    np.testing.assert_array_almost_equal(
+        df.loc[df.subgroup == "var4:y0", "coef"].values,
+        [-0.6798617801022, 5.9538885434287, -15.1758958532932])
+    np.testing.assert_array_almost_equal(
+        df.loc[df.subgroup == "var4:y1", "coef"].values,
+        [12.69000471889982, 4.2496912087917, 7.5291802846083])
+
+
+def test_gwaswriter_interactions(factors, tmp_path):
+    """test_gwaswriter.py:179-267."""
+    ph, geno, writer, out = factors
+    analysis.execute_formula(
+        ph, geno, "pheno ~ SNPs + var1 + var2 + factor(var3) + factor(var4) "
+        "+ factor(var5) + SNPs*var1", "linear", subscribers=[writer],
+        output_prefix="")
+    df = _table(out)
+    inter = "TRANSFORM:GWAS_INTER"
+    assert set(df.columns) == COMMON | {inter + ":" + s for s in STATS}
+    np.testing.assert_array_almost_equal(
+        df[inter + ":coef"].values,
+        [0.4073975765317, -0.04253919820585, -0.05814970176832])
+
+    spec._reset()
+    out2 = str(tmp_path / "output2.txt")
+    writer2 = GWASWriter(out2, "linear")
+    analysis.execute_formula(
+        ph, geno, "pheno ~ SNPs + var1 + var2 + factor(var3) + factor(var4) "
+        "+ factor(var5) + SNPs*factor(var3)", "linear", subscribers=[writer2],
+        output_prefix=out2)
+    df = _table(out2)
+    cols = {"{}:level.{}:{}".format(inter, lv, s)
+            for lv in ("x1", "x2") for s in STATS}
+    assert set(df.columns) == COMMON | cols
+    np.testing.assert_array_almost_equal(
+        df[inter + ":level.x1:coef"].values,
+        [6.15574045825434, 2.2178331615269, -1.94057337856961])
+    np.testing.assert_array_almost_equal(
+        df[inter + ":level.x2:coef"].values,
+        [21.47033225862596, 2.7136560668229, -0.05622018358578])
+
+
+def test_gwaswriter_interaction_subgroups(factors):
+    """test_gwaswriter.py:269-334."""
+    ph, geno, writer, out = factors
+    analysis.execute_formula(
+        ph, geno, "pheno | var4 ~ SNPs + var1 + var2 + factor(var3) + "
+        "factor(var5) + SNPs*factor(var3)", "linear", subscribers=[writer],
+        output_prefix=out)
+    df = _table(out)
+    inter = "TRANSFORM:GWAS_INTER"
+    y0, y1 = df.subgroup == "var4:y0", df.subgroup == "var4:y1"
+    np.testing.assert_array_almost_equal(
+        df.loc[y0, inter + ":level.x1:coef"].values,
+        [7.9838584795821, 0.8787655737690, -5.4257289463845])
+    np.testing.assert_array_almost_equal(
+        df.loc[y0, inter + ":level.x2:coef"].values,
+        [9.5318845882662, 2.1792184593254, -3.8901765902700])
+    np.testing.assert_array_almost_equal(
+        df.loc[y1, inter + ":level.x1:coef"].values,
+        [-7.33292032058131, -2.53148534004492, -14.560258817242])
+    np.testing.assert_array_almost_equal(
+        df.loc[y1, inter + ":level.x2:coef"].values,
+        [9.91504894770588, -1.35580107828104, -3.1717946298856])
+
+
+def test_name_filter_and_maf_threshold(tmp_path):
+    """variant predicates and the MAF failure line (analysis.py:151-153,
+    322-325)."""
+    from genetest_b200.modelspec.predicates import NameFilter
+    df = load_table("linear")
+    rng = np.random.default_rng(5)
+    snps = ["snp{}".format(i + 1) for i in range(5)]
+    geno = _plink(df, str(tmp_path / "in"), rng.permutation(df.index.values),
+                  snps)
+    ph = _phenotypes(df, "linear", rng)
+    modelspec, _ = _build_modelspec(CASES["linear"]["test_linear_gwas"])
+    sub = subscribers.ResultsMemory()
+    prefix = str(tmp_path / "out")
+    analysis.execute(ph, geno, modelspec, subscribers=[sub],
+                     variant_predicates=[NameFilter({"snp1", "snp2", "snp4"})],
+                     output_prefix=prefix, maf_t=0.05)
+    assert sorted(sub._get_gwas_results()) == ["snp2", "snp4"]
+    assert open(prefix + "_not_analyzed_snps.txt").read().split() == \
+        ["snp3", "snp5"]
+    assert open(prefix + "_failed_snps.txt").read().splitlines() == \
+        ["snp1\tMAF: 0.016666666666666666 < 0.05"]

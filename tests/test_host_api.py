@@ -1,0 +1,364 @@
+"""CPU tests of the host-side mirror of the reference API: formula grammar,
+design-matrix construction, subscribers, PLINK I/O, sample alignment, the
+C-ABI export table and the multi-rank gather (gloo, world_size 2)."""
+
+import ctypes
+import os
+import re
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from genetest_b200 import modelspec as spec
+from genetest_b200 import sharding
+from genetest_b200.genotypes import (DataFrameReader, PlinkReader,
+                                     PlinkWriter, pack_rows, unpack_rows)
+from genetest_b200.modelspec.predicates import MAFFilter, NameFilter
+from genetest_b200.phenotypes import _DummyPhenotypes
+from genetest_b200.statistics.descriptive import get_maf, get_sex_maf
+from genetest_b200.subscribers import GWASWriter, ResultsMemory, RowWriter
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(autouse=True)
+def _reset_spec():
+    spec._reset()
+    yield
+    spec._reset()
+
+
+@pytest.fixture()
+def containers():
+    rng = np.random.default_rng(3)
+    n = 100
+    data = pd.DataFrame({
+        "pheno": rng.normal(size=n), "var1": rng.normal(2, 1, n) ** 2 + 1,
+        "var2": rng.integers(0, 3, n).astype(float),
+        "var3": rng.choice(["x0", "x1", "x2"], n),
+        "snp": rng.integers(0, 3, n).astype(float),
+    }, index=["s{}".format(i) for i in range(n)])
+    data.loc["s5", "var1"] = np.nan
+    ph = _DummyPhenotypes()
+    ph.data = data.drop("snp", axis=1).iloc[rng.permutation(n)]
+    info = pd.DataFrame({"chrom": ["1"], "pos": [10], "a1": ["B"],
+                         "a2": ["A"]}, index=["snp"])
+    geno = DataFrameReader(data[["snp"]].iloc[rng.permutation(n)], info)
+    return data, ph, geno
+
+
+# ---- grammar (modelspec.ebnf) ---------------------------------------------
+def test_formula_simple_and_transformations(containers):
+    data, ph, geno = containers
+    model = spec.parse_formula(
+        "pheno ~ g(snp) + var1 + pow(var1, 4) + log10(var1) + ln(var1)")
+    assert model["conditions"] is None
+    del model["conditions"]
+    model["test"] = "linear"
+    ms = spec.ModelSpec(**model)
+    matrix = ms.create_data_matrix(ph, geno)
+    assert matrix.shape == (100, 7)
+    assert matrix.intercept.unique().tolist() == [1]
+    m = matrix.loc[data.index]
+    # the marker column is oriented on the minor allele
+    g = data.snp.values
+    if np.nanmean(g) / 2 > 0.5:
+        g = 2 - g
+    np.testing.assert_array_equal(m[spec.genotypes.snp.id].values, g)
+    np.testing.assert_array_equal(
+        m[spec.pow(spec.phenotypes.var1, 4).id].values, data.var1.values ** 4)
+    np.testing.assert_array_equal(
+        m[spec.log10(spec.phenotypes.var1).id].values,
+        np.log10(data.var1.values))
+    np.testing.assert_array_equal(
+        m[spec.ln(spec.phenotypes.var1).id].values, np.log(data.var1.values))
+    assert ms.get_translations()[spec.phenotypes.var1.id] == "var1"
+    meta = ms.variant_metadata[spec.genotypes.snp.id]
+    assert meta["name"] == "snp" and meta["chrom"] == "1"
+
+
+def test_formula_factor_interaction_and_gwas(containers):
+    data, ph, geno = containers
+    model = spec.parse_formula(
+        "pheno ~ SNPs + var1 + factor(var3) as f3 + var1*var2 as v12 + "
+        "SNPs*factor(var3)")
+    assert model["predictors"][0] == "SNPs"
+    del model["conditions"]
+    model["test"] = "linear"
+    ms = spec.ModelSpec(**model)
+    matrix = ms.create_data_matrix(ph, geno).loc[data.index]
+    f3 = spec.factor(spec.phenotypes.var3, name="f3")
+    assert f3.id == "TRANSFORM:f3"
+    for level in ("x1", "x2"):
+        np.testing.assert_array_equal(
+            matrix["TRANSFORM:f3:level." + level].values,
+            (data.var3 == level).astype(float).values)
+    assert "TRANSFORM:f3:level.x0" not in matrix.columns   # reference level
+    got = matrix["TRANSFORM:v12"].values
+    np.testing.assert_array_equal(np.isnan(got), np.isnan(data.var1.values))
+    np.testing.assert_allclose(got[~np.isnan(got)],
+                               (data.var1 * data.var2).dropna().values)
+    assert ms.has_gwas_interaction
+    assert sorted(ms.gwas_interaction) == [
+        "TRANSFORM:GWAS_INTER:level.x1", "TRANSFORM:GWAS_INTER:level.x2"]
+    fac = "TRANSFORM:ENCODE_FACTOR:" + spec.phenotypes.var3.id
+    assert ms.gwas_interaction["TRANSFORM:GWAS_INTER:level.x1"] == \
+        (fac + ":level.x1",)
+    # the GWAS interaction adds no column by itself
+    assert not any(c.startswith("TRANSFORM:GWAS_INTER")
+                   for c in matrix.columns)
+
+
+def test_formula_conditions_and_labelled_outcomes():
+    ms, subgroups = spec.modelspec_from_formula(
+        "[tte=t, event=e] | sex = 1, g(rs1) = \"AT\", grp ~ SNPs + x",
+        "coxph", None)
+    assert set(ms.outcome) == {"tte", "event"}
+    assert ms.outcome["tte"] is spec.phenotypes.t
+    assert subgroups == [1, "AT", None]
+    assert ms.stratify_by == [spec.phenotypes.sex, spec.genotypes.rs1,
+                              spec.phenotypes.grp]
+    with pytest.raises(RuntimeError):
+        spec.parse_formula("y ~ ")
+    with pytest.raises(RuntimeError):
+        spec.parse_formula("y ~ x +")
+    with pytest.raises(ValueError):
+        spec.ModelSpec(outcome=spec.phenotypes.y, predictors=[], test="nope")
+    # names may contain ':' and '_' and "as" is only a keyword on its own
+    model = spec.parse_formula("y_1 ~ assay + a:b")
+    assert model["predictors"] == [spec.phenotypes.assay,
+                                   spec.phenotypes["a:b"]]
+
+
+def test_modelspec_sample_intersection_and_missing_marker(containers):
+    data, ph, geno = containers
+    geno.df = geno.df.iloc[:60]
+    ms = spec.ModelSpec(outcome=spec.phenotypes.pheno,
+                        predictors=[spec.genotypes.snp, spec.phenotypes.var2],
+                        test="linear")
+    matrix = ms.create_data_matrix(ph, geno)
+    assert sorted(matrix.index) == sorted(geno.df.index)
+    spec._reset()
+    ms = spec.ModelSpec(outcome=spec.phenotypes.pheno,
+                        predictors=[spec.genotypes.unknown], test="linear")
+    with pytest.raises(ValueError):
+        ms.create_data_matrix(ph, geno)
+
+
+# ---- descriptive ------------------------------------------------------------
+def test_maf_helpers():
+    g = np.array([0, 0, 0, 1, 0, 0, 1, 2, 0, 0], dtype=float)
+    assert get_maf(g, "B", "A") == (0.2, "B", "A", False)
+    maf, minor, major, flip = get_maf(2 - g, "B", "A")
+    assert (minor, major, flip) == ("A", "B", True) and abs(maf - 0.2) < 1e-15
+    g[[1, 5]] = np.nan
+    assert get_maf(g, "B", "A")[0] == 4 / 16
+    assert np.isnan(get_maf(np.full(3, np.nan), "B", "A")[0])
+    sex = np.array([1, 0, 1, 1, 0, 0, 0, 1, 1, 0], dtype=float)
+    g = np.array([0, 0, 0, 2, 0, 0, 1, 2, 0, 0], dtype=float)
+    assert abs(get_sex_maf(g, sex, "B", "A")[0] - 3 / 15) < 1e-15
+    assert np.isnan(get_sex_maf(np.full(3, np.nan), np.ones(3), "B", "A")[0])
+
+
+# ---- PLINK I/O -----------------------------------------------------------------
+def test_plink_roundtrip(tmp_path):
+    rng = np.random.default_rng(1)
+    n, m = 37, 9                       # 37 samples: last byte is padded
+    G = rng.integers(-1, 3, (m, n)).astype(float)
+    G[G < 0] = np.nan
+    packed = pack_rows(G)
+    assert packed.shape == (m, 10)
+    np.testing.assert_array_equal(unpack_rows(packed, n), G)
+    # PLINK coding: 00 hom A1 (=2), 01 missing, 10 het, 11 hom A2 (=0)
+    assert pack_rows(np.array([[2, np.nan, 1, 0]]))[0, 0] == 0b11100100
+    prefix = str(tmp_path / "t")
+    samples = ["id{}".format(i) for i in range(n)]
+    with PlinkWriter(prefix) as w:
+        for row in G:
+            w.write_genotypes(np.where(np.isnan(row), -1, row))
+        w.write_bim([(1, "rs{}".format(j), 100 + j, "T", "C")
+                     for j in range(m)])
+        w.write_fam(samples)
+    assert open(prefix + ".bed", "rb").read(3) == bytes([0x6C, 0x1B, 0x01])
+    with PlinkReader(prefix) as r:
+        assert r.get_samples() == samples
+        assert r.get_number_variants() == m and r.get_number_samples() == n
+        rows = list(r.iter_genotypes())
+        np.testing.assert_array_equal(np.array([x.genotypes for x in rows]), G)
+        assert rows[3].variant.name == "rs3" and rows[3].variant.pos == 103
+        assert (rows[3].coded, rows[3].reference) == ("T", "C")
+        one = r.get_variant_by_name("rs7")
+        assert len(one) == 1
+        np.testing.assert_array_equal(one[0].genotypes, G[7])
+        assert r.get_variant_by_name("nope") == []
+        np.testing.assert_array_equal(np.asarray(r.packed()), packed)
+        assert MAFFilter(0.0)(rows[0]) and NameFilter({"rs1"})(rows[1])
+        assert not NameFilter({"rs1"})(rows[2])
+
+
+# ---- sample alignment ------------------------------------------------------------
+def test_generate_sample_order():
+    from genetest_b200.analysis import _generate_sample_order
+    x = pd.Index(["c", "a", "z", "b"])
+    geno = ["q", "b", "a", "r", "c"]
+    order, labels = _generate_sample_order(x, geno)
+    assert order.tolist() == [1, 2, 4]
+    assert labels.tolist() == ["b", "a", "c"]
+    order, labels = _generate_sample_order(pd.Index(["x"]), geno)
+    assert order.shape[0] == 0
+
+
+# ---- subscribers ---------------------------------------------------------------------
+def _fake_result(name, coef):
+    stats = {"coef": coef, "std_err": 0.5, "lower_ci": coef - 1,
+             "upper_ci": coef + 1, "t_value": 2 * coef, "p_value": 0.01}
+    snp = dict(stats, chrom="3", pos=12, major="C", minor="T", name=name,
+               maf=0.25)
+    return {"MODEL": {"nobs": 60.0, "log_likelihood": -10.5,
+                      "r_squared_adj": 0.3}, "SNPs": snp,
+            "INT:level.2": dict(stats)}
+
+
+def test_gwas_writer_columns(tmp_path):
+    path = str(tmp_path / "out.txt")
+    w = GWASWriter(path, "linear")
+    w.init(None)
+    w.handle(_fake_result("rs1", 1.5))
+    w.handle(_fake_result("rs2", -0.25))
+    w.close()
+    lines = open(path).read().splitlines()
+    assert lines[0].split("\t") == [
+        "snp", "chr", "pos", "major", "minor", "maf", "n", "ll", "adj_r2",
+        "coef", "se", "lower", "upper", "t", "p"]
+    assert lines[1].split("\t") == [
+        "rs1", "3", "12", "C", "T", "0.25", "60.0", "-10.5", "0.3", "1.5",
+        "0.5", "0.5", "2.5", "3.0", "0.01"]
+    # interaction + subgroup headers are rewritten in place
+    path = str(tmp_path / "out2.txt")
+    w = GWASWriter(path, "linear")
+    w.init(None)
+    w._update_gwas_interaction(["INT:level.2"])
+    w._update_current_subset({"sex": 1})
+    w.handle(_fake_result("rs1", 1.0))
+    w.close()
+    header = open(path).read().splitlines()[0].split("\t")
+    assert header[:9] == ["snp", "chr", "pos", "major", "minor", "maf", "n",
+                          "ll", "subgroup"]
+    assert header[9:] == ["adj_r2"] + ["INT:level.2:" + s for s in
+                                       ("coef", "se", "lower", "upper", "t",
+                                        "p")]
+    row = open(path).read().splitlines()[1].split("\t")
+    assert row[8] == "sex:1" and row[10] == "1.0"
+    for test, col in (("logistic", "n_events"), ("coxph", "n_events")):
+        w = GWASWriter(str(tmp_path / (test + ".txt")), test)
+        assert col in [c[0] for c in w.columns]
+        w.close()
+    cox = GWASWriter(str(tmp_path / "c.txt"), "coxph")
+    assert [c[0] for c in cox.columns][9:] == [
+        "coef", "se", "hr", "hr_lower", "hr_upper", "z", "p"]
+    cox.close()
+
+
+def test_results_memory_and_row_writer(tmp_path, capsys):
+    class _Spec(object):
+        def get_translations(self):
+            return {"uuid-1": "age"}
+    mem = ResultsMemory()
+    mem.init(_Spec())
+    res = _fake_result("rs9", 2.0)
+    res["uuid-1"] = {"coef": 1.0}
+    mem.handle(res)
+    assert "age" in mem.results[0] and "uuid-1" not in mem.results[0]
+    assert list(mem._get_gwas_results()) == ["rs9"]
+    rw = RowWriter(columns=[("name", spec.result["SNPs"]["name"]),
+                            ("tag", "const")], header=True, sep=",")
+    rw.init(None)
+    rw.handle(res)
+    assert capsys.readouterr().out.splitlines() == ["name,tag", "rs9,const"]
+    # factor levels are gathered per level
+    fac = spec.phenotypes.var3
+    got = spec.result[fac]["coef"]  # noqa: F841 (path building only)
+    per_level = spec.core.Result(fac).get(
+        {fac.id + ":level.a": 1, fac.id + ":level.b": 2, "other": 3})
+    assert per_level == {"level.a": 1, "level.b": 2}
+
+
+# ---- C ABI ---------------------------------------------------------------------------------
+def test_shared_library_exports_every_declared_symbol():
+    """The library loads on a CPU box and exports what include/*.h declares
+    (no compute call is made here)."""
+    header = open(os.path.join(ROOT, "include", "genetest_b200.h")).read()
+    declared = set(re.findall(r"\b(gt_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 18
+    from genetest_b200 import engine
+    assert declared == set(engine.ABI_SYMBOLS)
+    lib = ctypes.CDLL(engine.library_path())
+    for name in sorted(declared):
+        assert hasattr(lib, name), name
+    lib.gt_abi_version.restype = ctypes.c_int
+    assert lib.gt_abi_version() == 1
+    lib.gt_packed_pitch.restype = ctypes.c_int64
+    assert lib.gt_packed_pitch(100000) == 25088
+
+
+def test_engine_refuses_to_run_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from genetest_b200.engine import Engine, EngineError
+    with pytest.raises(EngineError):
+        Engine(0)
+
+
+# ---- sharding (gloo, world_size 2) -------------------------------------------------------
+def test_shard_range_covers_everything():
+    for n in (0, 1, 7, 62500, 500000):
+        for world in (1, 2, 3, 8):
+            spans = [sharding.shard_range(n, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for (a, b), (c, d) in zip(spans, spans[1:]):
+                assert b == c and a <= b and c <= d
+    assert sharding.shard_range(500000, 8, 3) == (187500, 250000)
+
+
+def _gather_worker(rank, world, port, tmp):
+    import torch.distributed as dist
+    from genetest_b200 import sharding as sh
+    from genetest_b200.engine import Results
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        assert sh.rank_world() == (rank, world)
+        n = 500
+        lo, hi = sh.shard_range(n, world, rank)
+        if rank == 1:
+            hi -= 3                       # ragged shard
+        idx = np.arange(lo, hi)
+        out = np.vstack([idx * 1.5, -idx.astype(float)])
+        iout = np.vstack([idx, idx % 7]).astype(np.int32)
+        res = Results(out, iout, 1)
+        meta = [("rs{}".format(i), "1", int(i), "A", "B") for i in idx]
+        got, got_meta = sh.gather_results(res, meta)
+        if rank == 0:
+            want = np.concatenate([np.arange(0, 250), np.arange(250, 497)])
+            np.testing.assert_array_equal(got.iout[0], want)
+            np.testing.assert_array_equal(got.out[0], want * 1.5)
+            assert [m[2] for m in got_meta] == want.tolist()
+            open(os.path.join(tmp, "ok"), "w").write("ok")
+        else:
+            assert got is None and got_meta is None
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_results_two_ranks_gloo(tmp_path):
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_gather_worker, args=(2, port, str(tmp_path)), nprocs=2,
+             join=True)
+    assert os.path.exists(str(tmp_path / "ok"))
