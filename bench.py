@@ -35,6 +35,9 @@ WORKLOADS = {
     "logistic": dict(n=50000, k_cov=10, snps=20000, missing=0.0,
                      name="config3: logistic GWAS 50k samples, 10 covariates "
                           "+ intercept (batched IRLS), SNP shard per step"),
+    "coxph": dict(n=20000, k_cov=10, snps=20000, missing=0.0,
+                  name="config5: Cox PH (Efron) 20k samples, 10 covariates, "
+                       "time/event phenotypes, SNP shard per step"),
 }
 
 
@@ -45,8 +48,17 @@ def make_design(model, n, k_cov, rng):
     age = (age - age.mean()) / age.std()
     sex = rng.integers(0, 2, n).astype(float)
     cols = [age, sex] + [rng.normal(size=n) for _ in range(k_cov - 2)]
-    C = np.column_stack(cols + [np.ones(n)])
     names = ["age", "sex"] + ["c{}".format(i) for i in range(k_cov - 2)]
+    if model == "coxph":
+        # tte ~ Exp(rate = exp(0.1 z(age))), independent censoring Exp(0.5);
+        # StatsCoxPH drops the intercept (survival.py:51-52)
+        C = np.column_stack(cols)
+        t_event = rng.exponential(1.0 / np.exp(0.1 * age))
+        t_cens = rng.exponential(2.0, n)
+        y = np.column_stack((np.minimum(t_event, t_cens),
+                             (t_event <= t_cens).astype(float)))
+        return y, C, names
+    C = np.column_stack(cols + [np.ones(n)])
     names.append("intercept")
     if model == "linear":
         y = 0.1 * age + rng.normal(size=n)
@@ -133,8 +145,9 @@ def _cpu_work(args):
         maf = rng.uniform(0.05, 0.5)
         g = rng.binomial(2, maf, n).astype(float)
         g[rng.random(n) < 0.01] = np.nan
-        og.gwas_one(_CPU["model"], _CPU["y"][:, None], _CPU["C"],
-                    _CPU["names"], g)
+        y = _CPU["y"]
+        og.gwas_one(_CPU["model"], y if y.ndim == 2 else y[:, None],
+                    _CPU["C"], _CPU["names"], g)
         done += 1
     return done
 
@@ -163,7 +176,8 @@ def run_reference(args, rank, world):
     rng = np.random.default_rng(SEED)
     y, C, names = make_design(args.model, w["n"], w["k_cov"], rng)
     cores = os.cpu_count() or 1
-    per_step = args.ref_snps or (cores * (48 if args.model == "linear" else 12))
+    per_step = args.ref_snps or (cores * {"linear": 48, "logistic": 12,
+                                            "coxph": 1}[args.model])
     import multiprocessing as mp
     pool = mp.get_context("spawn").Pool(cores, _cpu_init,
                                        (args.model, y, C, names))
@@ -218,7 +232,11 @@ def run_ours(args, rank, world, local_rank):
     eng.use_torch_stream()
     # sample ids in a random permutation relative to the phenotype table
     pos = np.random.default_rng(SEED + 1).permutation(n).astype(np.int32)
-    eng.set_design(args.model, y, C, sample_pos=pos, n_file=n)
+    if args.model == "coxph":
+        eng.set_design(args.model, y[:, 0], C, event=y[:, 1], sample_pos=pos,
+                       n_file=n)
+    else:
+        eng.set_design(args.model, y, C, sample_pos=pos, n_file=n)
     packed = eng.synth_packed(n, snps, seed=SEED + 1000 * rank,
                               missing_rate=w["missing"])
     pitch = packed.stride(0)
@@ -317,7 +335,8 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- CPU baseline: restated reference path on the host cores ----
     cores = os.cpu_count() or 1
-    cpu_snps = args.cpu_snps or (cores * (200 if args.model == "linear" else 50))
+    cpu_snps = args.cpu_snps or (cores * {"linear": 200, "logistic": 50,
+                                          "coxph": 2}[args.model])
     cpu_value, cpu_done, cpu_dt = cpu_throughput(args.model, y, C, names,
                                                  cpu_snps, cores)
     value = world * snps * args.steps / (ms * 1e-3)
