@@ -249,7 +249,7 @@ def run_ours(args, rank, world, local_rank):
 
     def step():
         eng.run_packed_dev(packed, snps, pitch, out, iout)
-        if world > 1:
+        if world > 1 and not os.environ.get("GT_BENCH_NO_GATHER"):
             # the only collective: fixed-size result blocks -> rank 0
             dist.gather(out, gathered if rank == 0 else None, dst=0)
             dist.gather(iout, gathered_i if rank == 0 else None, dst=0)
@@ -257,13 +257,14 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
         time.sleep(0.3)
+    # every rank enters the timed region together (rank 0 just slept)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
     eng.enable_timing(True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -276,6 +277,9 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.synchronize()
     eng.synchronize()
     ms = ev0.elapsed_time(ev1)
+    if os.environ.get("GT_BENCH_DEBUG"):
+        print("rank {} local ms/step {:.2f}".format(rank, ms / args.steps),
+              file=sys.stderr, flush=True)
     kms, klaunches, all_launches = eng.kernel_time()
     eng.enable_timing(False)
     clocks = sampler.stop() if sampler else None
@@ -325,6 +329,12 @@ def run_ours(args, rank, world, local_rank):
     per_launch_snps = snps * args.steps / max(1, klaunches)
     kernel_ms = kms / max(1, klaunches)
     achieved = per_launch_snps * bytes_per_snp / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    try:        # dram bytes per launch of the dominant kernel, from the ncu capture
+        prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = prof.get(args.model, {}).get("dram_bytes_per_launch")
+    except Exception:
+        pass
     fp64_peak = eng.fp64_peak_tflops()
     dmma_peak = eng.dmma_peak_tflops()
     if args.model == "linear":
@@ -355,7 +365,7 @@ def run_ours(args, rank, world, local_rank):
                    "ok_markers_last_step": n_ok, "markers_last_step": n_tested},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak,
                      "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": None, "peak_source": peak_src,
+                     "traffic": traffic, "peak_source": peak_src,
                      "kernel": eng.dominant_kernel(),
                      "kernel_ms_per_launch": kernel_ms,
                      "kernel_share_of_step": kms / ms,
@@ -385,6 +395,9 @@ def run_ours(args, rank, world, local_rank):
 
 
 def main():
+    # keep stdout to the one JSON line (NCCL_DEBUG=VERSION prints there)
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
+        os.environ["NCCL_DEBUG"] = "WARN"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

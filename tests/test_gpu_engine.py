@@ -318,3 +318,50 @@ def test_coxph_interaction_subset_dosage(engine):
     problems, worst, n_ok = compare("coxph", res, oracle, names,
                                     inter_keys=list(inter), rtol=LOGIT_TOL)
     assert not problems, problems[:10]
+
+
+def test_linear_config2_shape_sampled_parity(engine):
+    """BASELINE config 2 shape: 100,000 samples, 10 covariates + intercept,
+    1 % missing.  4,096 markers generated on the device; a stratified sample
+    (lowest MAF, most missing, plus a random draw) is checked against the
+    oracle, and size-independent properties on all of them: nobs + missing =
+    n, MAF in (0, 0.5], recoding A1 <-> A2 gives the same fit with the flip
+    flag inverted."""
+    rng = np.random.default_rng(20261019)
+    n, n_snps = 100000, 4096
+    C, names = synth_design(rng, n, k_extra=8)
+    y = 0.1 * C[:, 0] + rng.normal(size=n) + 10.0
+    pos = rng.permutation(n).astype(np.int32)
+    engine.set_design("linear", y, C, sample_pos=pos, n_file=n)
+    dev = engine.synth_packed(n, n_snps, seed=7, missing_rate=0.01)
+    out, iout = engine.run_packed_dev(dev, n_snps)
+    res = engine.fetch(out, iout)
+    assert (res.status == 0).all()
+    packed = dev.cpu().numpy()[:, :(n + 3) // 4]
+    G = unpack_rows(packed, n)
+    np.testing.assert_array_equal(res.nobs, n - np.isnan(G).sum(axis=1))
+    assert ((res.maf > 0) & (res.maf <= 0.5)).all()
+    pick = np.unique(np.concatenate([
+        np.argsort(res.maf)[:8], np.argsort(res.nobs)[:8],
+        rng.choice(n_snps, 16, replace=False)]))
+    sub = type(res)(res.out[:, pick], res.iout[:, pick], res.n_params)
+    oracle = run_oracle("linear", y[:, None], C, names, G[pick][:, pos])
+    problems, worst, n_ok = compare("linear", sub, oracle, names, rtol=LIN_TOL)
+    assert not problems, problems[:10]
+    print("config-2 shape: {} markers vs oracle, worst rel err {:.2e}".format(
+        n_ok, worst))
+    # recoding A1 <-> A2 (00 <-> 11): the engine flips it back -> same fit
+    swapped = packed.copy()
+    hom_a1 = np.zeros_like(swapped)
+    for s in (0, 2, 4, 6):
+        code = (swapped >> s) & 3
+        hom_a1 |= (np.where(code == 0, 3, np.where(code == 3, 0, code))
+                   << s).astype(np.uint8)
+    res2 = engine.run_packed_host(hom_a1[:256])
+    k = len(names)
+    np.testing.assert_array_equal(res2.flip, 1 - res.flip[:256])
+    np.testing.assert_allclose(res2.maf, res.maf[:256], rtol=1e-14)
+    np.testing.assert_allclose(res2.param(k)[0], res.param(k)[0, :256],
+                               rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(res2.param(k)[1], res.param(k)[1, :256],
+                               rtol=1e-10)
