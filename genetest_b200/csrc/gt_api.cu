@@ -13,6 +13,7 @@
 #include "gt_common.cuh"
 #include "gt_host.cuh"
 #include "gt_contract.cuh"
+#include "gt_contract_tc.cuh"
 #include "gt_linear.cuh"
 #include "gt_logistic.cuh"
 #include "gt_cox.cuh"
@@ -25,6 +26,9 @@ struct gt_engine {
     GtDesignDev D{};
     gtk::IterDesignDev T{};           // logistic / coxph design
     DevBuf dE, dMask, dFF0, dR, dRinv, dTq, dIter;   // design
+    DevBuf dBimg, dScale, dErr;                      // tcgen05 contraction (lean designs)
+    bool use_tc = false;
+    int tc_N = 0, tc_stages = 0, tc_ncol = 0;
     DevBuf dS, dCounts, dGsum;                 // per-batch workspace
     DevBuf dGeno, dOut, dIout;                 // staging of the *_host entry points
     int contract_idx = -1;
@@ -179,7 +183,7 @@ int gt_engine_destroy(gt_engine *e) {
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
     for (auto &ev : e->events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
-    DevBuf *bufs[] = {&e->dE, &e->dMask, &e->dFF0, &e->dR, &e->dRinv, &e->dTq, &e->dIter,
+    DevBuf *bufs[] = {&e->dE, &e->dMask, &e->dFF0, &e->dR, &e->dRinv, &e->dTq, &e->dIter, &e->dBimg, &e->dScale, &e->dErr,
                       &e->dS, &e->dCounts, &e->dGsum, &e->dGeno, &e->dOut, &e->dIout};
     for (DevBuf *b : bufs) b->release();
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
@@ -199,6 +203,14 @@ int gt_engine_synchronize(gt_engine *e) {
     if (!e) return fail(GT_E_ARG, "engine is NULL");
     CK(cudaSetDevice(e->device));
     CK(cudaStreamSynchronize(e->stream));
+    if (e->dErr.p) {
+        int flag = 0;
+        CK(cudaMemcpy(&flag, e->dErr.p, 4, cudaMemcpyDeviceToHost));
+        if (flag) {
+            cudaMemset(e->dErr.p, 0, 4);
+            return fail(GT_E_CUDA, "tcgen05 contraction: a pipeline barrier timed out");
+        }
+    }
     for (size_t i = 0; i < e->events_used; ++i) {
         float ms = 0.f;
         CK(cudaEventElapsedTime(&ms, e->events[i].first, e->events[i].second));
@@ -206,6 +218,12 @@ int gt_engine_synchronize(gt_engine *e) {
     }
     e->events_used = 0;
     return 0;
+}
+
+int gt_engine_set_option(gt_engine *e, const char *name, int value) {
+    if (!e || !name) return fail(GT_E_ARG, "gt_engine_set_option: NULL argument");
+    if (std::strcmp(name, "contract_tc") == 0) { e->use_tc = value != 0; return 0; }
+    return fail(GT_E_ARG, "gt_engine_set_option: unknown option '%s'", name);
 }
 
 int gt_engine_enable_timing(gt_engine *e, int on) {
@@ -342,6 +360,48 @@ int gt_engine_set_design(gt_engine *e, const gt_design_desc *d) {
                 }
         }
         if ((rc = upload(e->dE, E.data(), E.size() * 8, st))) return rc;
+        // ---- digit planes for the tcgen05 int8 contraction (lean designs) ----
+        e->tc_N = 0;
+        std::vector<uint8_t> Bimg;
+        std::vector<double> scale;
+        if (lean && 8 * NC1 <= 192) {
+            const int ncol = NC1;
+            const int N = (8 * ncol + 15) / 16 * 16;
+            const int n_st = (n_file + gtk::kTcStageK - 1) / gtk::kTcStageK;
+            static const int perm16[16] = {0, 2, 4, 6, 8, 10, 12, 14, 1, 3, 5, 7, 9, 11, 13, 15};
+            scale.assign(ncol, 1.0);
+            for (int c = 0; c < ncol; ++c) {
+                double mx = 0.0;
+                for (int i = 0; i < n; ++i) mx = std::max(mx, std::fabs(E[(size_t)pos[i] * NCP + c]));
+                scale[c] = mx > 0.0 ? mx : 1.0;
+            }
+            Bimg.assign((size_t)n_st * N * 128, 0);
+            for (int st_i = 0; st_i < n_st; ++st_i) {
+                uint8_t *img = &Bimg[(size_t)st_i * N * 128];
+                for (int kk = 0; kk < 128; ++kk) {
+                    long long smp = (long long)st_i * 128 + (kk / 16) * 16 + perm16[kk % 16];
+                    if (smp >= (long long)n_pad) continue;
+                    const double *er = &E[(size_t)smp * NCP];
+                    for (int c = 0; c < ncol; ++c) {
+                        double x = er[c] / scale[c];
+                        long long Z = llround(std::ldexp(x, 54));
+                        for (int sl = 0; sl < 8; ++sl) {
+                            long long d8 = ((Z + 64) & 127) - 64;      // balanced base-128 digit
+                            Z = (Z - d8) / 128;
+                            int nrow = c * 8 + sl;
+                            int grp = nrow >> 3, r = nrow & 7, chunk = kk >> 4, b = kk & 15;
+                            img[(size_t)grp * 1024 + r * 128 + ((chunk ^ r) << 4) + b] = (uint8_t)(int8_t)d8;
+                        }
+                    }
+                }
+            }
+            for (int c = 0; c < ncol; ++c) scale[c] = std::ldexp(scale[c], -54);
+            if ((rc = upload(e->dBimg, Bimg.data(), Bimg.size(), st))) return rc;
+            if ((rc = upload(e->dScale, scale.data(), scale.size() * 8, st))) return rc;
+            if ((rc = e->dErr.reserve(16))) return rc;
+            CK(cudaMemsetAsync(e->dErr.p, 0, 16, st));
+            e->tc_N = N; e->tc_stages = n_st; e->tc_ncol = ncol;
+        }
         if ((rc = upload(e->dFF0, FF0.data(), FF0.size() * 8, st))) return rc;
         if ((rc = upload(e->dR, H.R.data(), H.R.size() * 8, st))) return rc;
         if ((rc = upload(e->dRinv, H.Rinv.data(), H.Rinv.size() * 8, st))) return rc;
@@ -398,6 +458,32 @@ static void time_end(gt_engine *e, int slot) {
 
 static int e_n_file(const gt_engine *e) { return e->model == GT_MODEL_LINEAR ? e->D.n_file : e->T.n_file; }
 
+static int launch_contract_tc(gt_engine *e, const uint8_t *g, int64_t pitch, int nb) {
+    gtk::TcParams P;
+    P.geno = g; P.pitch = pitch; P.n_snps = nb; P.ormask = e->D.ormask;
+    P.Bimg = (const uint8_t *)e->dBimg.p; P.scale = (const double *)e->dScale.p;
+    P.n_stages = e->tc_stages; P.ncol = e->tc_ncol; P.N = e->tc_N; P.NCP = e->D.NCP;
+    P.S = (double *)e->dS.p; P.counts = (int *)e->dCounts.p; P.gsum = (double *)e->dGsum.p;
+    P.error_flag = (int *)e->dErr.p;
+    const int grid = (nb + 127) / 128;
+    const int NT = e->tc_N / 16;
+    size_t smem = (size_t)gtk::kTcStages * e->tc_N * 128 + 1024 + 256;
+#define GT_TC(T)                                                                               \
+    case T:                                                                                    \
+        CK(cudaFuncSetAttribute((const void *)gtk::contract_tc_kernel<T>,                      \
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+        gtk::contract_tc_kernel<T><<<grid, gtk::kTcThreads, smem, e->stream>>>(P);             \
+        break;
+    switch (NT) {
+        GT_TC(1) GT_TC(2) GT_TC(3) GT_TC(4) GT_TC(5) GT_TC(6) GT_TC(7) GT_TC(8) GT_TC(9)
+        GT_TC(10) GT_TC(11) GT_TC(12)
+        default: return fail(GT_E_UNSUPPORTED, "tcgen05 contraction: N=%d not instantiated", e->tc_N);
+    }
+#undef GT_TC
+    CK(cudaGetLastError());
+    return 0;
+}
+
 template <bool PACKED>
 static int launch_finish(gt_engine *e, int NT2, int grid, int threads, size_t smem,
                          const void *g, int64_t pitch, int nb, double *out, int32_t *iout,
@@ -450,8 +536,12 @@ static int run_linear(gt_engine *e, const void *geno, int64_t pitch, bool packed
         if (packed) {
             const uint8_t *g = (const uint8_t *)geno + (int64_t)s0 * pitch;
             int slot = time_begin(e);
-            ce.fn<<<(nb + tile - 1) / tile, 32 * ce.warps, ce.smem, e->stream>>>(
-                g, pitch, nb, D.ormask, D.E, D.n_chunks, S, cnt, gs);
+            if (e->use_tc && e->tc_N > 0) {
+                if ((rc = launch_contract_tc(e, g, pitch, nb))) return rc;
+            } else {
+                ce.fn<<<(nb + tile - 1) / tile, 32 * ce.warps, ce.smem, e->stream>>>(
+                    g, pitch, nb, D.ormask, D.E, D.n_chunks, S, cnt, gs);
+            }
             time_end(e, slot);
             CK(cudaGetLastError());
             if ((rc = launch_finish<true>(e, NT2, grid, wpc * 32, fsmem, g, pitch, nb, out + s0,

@@ -1,0 +1,298 @@
+// K1 + K2 on the 5th-generation tensor cores (tcgen05, kind::i8): the exact
+// integer formulation of the genotype contraction.
+//
+// Genotype dosages are the small integers {0,1,2}; every column of E is split
+// on the host into eight balanced base-128 digits (int8, 56-bit fixed point
+// relative to the column's max), so  sum_i g_i E_ic  becomes eight exact int32
+// dot products that are recombined in FP64 in the epilogue -- the same sums
+// the FP64 kernel (gt_contract.cuh) produces, to ~1e-16 relative.
+//
+//   A (128 SNP rows x K samples, int8)  lives in TENSOR MEMORY: each of 128
+//     threads owns one SNP row, streams its 2-bit codes from HBM with 128-bit
+//     loads, expands them with a byte-permute lookup (PRMT) and stores them
+//     with tcgen05.st -- no shared-memory staging of genotypes at all;
+//   B (N = 8 * columns, K-major, 128B swizzle) is a pre-swizzled image of the
+//     digit planes, fetched per 128-sample stage with one cp.async.bulk (TMA
+//     bulk copy) that completes on an mbarrier;
+//   D (128 x N int32) accumulates in TMEM; one elected thread issues
+//     tcgen05.mma.cta_group::1.kind::i8 (M=128, N, K=32), tcgen05.commit
+//     releases the stage.
+// Warp roles: 0-3 expand + epilogue, 4 bulk-copy producer, 5 MMA issuer.
+#pragma once
+
+#include "gt_common.cuh"
+
+namespace gtk {
+
+constexpr int kTcStages = 4;          // pipeline depth (A in TMEM, B in smem)
+constexpr int kTcStageK = 128;        // samples per stage (4 MMAs of K=32)
+constexpr int kTcThreads = 192;
+
+struct TcParams {
+    const uint8_t *geno;      // packed rows
+    long long pitch;
+    int n_snps;
+    const uint8_t *ormask;    // [pitch] (only the class counts need it)
+    const uint8_t *Bimg;      // [n_stages][N*128] pre-swizzled digit planes
+    const double *scale;      // [ncol] column scale * 2^-54
+    int n_stages;
+    int ncol;                 // live E columns (N = 8 * ncol rounded up to 16)
+    int N;
+    int NCP;                  // S row stride
+    double *S;
+    int *counts;
+    double *gsum;
+    int *error_flag;          // set when a bounded wait times out
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
+                 ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// bounded wait: never hangs the GPU; gives up after ~0.2 s or as soon as
+// another thread of the CTA has flagged a failure
+__device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, volatile int *fail) {
+    uint32_t done = 0;
+    for (int spin = 0; spin < (1 << 23); ++spin) {
+        if ((spin & 1023) == 1023 && *fail) return false;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (done) return true;
+    }
+    return false;
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+        ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint4 ldg_stream16(const void *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;\n" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
+
+// shared-memory matrix descriptor: K-major, 128B swizzle, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);            // start address  [0,14)
+    d |= (uint64_t)1 << 16;                              // leading byte offset (unused, 1)
+    d |= (uint64_t)(1024 >> 4) << 32;                    // stride byte offset [32,46)
+    d |= (uint64_t)1 << 46;                              // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                              // SWIZZLE_128B
+    return d;
+}
+
+template <int NT /* N / 16, N <= 256 */>
+__global__ void __launch_bounds__(kTcThreads, 2)
+contract_tc_kernel(TcParams P) {
+    constexpr int N = 16 * NT;
+    constexpr int BSTAGE = N * 128;                      // bytes of one B stage
+    constexpr int TMEM_COLS = (N + kTcStages * 32) <= 128 ? 128 : ((N + kTcStages * 32) <= 256 ? 256 : 512);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // the 128B swizzle is a function of the shared-memory address: 1024 B alignment
+    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char *sB = smem;                                            // kTcStages * BSTAGE
+    uint64_t *bars = (uint64_t *)(smem + kTcStages * BSTAGE);
+    uint64_t *a_full = bars, *b_full = bars + kTcStages, *empty = bars + 2 * kTcStages,
+             *d_full = bars + 3 * kTcStages;
+    uint32_t *tmem_slot = (uint32_t *)(bars + 3 * kTcStages + 1);
+    int *fail = (int *)(tmem_slot + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < kTcStages; ++s) { mbar_init(&a_full[s], 128); mbar_init(&b_full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(d_full, 1);
+        *fail = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n"
+                     ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n");
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_d = tmem_base;                   // columns [0, N)
+    const uint32_t tmem_a = tmem_base + N;               // kTcStages x 32 columns
+    const int n_stages = P.n_stages;
+
+    if (warp < 4) {
+        // ===== expansion: thread <-> SNP row =====
+        const int row = warp * 32 + lane;
+        const int snp = min(blockIdx.x * 128 + row, P.n_snps - 1);
+        const unsigned char *grow = P.geno + (long long)snp * P.pitch;
+        const uint32_t lane_base = ((uint32_t)(warp * 32)) << 16;
+        int nhet = 0, nhom = 0, nmis = 0;
+        // a 128-B line of the row (512 samples = 4 stages) lives in registers
+        uint4 cur[8], nxt[8];
+        const int n_lines = (n_stages + 3) / 4;
+        auto load_line = [&](int line, uint4 *dst) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                long long off = (long long)line * 128 + q * 16;
+                dst[q] = (off + 16 <= P.pitch) ? ldg_stream16(grow + off) : make_uint4(~0u, ~0u, ~0u, ~0u);
+            }
+        };
+        load_line(0, cur);
+        for (int line = 0; line < n_lines; ++line) {
+            if (line + 1 < n_lines) load_line(line + 1, nxt);
+#pragma unroll
+            for (int sub = 0; sub < 4; ++sub) {
+                const int it = line * 4 + sub;
+                if (it >= n_stages) break;
+                const int s = it % kTcStages;
+                const uint32_t par = ((it / kTcStages) & 1) ^ 1;
+                if (it >= kTcStages && !mbar_wait(&empty[s], par, fail)) { *fail = 1; }
+                asm volatile("tcgen05.fence::after_thread_sync;\n");
+                // mask words of this stage (same for every row: broadcast loads)
+                const uint4 *mk = (const uint4 *)(P.ormask + (long long)it * 32);
+                uint32_t a[32];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint4 pw = cur[sub * 2 + h];
+                    uint4 m4 = ((long long)it * 32 + h * 16 + 16 <= P.pitch) ? __ldg(mk + h) : make_uint4(~0u, ~0u, ~0u, ~0u);
+                    const uint32_t words[4] = {pw.x, pw.y, pw.z, pw.w};
+                    const uint32_t masks[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t w = words[j];
+                        const uint32_t wm = w | masks[j];
+                        uint32_t lo = wm & 0x55555555u, hi = (wm >> 1) & 0x55555555u;
+                        nmis += __popc(lo & ~hi);
+                        nhet += __popc(hi & ~lo);
+                        nhom += __popc(~(lo | hi) & 0x55555555u);
+                        // code -> dosage byte: 00 -> 2, 01 -> 0, 10 -> 1, 11 -> 0
+                        const uint32_t even = w & 0x33333333u, odd = (w >> 2) & 0x33333333u;
+                        const int o = (h * 4 + j) * 4;
+                        a[o + 0] = prmt(0x00010002u, 0u, even & 0xFFFFu);
+                        a[o + 1] = prmt(0x00010002u, 0u, even >> 16);
+                        a[o + 2] = prmt(0x00010002u, 0u, odd & 0xFFFFu);
+                        a[o + 3] = prmt(0x00010002u, 0u, odd >> 16);
+                    }
+                }
+                const uint32_t taddr = tmem_a + lane_base + s * 32;
+                asm volatile(
+                    "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+                    "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+                    "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};\n"
+                    ::"r"(taddr),
+                      "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+                      "r"(a[8]), "r"(a[9]), "r"(a[10]), "r"(a[11]), "r"(a[12]), "r"(a[13]), "r"(a[14]), "r"(a[15]),
+                      "r"(a[16]), "r"(a[17]), "r"(a[18]), "r"(a[19]), "r"(a[20]), "r"(a[21]), "r"(a[22]), "r"(a[23]),
+                      "r"(a[24]), "r"(a[25]), "r"(a[26]), "r"(a[27]), "r"(a[28]), "r"(a[29]), "r"(a[30]), "r"(a[31])
+                    : "memory");
+                asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+                mbar_arrive(&a_full[s]);
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) cur[q] = nxt[q];
+        }
+        // ===== epilogue: D (int32, TMEM) -> FP64 sums =====
+        if (!mbar_wait(d_full, 0, fail)) *fail = 1;
+        asm volatile("tcgen05.fence::after_thread_sync;\n");
+        const int out_snp = blockIdx.x * 128 + row;
+#pragma unroll 1
+        for (int c0 = 0; c0 < N; c0 += 32) {
+            uint32_t d[32];
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+                : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7]),
+                  "=r"(d[8]), "=r"(d[9]), "=r"(d[10]), "=r"(d[11]), "=r"(d[12]), "=r"(d[13]), "=r"(d[14]), "=r"(d[15]),
+                  "=r"(d[16]), "=r"(d[17]), "=r"(d[18]), "=r"(d[19]), "=r"(d[20]), "=r"(d[21]), "=r"(d[22]), "=r"(d[23]),
+                  "=r"(d[24]), "=r"(d[25]), "=r"(d[26]), "=r"(d[27]), "=r"(d[28]), "=r"(d[29]), "=r"(d[30]), "=r"(d[31])
+                : "r"(tmem_d + lane_base + c0));
+            asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                const int col = c0 / 8 + cc;          // 8 digit planes per E column
+                double acc = (double)(int)d[cc * 8 + 7];
+#pragma unroll
+                for (int sl = 6; sl >= 0; --sl) acc = fma(acc, 128.0, (double)(int)d[cc * 8 + sl]);
+                if (col < P.ncol && out_snp < P.n_snps)
+                    P.S[(long long)out_snp * P.NCP + col] = acc * P.scale[col];
+            }
+        }
+        if (out_snp < P.n_snps) {
+            for (int col = P.ncol; col < P.NCP; ++col) P.S[(long long)out_snp * P.NCP + col] = 0.0;
+            P.counts[(long long)out_snp * 4 + 0] = nhet;
+            P.counts[(long long)out_snp * 4 + 1] = nhom;
+            P.counts[(long long)out_snp * 4 + 2] = nmis;
+            P.gsum[(long long)out_snp * 2 + 0] = (double)(nhet + 2 * nhom);
+            P.gsum[(long long)out_snp * 2 + 1] = (double)(nhet + 4 * nhom);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    } else if (warp == 4) {
+        // ===== B producer: one bulk copy per stage =====
+        if (lane == 0) {
+            for (int it = 0; it < n_stages; ++it) {
+                const int s = it % kTcStages;
+                const uint32_t par = ((it / kTcStages) & 1) ^ 1;
+                if (it >= kTcStages && !mbar_wait(&empty[s], par, fail)) { *fail = 1; }
+                mbar_expect_tx(&b_full[s], BSTAGE);
+                bulk_g2s(sB + s * BSTAGE, P.Bimg + (long long)it * BSTAGE, BSTAGE, &b_full[s]);
+            }
+        }
+    } else {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            // instruction descriptor: D=S32, A=U8 (dosages), B=S8 (digits), K-major both
+            const uint32_t idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) |
+                                   ((uint32_t)(128 >> 4) << 24);
+            for (int it = 0; it < n_stages; ++it) {
+                const int s = it % kTcStages;
+                const uint32_t par = (it / kTcStages) & 1;
+                if (!mbar_wait(&a_full[s], par, fail)) *fail = 1;
+                if (!mbar_wait(&b_full[s], par, fail)) *fail = 1;
+                asm volatile("tcgen05.fence::after_thread_sync;\n");
+                const uint32_t bbase = smem_u32(sB + s * BSTAGE);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const uint64_t bdesc = tc_smem_desc(bbase + kk * 32);
+                    const uint32_t acol = tmem_a + s * 32 + kk * 8;
+                    const uint32_t accum = (it > 0 || kk > 0) ? 1u : 0u;
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\t"
+                        "setp.ne.b32 p, %4, 0;\n\t"
+                        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t}\n"
+                        ::"r"(tmem_d), "r"(acol), "l"(bdesc), "r"(idesc), "r"(accum),
+                          "r"(0u), "r"(0u), "r"(0u), "r"(0u) : "memory");
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+                             ::"r"(smem_u32(&empty[s])) : "memory");
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+                         ::"r"(smem_u32(d_full)) : "memory");
+        }
+    }
+    __syncthreads();
+    if (tid == 0 && *fail) atomicExch(P.error_flag, 1);
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(TMEM_COLS));
+    }
+}
+
+}  // namespace gtk

@@ -29,6 +29,7 @@ I_STATUS, I_NOBS, I_FLIP, I_NITER, NUM_IFIELDS = 0, 1, 2, 3, 4
 ABI_SYMBOLS = [
     "gt_abi_version", "gt_last_error", "gt_engine_create",
     "gt_engine_destroy", "gt_engine_set_stream", "gt_engine_synchronize",
+    "gt_engine_set_option",
     "gt_engine_set_design", "gt_engine_num_params", "gt_engine_num_fields",
     "gt_packed_pitch", "gt_run_packed_dev", "gt_run_packed_host",
     "gt_run_dosage_dev", "gt_run_dosage_host", "gt_synth_packed_dev",
@@ -83,6 +84,7 @@ def load_library():
     lib.gt_engine_destroy.argtypes = [vp]
     lib.gt_engine_set_stream.argtypes = [vp, vp]
     lib.gt_engine_synchronize.argtypes = [vp]
+    lib.gt_engine_set_option.argtypes = [vp, c.c_char_p, c.c_int]
     lib.gt_engine_set_design.argtypes = [vp, c.POINTER(_DesignDesc)]
     lib.gt_engine_num_params.argtypes = [vp]
     lib.gt_engine_num_fields.argtypes = [vp]
@@ -200,6 +202,10 @@ class Engine(object):
         if s == 0:
             s = 1       # cudaStreamLegacy: torch's default stream
         self._check(self.lib.gt_engine_set_stream(self._h, ctypes.c_void_p(s)))
+
+    def set_option(self, name, value):
+        self._check(self.lib.gt_engine_set_option(self._h, name.encode(),
+                                                  int(value)))
 
     def synchronize(self):
         self._check(self.lib.gt_engine_synchronize(self._h))

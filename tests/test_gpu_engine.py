@@ -365,3 +365,42 @@ def test_linear_config2_shape_sampled_parity(engine):
                                rtol=1e-9, atol=1e-12)
     np.testing.assert_allclose(res2.param(k)[1], res.param(k)[1, :256],
                                rtol=1e-10)
+
+
+@pytest.mark.parametrize("shape", [(1000, 1000, 3, 0.0), (1003, 901, 5, 0.02),
+                                   (5000, 5000, 11, 0.01)])
+def test_linear_tcgen05_contraction_matches_fp64_and_oracle(engine, shape):
+    """The int8 tensor-core contraction (tcgen05.mma kind::i8, exact fixed
+    point) against the FP64 kernel and the oracle."""
+    n_file, n, k_extra, miss = shape
+    rng = np.random.default_rng(n_file + k_extra)
+    n_snps = 300
+    C, names = synth_design(rng, n, k_extra=k_extra)
+    pos = np.sort(rng.permutation(n_file)[:n]).astype(np.int32)
+    Gfile = synth_genotypes(rng, n_snps, n_file, missing=miss, maf_lo=0.02,
+                            maf_hi=0.98)
+    Gfile[0] = 0.0
+    Gfile[1] = 2.0
+    y = _linear_y(rng, C) + 50.0
+    packed = pack_rows(Gfile)
+    engine.set_design("linear", y, C, sample_pos=pos, n_file=n_file)
+    try:
+        engine.set_option("contract_tc", 0)
+        ref = engine.run_packed_host(packed)
+        engine.set_option("contract_tc", 1)
+        res = engine.run_packed_host(packed)
+    finally:
+        engine.set_option("contract_tc", 0)
+    np.testing.assert_array_equal(res.iout, ref.iout)
+    ok = res.status == 0
+    np.testing.assert_array_equal(res.maf[ok], ref.maf[ok])
+    k = len(names)
+    for j in range(k + 1):
+        a, b = res.param(j)[:, ok], ref.param(j)[:, ok]
+        scale = np.maximum(np.abs(b[0]), np.abs(b[1]))
+        assert np.max(np.abs(a[0] - b[0]) / scale) < 1e-10
+        assert np.max(np.abs(a[1] - b[1]) / b[1]) < 1e-10
+    oracle = run_oracle("linear", y[:, None], C, names, Gfile[:, pos])
+    problems, worst, n_ok = compare("linear", res, oracle, names, rtol=LIN_TOL)
+    assert not problems, problems[:10]
+    print("tcgen05 contraction worst rel err vs oracle", worst)
