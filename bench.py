@@ -237,6 +237,8 @@ def run_ours(args, rank, world, local_rank):
                        n_file=n)
     else:
         eng.set_design(args.model, y, C, sample_pos=pos, n_file=n)
+    if args.model == "linear":
+        eng.set_option("contract_tc", int(args.contract == "tc"))
     packed = eng.synth_packed(n, snps, seed=SEED + 1000 * rank,
                               missing_rate=w["missing"])
     pitch = packed.stride(0)
@@ -362,11 +364,15 @@ def run_ours(args, rank, world, local_rank):
                    "l2": "inputs ({:.1f} GB packed per GPU) larger than L2"
                          .format(snps * pitch / 1e9),
                    "parallelism": "snp-shard x{}".format(world),
+                   "contraction": args.contract if args.model == "linear"
+                   else None,
                    "ok_markers_last_step": n_ok, "markers_last_step": n_tested},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak,
                      "unit": "GB/s", "frac": achieved / hbm_peak,
                      "traffic": traffic, "peak_source": peak_src,
-                     "kernel": eng.dominant_kernel(),
+                     "kernel": ("contract_tc_kernel" if (args.model == "linear" and
+                                                        args.contract == "tc")
+                                else eng.dominant_kernel()),
                      "kernel_ms_per_launch": kernel_ms,
                      "kernel_share_of_step": kms / ms,
                      "algorithmic_bytes_per_snp": bytes_per_snp,
@@ -406,6 +412,8 @@ def main():
     ap.add_argument("--model", default="linear", choices=sorted(WORKLOADS))
     ap.add_argument("--snps", type=int, default=0, help="SNPs per GPU per step")
     ap.add_argument("--samples", type=int, default=0)
+    ap.add_argument("--contract", default="tc", choices=["tc", "fp64"],
+                    help="linear contraction kernel: tcgen05 int8 or FP64")
     ap.add_argument("--e2e-snps", type=int, default=65536)
     ap.add_argument("--cpu-snps", type=int, default=0)
     ap.add_argument("--ref-snps", type=int, default=0)

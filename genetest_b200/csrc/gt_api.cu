@@ -29,7 +29,8 @@ struct gt_engine {
     DevBuf dBimg, dScale, dErr;                      // tcgen05 contraction (lean designs)
     bool use_tc = false;
     int tc_N = 0, tc_stages = 0, tc_ncol = 0;
-    DevBuf dS, dCounts, dGsum;                 // per-batch workspace
+    DevBuf dS, dCounts, dGsum, dMlist;         // per-batch workspace
+    int mcap = 0;
     DevBuf dGeno, dOut, dIout;                 // staging of the *_host entry points
     int contract_idx = -1;
     // timing
@@ -184,7 +185,7 @@ int gt_engine_destroy(gt_engine *e) {
     cudaStreamSynchronize(e->stream);
     for (auto &ev : e->events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     DevBuf *bufs[] = {&e->dE, &e->dMask, &e->dFF0, &e->dR, &e->dRinv, &e->dTq, &e->dIter, &e->dBimg, &e->dScale, &e->dErr,
-                      &e->dS, &e->dCounts, &e->dGsum, &e->dGeno, &e->dOut, &e->dIout};
+                      &e->dS, &e->dCounts, &e->dGsum, &e->dMlist, &e->dGeno, &e->dOut, &e->dIout};
     for (DevBuf *b : bufs) b->release();
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
@@ -465,6 +466,7 @@ static int launch_contract_tc(gt_engine *e, const uint8_t *g, int64_t pitch, int
     P.n_stages = e->tc_stages; P.ncol = e->tc_ncol; P.N = e->tc_N; P.NCP = e->D.NCP;
     P.S = (double *)e->dS.p; P.counts = (int *)e->dCounts.p; P.gsum = (double *)e->dGsum.p;
     P.error_flag = (int *)e->dErr.p;
+    P.mlist = (int *)e->dMlist.p; P.mcap = e->mcap;
     const int grid = (nb + 127) / 128;
     const int NT = e->tc_N / 16;
     size_t smem = (size_t)gtk::kTcStages * e->tc_N * 128 + 1024 + 256;
@@ -487,17 +489,18 @@ static int launch_contract_tc(gt_engine *e, const uint8_t *g, int64_t pitch, int
 template <bool PACKED>
 static int launch_finish(gt_engine *e, int NT2, int grid, int threads, size_t smem,
                          const void *g, int64_t pitch, int nb, double *out, int32_t *iout,
-                         long long stride, int wpc) {
+                         long long stride, int wpc, bool use_list) {
     const GtDesignDev &D = e->D;
     const double *S = (const double *)e->dS.p;
     const int *cnt = (const int *)e->dCounts.p;
     const double *gs = (const double *)e->dGsum.p;
+    const int *ml = use_list ? (const int *)e->dMlist.p : nullptr;
 #define GT_FIN(N)                                                                            \
     case N:                                                                                  \
         CK(cudaFuncSetAttribute((const void *)gtk::linear_finish_kernel<PACKED, N>,          \
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
         gtk::linear_finish_kernel<PACKED, N><<<grid, threads, smem, e->stream>>>(            \
-            D, g, pitch, nb, S, cnt, gs, out, iout, stride, wpc);                            \
+            D, g, pitch, nb, S, cnt, gs, ml, e->mcap, out, iout, stride, wpc);                            \
         break;
     switch (NT2) {
         GT_FIN(1) GT_FIN(2) GT_FIN(3) GT_FIN(4) GT_FIN(5)
@@ -519,6 +522,13 @@ static int run_linear(gt_engine *e, const void *geno, int64_t pitch, bool packed
     if ((rc = e->dS.reserve((size_t)bmax * D.NCP * 8))) return rc;
     if ((rc = e->dCounts.reserve((size_t)bmax * 4 * 4))) return rc;
     if ((rc = e->dGsum.reserve((size_t)bmax * 2 * 8))) return rc;
+    const bool tc = packed && e->use_tc && e->tc_N > 0;
+    if (tc) {
+        // per-SNP list of missing samples written by the tcgen05 kernel:
+        // room for 4 % missing (overflow falls back to re-scanning the row)
+        e->mcap = std::max(64, (D.n_file + 24) / 25);
+        if ((rc = e->dMlist.reserve((size_t)bmax * e->mcap * 4))) return rc;
+    }
     CK(cudaFuncSetAttribute((const void *)ce.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ce.smem));
     gtk::FinishLayout lay = gtk::finish_layout(D.L, D.p, D.I);
     const int NT2 = (D.L + 7) / 8;
@@ -536,7 +546,7 @@ static int run_linear(gt_engine *e, const void *geno, int64_t pitch, bool packed
         if (packed) {
             const uint8_t *g = (const uint8_t *)geno + (int64_t)s0 * pitch;
             int slot = time_begin(e);
-            if (e->use_tc && e->tc_N > 0) {
+            if (tc) {
                 if ((rc = launch_contract_tc(e, g, pitch, nb))) return rc;
             } else {
                 ce.fn<<<(nb + tile - 1) / tile, 32 * ce.warps, ce.smem, e->stream>>>(
@@ -545,14 +555,14 @@ static int run_linear(gt_engine *e, const void *geno, int64_t pitch, bool packed
             time_end(e, slot);
             CK(cudaGetLastError());
             if ((rc = launch_finish<true>(e, NT2, grid, wpc * 32, fsmem, g, pitch, nb, out + s0,
-                                          iout + s0, (long long)n_snps, wpc))) return rc;
+                                          iout + s0, (long long)n_snps, wpc, tc))) return rc;
         } else {
             const double *g = (const double *)geno + (int64_t)s0 * pitch;
             gtk::contract_dosage_kernel<<<(nb + 7) / 8, 256, 0, e->stream>>>(
                 g, pitch, nb, D.n, D.E, D.NCA, D.NCB, D.NC1, D.NC2, S, cnt, gs);
             CK(cudaGetLastError());
             if ((rc = launch_finish<false>(e, NT2, grid, wpc * 32, fsmem, g, pitch, nb, out + s0,
-                                           iout + s0, (long long)n_snps, wpc))) return rc;
+                                           iout + s0, (long long)n_snps, wpc, false))) return rc;
         }
         e->all_launches += 2;
     }

@@ -43,6 +43,8 @@ struct TcParams {
     int *counts;
     double *gsum;
     int *error_flag;          // set when a bounded wait times out
+    int *mlist;               // [n_snps][mcap] positions of the missing samples, in order
+    int mcap;                 // capacity per SNP (counts[3] = -1 when it overflowed)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -144,6 +146,11 @@ contract_tc_kernel(TcParams P) {
         const unsigned char *grow = P.geno + (long long)snp * P.pitch;
         const uint32_t lane_base = ((uint32_t)(warp * 32)) << 16;
         int nhet = 0, nhom = 0, nmis = 0;
+        // this thread is the only one that sees the row: it can emit the list of
+        // its missing samples in order, without atomics
+        const bool owner = blockIdx.x * 128 + row < P.n_snps;
+        int *mrow = P.mlist + (long long)snp * P.mcap;
+        int mcur = 0;
         // a 128-B line of the row (512 samples = 4 stages) lives in registers
         uint4 cur[8], nxt[8];
         const int n_lines = (n_stages + 3) / 4;
@@ -168,6 +175,7 @@ contract_tc_kernel(TcParams P) {
                 // mask words of this stage (same for every row: broadcast loads)
                 const uint4 *mk = (const uint4 *)(P.ormask + (long long)it * 32);
                 uint32_t a[32];
+                uint32_t mflag[4];
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const uint4 pw = cur[sub * 2 + h];
@@ -179,7 +187,12 @@ contract_tc_kernel(TcParams P) {
                         const uint32_t w = words[j];
                         const uint32_t wm = w | masks[j];
                         uint32_t lo = wm & 0x55555555u, hi = (wm >> 1) & 0x55555555u;
-                        nmis += __popc(lo & ~hi);
+                        uint32_t mb = lo & ~hi;
+                        nmis += __popc(mb);
+                        // flags of two consecutive words share one 32-bit word:
+                        // even bits <- word 2m, odd bits <- word 2m + 1
+                        if (j & 1) mflag[h * 2 + (j >> 1)] |= mb << 1;
+                        else mflag[h * 2 + (j >> 1)] = mb;
                         nhet += __popc(hi & ~lo);
                         nhom += __popc(~(lo | hi) & 0x55555555u);
                         // code -> dosage byte: 00 -> 2, 01 -> 0, 10 -> 1, 11 -> 0
@@ -189,6 +202,22 @@ contract_tc_kernel(TcParams P) {
                         a[o + 1] = prmt(0x00010002u, 0u, even >> 16);
                         a[o + 2] = prmt(0x00010002u, 0u, odd & 0xFFFFu);
                         a[o + 3] = prmt(0x00010002u, 0u, odd >> 16);
+                    }
+                }
+                // emit the stage's missing samples (in order) once per stage
+                if (owner) {
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        unsigned long long m = (unsigned long long)mflag[2 * q] |
+                                               ((unsigned long long)mflag[2 * q + 1] << 32);
+                        while (m) {
+                            int b = __ffsll((long long)m) - 1;
+                            // bit b: 32-bit group b / 32 (two words), word parity b & 1, sample (b % 32) / 2
+                            int word = q * 4 + (b >> 5) * 2 + (b & 1);
+                            if (mcur < P.mcap) mrow[mcur] = it * kTcStageK + word * 16 + ((b & 31) >> 1);
+                            ++mcur;
+                            m &= m - 1;
+                        }
                     }
                 }
                 const uint32_t taddr = tmem_a + lane_base + s * 32;
@@ -241,6 +270,7 @@ contract_tc_kernel(TcParams P) {
             P.counts[(long long)out_snp * 4 + 0] = nhet;
             P.counts[(long long)out_snp * 4 + 1] = nhom;
             P.counts[(long long)out_snp * 4 + 2] = nmis;
+            P.counts[(long long)out_snp * 4 + 3] = (mcur <= P.mcap) ? mcur : -1;
             P.gsum[(long long)out_snp * 2 + 0] = (double)(nhet + 2 * nhom);
             P.gsum[(long long)out_snp * 2 + 1] = (double)(nhet + 4 * nhom);
         }

@@ -77,7 +77,7 @@ __device__ __forceinline__ void dmma884_lin(double &c0, double &c1, double a, do
 template <bool PACKED, int NT2>
 __device__ __forceinline__ void subtract_missing(const GtDesignDev &D, const void *rowp,
                                                  double *S0, double *stage, int *queue,
-                                                 int lane) {
+                                                 int lane, const int *mlist, int mcount) {
     constexpr int LS = finish_stage_stride(NT2);
     const int L = D.L;
     const int nlive = D.lean ? D.k + 1 : L;      // columns present in E
@@ -134,7 +134,48 @@ __device__ __forceinline__ void subtract_missing(const GtDesignDev &D, const voi
         return has;
     };
 
-    if (PACKED) {
+    if (mlist != nullptr && mcount >= 0) {
+        // the contraction kernel already listed the missing samples: gather
+        // group g + 1 while the tensor cores work on group g
+        constexpr int NV = 4 * NT2;                      // double2 per base vector
+        const int nv = (nlive + 1) / 2;
+        double2 regs[NV];
+        auto fetch = [&](int g) {
+            int t = g * 32 + lane;
+            int idx = (t < mcount) ? mlist[t] : -1;
+            const double2 *er = (const double2 *)(D.E + (long long)(idx < 0 ? 0 : idx) * D.NCP);
+#pragma unroll
+            for (int c = 0; c < NV; ++c)
+                regs[c] = (idx >= 0 && c < nv) ? er[c] : make_double2(0.0, 0.0);
+            return idx >= 0;
+        };
+        const int ngroups = (mcount + 31) / 32;
+        bool valid = ngroups > 0 ? fetch(0) : false;
+        for (int g = 0; g < ngroups; ++g) {
+            double2 *s2 = (double2 *)(stage + lane * LS);
+#pragma unroll
+            for (int c = 0; c < NV; ++c) if (2 * c < LS) s2[c] = regs[c];
+            if (valid) {
+                if (D.lean) stage[lane * LS + D.k + 1] = 1.0;
+                else if (nlive & 1) stage[lane * LS + nlive] = 0.0;
+            }
+            __syncwarp();
+            if (g + 1 < ngroups) valid = fetch(g + 1);
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+                const int e = ks * 4 + (lane & 3), c = lane >> 2;
+                double f[NT2];
+#pragma unroll
+                for (int t = 0; t < NT2; ++t) f[t] = stage[e * LS + t * 8 + c];
+#pragma unroll
+                for (int mt = 0; mt < NT2; ++mt)
+#pragma unroll
+                    for (int nt = mt; nt < NT2; ++nt)
+                        dmma884_lin(acc[mt][nt][0], acc[mt][nt][1], f[mt], f[nt]);
+            }
+            __syncwarp();
+        }
+    } else if (PACKED) {
         const int nwords = (D.n_file + 15) / 16;         // 32-bit words of 16 samples
         const int nblocks = (nwords + 127) / 128;        // 4 words (64 samples) per lane
         const uint4 *row4 = (const uint4 *)rowp;
@@ -192,10 +233,10 @@ __device__ __forceinline__ void subtract_missing(const GtDesignDev &D, const voi
 }
 
 template <bool PACKED, int NT2>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 linear_finish_kernel(GtDesignDev D, const void *__restrict__ geno, long long pitch, int n_snps,
                      const double *__restrict__ S, const int *__restrict__ counts,
-                     const double *__restrict__ gsum,
+                     const double *__restrict__ gsum, const int *__restrict__ mlist, int mcap,
                      double *__restrict__ out, int *__restrict__ iout, long long ostride,
                      int wpc) {
     extern __shared__ __align__(16) double sm[];
@@ -227,7 +268,9 @@ linear_finish_kernel(GtDesignDev D, const void *__restrict__ geno, long long pit
     if (n_miss > 0) {
         const void *rowp = PACKED ? (const void *)((const uint8_t *)geno + (long long)snp * pitch)
                                   : (const void *)((const double *)geno + (long long)snp * pitch);
-        subtract_missing<PACKED, NT2>(D, rowp, S0, stage, queue, lane);
+        const int mcount = mlist ? counts[(long long)snp * 4 + 3] : -1;
+        subtract_missing<PACKED, NT2>(D, rowp, S0, stage, queue, lane,
+                                      mlist ? mlist + (long long)snp * mcap : nullptr, mcount);
     }
     __syncwarp();
 
