@@ -122,7 +122,7 @@ static int launch_logistic(const IterDesignDev &T, const void *geno, int64_t pit
                            double *out, int32_t *iout, cudaStream_t st) {
     using Cfg = LogitCfg<NT>;
     const int wpc = 8;
-    size_t smem = (size_t)wpc * Cfg::perWarp * 8;
+    size_t smem = (size_t)wpc * Cfg::perWarp * 8;   // NT = 2: 92 KB -> two CTAs per SM
     CK(cudaFuncSetAttribute((const void *)logistic_irls_kernel<PACKED, NT>,
                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     logistic_irls_kernel<PACKED, NT><<<(n_snps + wpc - 1) / wpc, wpc * 32, smem, st>>>(

@@ -61,10 +61,13 @@ __device__ __forceinline__ bool load_geno(const void *rowp, int i, double &g) {
 
 template <int NT>
 struct LogitCfg {
-    static constexpr int PS = (NT <= 2) ? 20 : 36;   // staging row stride, == 4 (mod 16)
     static constexpr int PH = 8 * NT;                // padded Hessian dimension
-    // per-warp doubles: xs, wxs, H, Hc, Hinv, beta, rhs, tmp
-    static constexpr int perWarp = 2 * 32 * PS + PH * PH + 2 * PH * PH + 4 * PH;
+    // staging tile, TRANSPOSED: row a (design column, then z, then the weights)
+    // holds the 32 samples of the block; row stride 36 doubles keeps both the
+    // per-lane stores and the MMA fragment loads bank-conflict free
+    static constexpr int XT = 36;
+    // per-warp doubles: xsT (PH + 1 rows), H, Hc, Hinv, beta, rhs, coef, var
+    static constexpr int perWarp = (PH + 1) * XT + 3 * PH * PH + 4 * PH;
 };
 
 template <bool PACKED, int NT>
@@ -72,7 +75,7 @@ __global__ void __launch_bounds__(256)
 logistic_irls_kernel(IterDesignDev T, const void *__restrict__ geno, long long pitch, int n_snps,
                      double *__restrict__ out, int *__restrict__ iout, long long ostride) {
     using Cfg = LogitCfg<NT>;
-    constexpr int PS = Cfg::PS, PH = Cfg::PH;
+    constexpr int PH = Cfg::PH, XT = Cfg::XT;
     extern __shared__ __align__(16) double sm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int snp = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -82,7 +85,7 @@ logistic_irls_kernel(IterDesignDev T, const void *__restrict__ geno, long long p
     const double EPS = 2.220446049250313e-16;
 
     double *W = sm + (size_t)warp * Cfg::perWarp;
-    double *xs = W, *wxs = xs + 32 * PS, *H = wxs + 32 * PS, *Hc = H + PH * PH,
+    double *xsT = W, *ws = xsT + PH * XT, *H = xsT + (PH + 1) * XT, *Hc = H + PH * PH,
            *Hinv = Hc + PH * PH, *beta = Hinv + PH * PH, *rhs = beta + PH, *coef = rhs + PH,
            *var = coef + PH;
 
@@ -131,7 +134,7 @@ logistic_irls_kernel(IterDesignDev T, const void *__restrict__ geno, long long p
     // for the redundant direction -> NaN inference
     if (T.degenerate) { write_fail(GT_NAN_PVALUE, flip, maf, nan(""), 0); return; }
 
-    for (int t = lane; t < 2 * 32 * PS; t += 32) xs[t] = 0.0;   // xs and wxs (padding stays 0)
+    for (int t = lane; t < (PH + 1) * XT; t += 32) xsT[t] = 0.0;   // padding rows stay 0
     for (int t = lane; t < PH; t += 32) beta[t] = 0.0;
     __syncwarp();
 
@@ -154,45 +157,59 @@ logistic_irls_kernel(IterDesignDev T, const void *__restrict__ geno, long long p
             double g = 0.0;
             bool ok = (yv == yv);
             if (ok) ok = load_geno<PACKED>(rowp, i, g);
-            double *xr = xs + lane * PS, *wr = wxs + lane * PS;
+            if (!ok) g = 0.0;
+            else if (flip) g = 2.0 - g;
+            // design row [q | g | g w] into the transposed staging tile, eta = x'beta
+            const double *xi = T.X + (long long)(ok ? i : 0) * T.XS;
+            double eta = 0.0;
+#pragma unroll
+            for (int a = 0; a < PH; ++a)
+                if (a < k) { double v = xi[a]; xsT[a * XT + lane] = v; eta = fma(v, beta[a], eta); }
+            xsT[k * XT + lane] = g; eta = fma(g, beta[k], eta);
+            for (int j = 0; j < I; ++j) {
+                double v = g * xi[k + j];
+                xsT[(k + 1 + j) * XT + lane] = v; eta = fma(v, beta[k + 1 + j], eta);
+            }
+            double w = 0.0, z = 0.0;
             if (ok) {
-                if (flip) g = 2.0 - g;
-                const double *xi = T.X + (long long)i * T.XS;
-                double eta = 0.0;
-                for (int a = 0; a < k; ++a) { double v = xi[a]; xr[a] = v; eta = fma(v, beta[a], eta); }
-                xr[k] = g; eta = fma(g, beta[k], eta);
-                for (int j = 0; j < I; ++j) { double v = g * xi[k + j]; xr[k + 1 + j] = v; eta = fma(v, beta[k + 1 + j], eta); }
                 double mu;
-                if (pass == 0) { mu = (yv + 0.5) / 2.0; eta = log(mu / (1.0 - mu)); }
-                else {
-                    mu = 1.0 / (1.0 + exp(-eta));
-                    // deviance / log-likelihood / separation at the updated mu
-                    double e1 = yv / (mu + 1e-20), e0 = (1.0 - yv) / (1.0 - mu + 1e-20);
-                    e1 = fmax(e1, EPS); e0 = fmax(e0, EPS);
+                const bool binary = (yv == 0.0) || (yv == 1.0);
+                if (pass == 0) {
+                    mu = (yv + 0.5) / 2.0;
+                    eta = log(mu / (1.0 - mu));
+                    double e1 = fmax(yv / (mu + 1e-20), EPS), e0 = fmax((1.0 - yv) / (1.0 - mu + 1e-20), EPS);
                     dev += 2.0 * (yv * log(e1) + (1.0 - yv) * log(e0));
-                    ll += yv * log(mu / (1.0 - mu) + 1e-20) + log(1.0 - mu + 1e-20);
+                } else {
+                    // mu = 1 / (1 + exp(-eta)); log(1 - mu) = -(max(eta, 0) + log1p(exp(-|eta|)))
+                    double t = exp(-fabs(eta));
+                    double inv = 1.0 / (1.0 + t);
+                    mu = (eta >= 0.0) ? inv : t * inv;
+                    if (binary) {
+                        // y in {0, 1}: loglike_i = y eta + log(1 - mu), deviance_i = -2 loglike_i
+                        double li = yv * eta - (fmax(eta, 0.0) + log1p(t));
+                        ll += li;
+                        dev -= 2.0 * li;
+                    } else {
+                        double e1 = fmax(yv / (mu + 1e-20), EPS), e0 = fmax((1.0 - yv) / (1.0 - mu + 1e-20), EPS);
+                        dev += 2.0 * (yv * log(e1) + (1.0 - yv) * log(e0));
+                        ll += yv * log(mu / (1.0 - mu) + 1e-20) + log(1.0 - mu + 1e-20);
+                    }
                     if (!(fabs(mu - yv) <= 1e-8)) sep = 0;
                 }
-                if (pass == 0) {
-                    double e1 = yv / (mu + 1e-20), e0 = (1.0 - yv) / (1.0 - mu + 1e-20);
-                    e1 = fmax(e1, EPS); e0 = fmax(e0, EPS);
-                    dev += 2.0 * (yv * log(e1) + (1.0 - yv) * log(e0));
-                }
                 double pc = fmin(fmax(mu, EPS), 1.0 - EPS);
-                double d = 1.0 / (pc * (1.0 - pc));
-                double w = 1.0 / (d * d * (pc * (1.0 - pc)));
-                xr[p] = eta + d * (yv - mu);                  // working response
-                for (int a = 0; a < p; ++a) wr[a] = w * xr[a];
-            } else {
-                for (int a = 0; a <= p; ++a) { xr[a] = 0.0; wr[a] = 0.0; }
+                w = pc * (1.0 - pc);                 // 1 / (link.deriv^2 * variance)
+                z = eta + (yv - mu) / w;             // working response
             }
+            xsT[p * XT + lane] = z;
+            ws[lane] = w;
             __syncwarp();
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks) {
                 const int e = ks * 4 + (lane & 3), c = lane >> 2;
+                const double wv = ws[e];
                 double af[NT], bf[NT];
 #pragma unroll
-                for (int t = 0; t < NT; ++t) { af[t] = wxs[e * PS + t * 8 + c]; bf[t] = xs[e * PS + t * 8 + c]; }
+                for (int t = 0; t < NT; ++t) { bf[t] = xsT[(t * 8 + c) * XT + e]; af[t] = wv * bf[t]; }
 #pragma unroll
                 for (int mt = 0; mt < NT; ++mt)
 #pragma unroll
