@@ -29,7 +29,7 @@ struct gt_engine {
     DevBuf dBimg, dScale, dErr;                      // tcgen05 contraction (lean designs)
     bool use_tc = false;
     int tc_N = 0, tc_stages = 0, tc_ncol = 0;
-    DevBuf dS, dCounts, dGsum, dMlist;         // per-batch workspace
+    DevBuf dS, dCounts, dGsum, dMlist, dMcount; // per-batch workspace
     int mcap = 0;
     DevBuf dGeno, dOut, dIout;                 // staging of the *_host entry points
     int contract_idx = -1;
@@ -185,7 +185,7 @@ int gt_engine_destroy(gt_engine *e) {
     cudaStreamSynchronize(e->stream);
     for (auto &ev : e->events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     DevBuf *bufs[] = {&e->dE, &e->dMask, &e->dFF0, &e->dR, &e->dRinv, &e->dTq, &e->dIter, &e->dBimg, &e->dScale, &e->dErr,
-                      &e->dS, &e->dCounts, &e->dGsum, &e->dMlist, &e->dGeno, &e->dOut, &e->dIout};
+                      &e->dS, &e->dCounts, &e->dGsum, &e->dMlist, &e->dMcount, &e->dGeno, &e->dOut, &e->dIout};
     for (DevBuf *b : bufs) b->release();
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
@@ -466,10 +466,10 @@ static int launch_contract_tc(gt_engine *e, const uint8_t *g, int64_t pitch, int
     P.n_stages = e->tc_stages; P.ncol = e->tc_ncol; P.N = e->tc_N; P.NCP = e->D.NCP;
     P.S = (double *)e->dS.p; P.counts = (int *)e->dCounts.p; P.gsum = (double *)e->dGsum.p;
     P.error_flag = (int *)e->dErr.p;
-    P.mlist = (int *)e->dMlist.p; P.mcap = e->mcap;
+    P.mlist = (int *)e->dMlist.p; P.mcap = e->mcap; P.mcount = (int *)e->dMcount.p;
     const int grid = (nb + 127) / 128;
     const int NT = e->tc_N / 16;
-    size_t smem = (size_t)gtk::kTcStages * e->tc_N * 128 + 1024 + 256;
+    size_t smem = (size_t)gtk::kTcStages * e->tc_N * 128 + 1024 + 256 + 128 * 3 * 4;
 #define GT_TC(T)                                                                               \
     case T:                                                                                    \
         CK(cudaFuncSetAttribute((const void *)gtk::contract_tc_kernel<T>,                      \
@@ -495,12 +495,13 @@ static int launch_finish(gt_engine *e, int NT2, int grid, int threads, size_t sm
     const int *cnt = (const int *)e->dCounts.p;
     const double *gs = (const double *)e->dGsum.p;
     const int *ml = use_list ? (const int *)e->dMlist.p : nullptr;
+    const int *mc = (const int *)e->dMcount.p;
 #define GT_FIN(N)                                                                            \
     case N:                                                                                  \
         CK(cudaFuncSetAttribute((const void *)gtk::linear_finish_kernel<PACKED, N>,          \
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
         gtk::linear_finish_kernel<PACKED, N><<<grid, threads, smem, e->stream>>>(            \
-            D, g, pitch, nb, S, cnt, gs, ml, e->mcap, out, iout, stride, wpc);                            \
+            D, g, pitch, nb, S, cnt, gs, ml, e->mcap, mc, out, iout, stride, wpc);                            \
         break;
     switch (NT2) {
         GT_FIN(1) GT_FIN(2) GT_FIN(3) GT_FIN(4) GT_FIN(5)
@@ -516,7 +517,8 @@ static int run_linear(gt_engine *e, const void *geno, int64_t pitch, bool packed
     const GtDesignDev &D = e->D;
     const ContractEntry &ce = kContract[e->contract_idx];
     const int tile = 32 * ce.rows;
-    const int kBatch = 1 << 16;
+    // a multiple of the tcgen05 kernel's wave (148 SMs x 2 CTAs x 128 SNPs)
+    const int kBatch = 148 * 2 * 128 * 2;
     int rc;
     const int bmax = std::min<int>(n_snps, kBatch);
     if ((rc = e->dS.reserve((size_t)bmax * D.NCP * 8))) return rc;
@@ -526,8 +528,9 @@ static int run_linear(gt_engine *e, const void *geno, int64_t pitch, bool packed
     if (tc) {
         // per-SNP list of missing samples written by the tcgen05 kernel:
         // room for 4 % missing (overflow falls back to re-scanning the row)
-        e->mcap = std::max(64, (D.n_file + 24) / 25);
+        e->mcap = std::max(64, (D.n_file + 24) / 25) & ~1;
         if ((rc = e->dMlist.reserve((size_t)bmax * e->mcap * 4))) return rc;
+        if ((rc = e->dMcount.reserve((size_t)bmax * 2 * 4))) return rc;
     }
     CK(cudaFuncSetAttribute((const void *)ce.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ce.smem));
     gtk::FinishLayout lay = gtk::finish_layout(D.L, D.p, D.I);

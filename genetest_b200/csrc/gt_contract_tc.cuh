@@ -17,7 +17,8 @@
 //   D (128 x N int32) accumulates in TMEM; one elected thread issues
 //     tcgen05.mma.cta_group::1.kind::i8 (M=128, N, K=32), tcgen05.commit
 //     releases the stage.
-// Warp roles: 0-3 expand + epilogue, 4 bulk-copy producer, 5 MMA issuer.
+// Warp roles: 0-7 expand + epilogue (two threads per SNP row, 64 samples of a
+// stage each), 8 bulk-copy producer, 9 MMA issuer.  Two CTAs per SM.
 #pragma once
 
 #include "gt_common.cuh"
@@ -26,7 +27,7 @@ namespace gtk {
 
 constexpr int kTcStages = 4;          // pipeline depth (A in TMEM, B in smem)
 constexpr int kTcStageK = 128;        // samples per stage (4 MMAs of K=32)
-constexpr int kTcThreads = 192;
+constexpr int kTcThreads = 320;       // 8 expansion warps, 1 producer, 1 MMA issuer
 
 struct TcParams {
     const uint8_t *geno;      // packed rows
@@ -43,8 +44,9 @@ struct TcParams {
     int *counts;
     double *gsum;
     int *error_flag;          // set when a bounded wait times out
-    int *mlist;               // [n_snps][mcap] positions of the missing samples, in order
-    int mcap;                 // capacity per SNP (counts[3] = -1 when it overflowed)
+    int *mlist;               // [n_snps][2][mcap / 2] positions of the missing samples
+    int mcap;                 // capacity per SNP (two halves)
+    int *mcount;              // [n_snps][2] entries per half, -1 when a half overflowed
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -118,10 +120,11 @@ contract_tc_kernel(TcParams P) {
              *d_full = bars + 3 * kTcStages;
     uint32_t *tmem_slot = (uint32_t *)(bars + 3 * kTcStages + 1);
     int *fail = (int *)(tmem_slot + 1);
+    int *cnt_s = (int *)(tmem_slot + 2);                 // [128][3] counts of the second half
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
-        for (int s = 0; s < kTcStages; ++s) { mbar_init(&a_full[s], 128); mbar_init(&b_full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < kTcStages; ++s) { mbar_init(&a_full[s], 256); mbar_init(&b_full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(d_full, 1);
         *fail = 0;
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -139,26 +142,29 @@ contract_tc_kernel(TcParams P) {
     const uint32_t tmem_a = tmem_base + N;               // kTcStages x 32 columns
     const int n_stages = P.n_stages;
 
-    if (warp < 4) {
-        // ===== expansion: thread <-> SNP row =====
-        const int row = warp * 32 + lane;
+    if (warp < 8) {
+        // ===== expansion: two threads per SNP row, 64 samples of a stage each =====
+        const int half = warp >> 2;
+        const int row = (warp & 3) * 32 + lane;
         const int snp = min(blockIdx.x * 128 + row, P.n_snps - 1);
-        const unsigned char *grow = P.geno + (long long)snp * P.pitch;
-        const uint32_t lane_base = ((uint32_t)(warp * 32)) << 16;
+        const unsigned char *grow = P.geno + (long long)snp * P.pitch + half * 16;
+        const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
         int nhet = 0, nhom = 0, nmis = 0;
-        // this thread is the only one that sees the row: it can emit the list of
-        // its missing samples in order, without atomics
+        // the two threads of a row see disjoint samples: each emits its own
+        // in-order list of missing samples, no atomics
         const bool owner = blockIdx.x * 128 + row < P.n_snps;
-        int *mrow = P.mlist + (long long)snp * P.mcap;
+        const int hcap = P.mcap >> 1;
+        int *mrow = P.mlist + (long long)snp * P.mcap + half * hcap;
         int mcur = 0;
-        // a 128-B line of the row (512 samples = 4 stages) lives in registers
-        uint4 cur[8], nxt[8];
+        // the thread's 16 B of four consecutive stages live in registers
+        uint4 cur[4], nxt[4];
         const int n_lines = (n_stages + 3) / 4;
         auto load_line = [&](int line, uint4 *dst) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                long long off = (long long)line * 128 + q * 16;
-                dst[q] = (off + 16 <= P.pitch) ? ldg_stream16(grow + off) : make_uint4(~0u, ~0u, ~0u, ~0u);
+            for (int q = 0; q < 4; ++q) {
+                long long off = (long long)line * 128 + q * 32;
+                dst[q] = (off + half * 16 + 16 <= P.pitch) ? ldg_stream16(grow + off)
+                                                           : make_uint4(~0u, ~0u, ~0u, ~0u);
             }
         };
         load_line(0, cur);
@@ -170,80 +176,91 @@ contract_tc_kernel(TcParams P) {
                 if (it >= n_stages) break;
                 const int s = it % kTcStages;
                 const uint32_t par = ((it / kTcStages) & 1) ^ 1;
+                // mask words of this half stage (same for every row: broadcast load)
+                const long long moff = (long long)it * 32 + half * 16;
+                const uint4 m4 = (moff + 16 <= P.pitch) ? __ldg((const uint4 *)(P.ormask + moff))
+                                                        : make_uint4(~0u, ~0u, ~0u, ~0u);
+                const uint4 pw = cur[sub];
+                const uint32_t words[4] = {pw.x, pw.y, pw.z, pw.w};
+                const uint32_t masks[4] = {m4.x, m4.y, m4.z, m4.w};
+                uint32_t a[16];
+                uint32_t mflag[2];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t w = words[j];
+                    const uint32_t wm = w | masks[j];
+                    const uint32_t lo = wm & 0x55555555u, hi = (wm >> 1) & 0x55555555u;
+                    const uint32_t mb = lo & ~hi;
+                    nmis += __popc(mb);
+                    nhet += __popc(hi & ~lo);
+                    nhom += __popc(~(lo | hi) & 0x55555555u);
+                    // flags of two consecutive words share one 32-bit word
+                    if (j & 1) mflag[j >> 1] |= mb << 1; else mflag[j >> 1] = mb;
+                    // code -> dosage byte: 00 -> 2, 01 -> 0, 10 -> 1, 11 -> 0
+                    const uint32_t even = w & 0x33333333u, odd = (w >> 2) & 0x33333333u;
+                    a[j * 4 + 0] = prmt(0x00010002u, 0u, even);
+                    a[j * 4 + 1] = prmt(0x00010002u, 0u, even >> 16);
+                    a[j * 4 + 2] = prmt(0x00010002u, 0u, odd);
+                    a[j * 4 + 3] = prmt(0x00010002u, 0u, odd >> 16);
+                }
+                if (owner) {        // emit the missing samples of this half stage, in order
+                    unsigned long long m = (unsigned long long)mflag[0] | ((unsigned long long)mflag[1] << 32);
+                    while (m) {
+                        int b = __ffsll((long long)m) - 1;
+                        int word = half * 4 + (b >> 5) * 2 + (b & 1);
+                        if (mcur < hcap) mrow[mcur] = it * kTcStageK + word * 16 + ((b & 31) >> 1);
+                        ++mcur;
+                        m &= m - 1;
+                    }
+                }
+                // publish the PREVIOUS stage only now: its TMEM store drained while
+                // this stage's bytes were being expanded
+                if (it > 0) {
+                    asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+                    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+                    mbar_arrive(&a_full[(it - 1) % kTcStages]);
+                }
                 if (it >= kTcStages && !mbar_wait(&empty[s], par, fail)) { *fail = 1; }
                 asm volatile("tcgen05.fence::after_thread_sync;\n");
-                // mask words of this stage (same for every row: broadcast loads)
-                const uint4 *mk = (const uint4 *)(P.ormask + (long long)it * 32);
-                uint32_t a[32];
-                uint32_t mflag[4];
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const uint4 pw = cur[sub * 2 + h];
-                    uint4 m4 = ((long long)it * 32 + h * 16 + 16 <= P.pitch) ? __ldg(mk + h) : make_uint4(~0u, ~0u, ~0u, ~0u);
-                    const uint32_t words[4] = {pw.x, pw.y, pw.z, pw.w};
-                    const uint32_t masks[4] = {m4.x, m4.y, m4.z, m4.w};
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const uint32_t w = words[j];
-                        const uint32_t wm = w | masks[j];
-                        uint32_t lo = wm & 0x55555555u, hi = (wm >> 1) & 0x55555555u;
-                        uint32_t mb = lo & ~hi;
-                        nmis += __popc(mb);
-                        // flags of two consecutive words share one 32-bit word:
-                        // even bits <- word 2m, odd bits <- word 2m + 1
-                        if (j & 1) mflag[h * 2 + (j >> 1)] |= mb << 1;
-                        else mflag[h * 2 + (j >> 1)] = mb;
-                        nhet += __popc(hi & ~lo);
-                        nhom += __popc(~(lo | hi) & 0x55555555u);
-                        // code -> dosage byte: 00 -> 2, 01 -> 0, 10 -> 1, 11 -> 0
-                        const uint32_t even = w & 0x33333333u, odd = (w >> 2) & 0x33333333u;
-                        const int o = (h * 4 + j) * 4;
-                        a[o + 0] = prmt(0x00010002u, 0u, even & 0xFFFFu);
-                        a[o + 1] = prmt(0x00010002u, 0u, even >> 16);
-                        a[o + 2] = prmt(0x00010002u, 0u, odd & 0xFFFFu);
-                        a[o + 3] = prmt(0x00010002u, 0u, odd >> 16);
-                    }
-                }
-                // emit the stage's missing samples (in order) once per stage
-                if (owner) {
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        unsigned long long m = (unsigned long long)mflag[2 * q] |
-                                               ((unsigned long long)mflag[2 * q + 1] << 32);
-                        while (m) {
-                            int b = __ffsll((long long)m) - 1;
-                            // bit b: 32-bit group b / 32 (two words), word parity b & 1, sample (b % 32) / 2
-                            int word = q * 4 + (b >> 5) * 2 + (b & 1);
-                            if (mcur < P.mcap) mrow[mcur] = it * kTcStageK + word * 16 + ((b & 31) >> 1);
-                            ++mcur;
-                            m &= m - 1;
-                        }
-                    }
-                }
-                const uint32_t taddr = tmem_a + lane_base + s * 32;
+                const uint32_t taddr = tmem_a + lane_base + s * 32 + half * 16;
                 asm volatile(
-                    "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-                    "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
-                    "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};\n"
+                    "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+                    "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};\n"
                     ::"r"(taddr),
                       "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
-                      "r"(a[8]), "r"(a[9]), "r"(a[10]), "r"(a[11]), "r"(a[12]), "r"(a[13]), "r"(a[14]), "r"(a[15]),
-                      "r"(a[16]), "r"(a[17]), "r"(a[18]), "r"(a[19]), "r"(a[20]), "r"(a[21]), "r"(a[22]), "r"(a[23]),
-                      "r"(a[24]), "r"(a[25]), "r"(a[26]), "r"(a[27]), "r"(a[28]), "r"(a[29]), "r"(a[30]), "r"(a[31])
+                      "r"(a[8]), "r"(a[9]), "r"(a[10]), "r"(a[11]), "r"(a[12]), "r"(a[13]), "r"(a[14]), "r"(a[15])
                     : "memory");
-                asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
-                asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-                mbar_arrive(&a_full[s]);
             }
 #pragma unroll
-            for (int q = 0; q < 8; ++q) cur[q] = nxt[q];
+            for (int q = 0; q < 4; ++q) cur[q] = nxt[q];
         }
-        // ===== epilogue: D (int32, TMEM) -> FP64 sums =====
+        if (n_stages > 0) {
+            asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+            mbar_arrive(&a_full[(n_stages - 1) % kTcStages]);
+        }
+        // the second half hands its class counts to the first
+        if (half == 1) { cnt_s[row * 3 + 0] = nhet; cnt_s[row * 3 + 1] = nhom; cnt_s[row * 3 + 2] = nmis; }
+        asm volatile("bar.sync 1, 256;\n" ::: "memory");
+        const int out_snp = blockIdx.x * 128 + row;
+        if (out_snp < P.n_snps) {
+            P.mcount[(long long)out_snp * 2 + half] = (mcur <= hcap) ? mcur : -1;
+            if (half == 0) {
+                nhet += cnt_s[row * 3 + 0]; nhom += cnt_s[row * 3 + 1]; nmis += cnt_s[row * 3 + 2];
+                P.counts[(long long)out_snp * 4 + 0] = nhet;
+                P.counts[(long long)out_snp * 4 + 1] = nhom;
+                P.counts[(long long)out_snp * 4 + 2] = nmis;
+                P.counts[(long long)out_snp * 4 + 3] = 0;
+                P.gsum[(long long)out_snp * 2 + 0] = (double)(nhet + 2 * nhom);
+                P.gsum[(long long)out_snp * 2 + 1] = (double)(nhet + 4 * nhom);
+                for (int col = P.ncol; col < P.NCP; ++col) P.S[(long long)out_snp * P.NCP + col] = 0.0;
+            }
+        }
+        // ===== epilogue: D (int32, TMEM) -> FP64 sums; the halves interleave 32-column groups =====
         if (!mbar_wait(d_full, 0, fail)) *fail = 1;
         asm volatile("tcgen05.fence::after_thread_sync;\n");
-        const int out_snp = blockIdx.x * 128 + row;
 #pragma unroll 1
-        for (int c0 = 0; c0 < N; c0 += 32) {
+        for (int c0 = half * 32; c0 < N; c0 += 64) {
             uint32_t d[32];
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -265,17 +282,8 @@ contract_tc_kernel(TcParams P) {
                     P.S[(long long)out_snp * P.NCP + col] = acc * P.scale[col];
             }
         }
-        if (out_snp < P.n_snps) {
-            for (int col = P.ncol; col < P.NCP; ++col) P.S[(long long)out_snp * P.NCP + col] = 0.0;
-            P.counts[(long long)out_snp * 4 + 0] = nhet;
-            P.counts[(long long)out_snp * 4 + 1] = nhom;
-            P.counts[(long long)out_snp * 4 + 2] = nmis;
-            P.counts[(long long)out_snp * 4 + 3] = (mcur <= P.mcap) ? mcur : -1;
-            P.gsum[(long long)out_snp * 2 + 0] = (double)(nhet + 2 * nhom);
-            P.gsum[(long long)out_snp * 2 + 1] = (double)(nhet + 4 * nhom);
-        }
         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-    } else if (warp == 4) {
+    } else if (warp == 8) {
         // ===== B producer: one bulk copy per stage =====
         if (lane == 0) {
             for (int it = 0; it < n_stages; ++it) {

@@ -77,7 +77,8 @@ __device__ __forceinline__ void dmma884_lin(double &c0, double &c1, double a, do
 template <bool PACKED, int NT2>
 __device__ __forceinline__ void subtract_missing(const GtDesignDev &D, const void *rowp,
                                                  double *S0, double *stage, int *queue,
-                                                 int lane, const int *mlist, int mcount) {
+                                                 int lane, const int *mlist, int mcountA,
+                                                 int mcountB, int hcap) {
     constexpr int LS = finish_stage_stride(NT2);
     const int L = D.L;
     const int nlive = D.lean ? D.k + 1 : L;      // columns present in E
@@ -134,7 +135,8 @@ __device__ __forceinline__ void subtract_missing(const GtDesignDev &D, const voi
         return has;
     };
 
-    if (mlist != nullptr && mcount >= 0) {
+    if (mlist != nullptr && mcountA >= 0 && mcountB >= 0) {
+        const int mcount = mcountA + mcountB;
         // the contraction kernel already listed the missing samples: gather
         // group g + 1 while the tensor cores work on group g
         constexpr int NV = 4 * NT2;                      // double2 per base vector
@@ -142,7 +144,7 @@ __device__ __forceinline__ void subtract_missing(const GtDesignDev &D, const voi
         double2 regs[NV];
         auto fetch = [&](int g) {
             int t = g * 32 + lane;
-            int idx = (t < mcount) ? mlist[t] : -1;
+            int idx = (t < mcount) ? (t < mcountA ? mlist[t] : mlist[hcap + t - mcountA]) : -1;
             const double2 *er = (const double2 *)(D.E + (long long)(idx < 0 ? 0 : idx) * D.NCP);
 #pragma unroll
             for (int c = 0; c < NV; ++c)
@@ -237,6 +239,7 @@ __global__ void __launch_bounds__(256, 2)
 linear_finish_kernel(GtDesignDev D, const void *__restrict__ geno, long long pitch, int n_snps,
                      const double *__restrict__ S, const int *__restrict__ counts,
                      const double *__restrict__ gsum, const int *__restrict__ mlist, int mcap,
+                     const int *__restrict__ mcount,
                      double *__restrict__ out, int *__restrict__ iout, long long ostride,
                      int wpc) {
     extern __shared__ __align__(16) double sm[];
@@ -268,9 +271,11 @@ linear_finish_kernel(GtDesignDev D, const void *__restrict__ geno, long long pit
     if (n_miss > 0) {
         const void *rowp = PACKED ? (const void *)((const uint8_t *)geno + (long long)snp * pitch)
                                   : (const void *)((const double *)geno + (long long)snp * pitch);
-        const int mcount = mlist ? counts[(long long)snp * 4 + 3] : -1;
+        const int mA = mlist ? mcount[(long long)snp * 2] : -1;
+        const int mB = mlist ? mcount[(long long)snp * 2 + 1] : -1;
         subtract_missing<PACKED, NT2>(D, rowp, S0, stage, queue, lane,
-                                      mlist ? mlist + (long long)snp * mcap : nullptr, mcount);
+                                      mlist ? mlist + (long long)snp * mcap : nullptr, mA, mB,
+                                      mcap >> 1);
     }
     __syncwarp();
 
