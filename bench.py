@@ -283,6 +283,7 @@ def run_ours(args, rank, world, local_rank):
         print("rank {} local ms/step {:.2f}".format(rank, ms / args.steps),
               file=sys.stderr, flush=True)
     kms, klaunches, all_launches = eng.kernel_time()
+    breakdown = eng.kernel_breakdown()
     eng.enable_timing(False)
     clocks = sampler.stop() if sampler else None
     if world > 1:
@@ -375,6 +376,8 @@ def run_ours(args, rank, world, local_rank):
                                 else eng.dominant_kernel()),
                      "kernel_ms_per_launch": kernel_ms,
                      "kernel_share_of_step": kms / ms,
+                     "step_breakdown_ms": {k: v / args.steps
+                                           for k, v in breakdown.items()},
                      "algorithmic_bytes_per_snp": bytes_per_snp,
                      "fp64": {"achieved_tflops": fp64_achieved,
                               "peak_tflops_measured": fp64_peak,

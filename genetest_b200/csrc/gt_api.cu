@@ -28,14 +28,18 @@ struct gt_engine {
     DevBuf dE, dMask, dFF0, dR, dRinv, dTq, dIter;   // design
     DevBuf dBimg, dScale, dErr;                      // tcgen05 contraction (lean designs)
     bool use_tc = false;
-    int tc_N = 0, tc_stages = 0, tc_ncol = 0;
-    DevBuf dS, dCounts, dGsum, dMlist, dMcount; // per-batch workspace
+    int tc_dbg = 0;
+    bool split_corr = false;   // run the missing-sample corrections as their own kernel
+    int tc_N = 0, tc_stages = 0, tc_ncol = 0, tc_mask_zero_lines = 0;
+    DevBuf dS, dCounts, dGsum, dMlist, dMcount, dCorr; // per-batch workspace
     int mcap = 0;
     DevBuf dGeno, dOut, dIout;                 // staging of the *_host entry points
     int contract_idx = -1;
     // timing
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
+    std::vector<int> event_class;      // 0 contraction, 1 corrections, 2 finish / iterative
+    double ms_class[4] = {0, 0, 0, 0};
     size_t events_used = 0;
     double ms_total = 0.0;
     int64_t launches = 0, all_launches = 0;
@@ -149,8 +153,57 @@ __global__ void dmma_peak_kernel(double *sink, int iters, double a, double b) {
     if (s == 123.456) sink[0] = s;
 }
 
+// Access-pattern probe (tests / tuning only): 128 rows per CTA, `tpr` threads
+// per row, each thread streams `vec` x 16 B per step with `ahead` steps in
+// flight, XOR-reducing what it reads.
+__global__ void __launch_bounds__(512, 1)
+read_pattern_kernel(const uint8_t *geno, long long pitch, int n_rows, int tpr, int vec,
+                    unsigned *sink) {
+    const int row_in = threadIdx.x % 128, part = threadIdx.x / 128;
+    if (part >= tpr) return;
+    const int row = min(blockIdx.x * 128 + row_in, n_rows - 1);
+    const uint4 *p = (const uint4 *)(geno + (long long)row * pitch);
+    const long long nvec = pitch / 16;
+    unsigned acc = 0;
+    // step = tpr * vec uint4 per row; this thread takes [part*vec, part*vec+vec)
+    for (long long base = 0; base + (long long)tpr * vec <= nvec; base += (long long)tpr * vec) {
+        for (int v = 0; v < vec; ++v) {
+            uint4 x = gtk::ldg_stream16(p + base + part * vec + v);
+            acc ^= x.x ^ x.y ^ x.z ^ x.w;
+        }
+    }
+    if (acc == 0x12345678u) sink[0] = acc;
+}
+
 // ---------------------------------------------------------------------------
 extern "C" {
+
+int gt_debug_read_pattern(gt_engine *e, const uint8_t *packed_dev, int64_t pitch, int32_t n_rows,
+                          int tpr, int vec, int ctas_per_sm, double *gbs) {
+    if (!e || !gbs) return fail(GT_E_ARG, "gt_debug_read_pattern: NULL argument");
+    CK(cudaSetDevice(e->device));
+    int rc = e->dS.reserve(64);
+    if (rc) return rc;
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    int grid = (n_rows + 127) / 128;
+    (void)ctas_per_sm;
+    double best = 0;
+    for (int rep = 0; rep < 3; ++rep) {
+        CK(cudaEventRecord(a, e->stream));
+        read_pattern_kernel<<<grid, 128 * tpr, 0, e->stream>>>(packed_dev, pitch, n_rows, tpr, vec,
+                                                              (unsigned *)e->dS.p);
+        CK(cudaEventRecord(b, e->stream));
+        CK(cudaEventSynchronize(b));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, a, b));
+        double g = (double)n_rows * pitch / (ms * 1e-3) / 1e9;
+        if (g > best) best = g;
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    *gbs = best;
+    return 0;
+}
 
 int gt_abi_version(void) { return GT_ABI_VERSION; }
 const char *gt_last_error(void) { return g_err.c_str(); }
@@ -185,7 +238,7 @@ int gt_engine_destroy(gt_engine *e) {
     cudaStreamSynchronize(e->stream);
     for (auto &ev : e->events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     DevBuf *bufs[] = {&e->dE, &e->dMask, &e->dFF0, &e->dR, &e->dRinv, &e->dTq, &e->dIter, &e->dBimg, &e->dScale, &e->dErr,
-                      &e->dS, &e->dCounts, &e->dGsum, &e->dMlist, &e->dMcount, &e->dGeno, &e->dOut, &e->dIout};
+                      &e->dS, &e->dCounts, &e->dGsum, &e->dMlist, &e->dMcount, &e->dCorr, &e->dGeno, &e->dOut, &e->dIout};
     for (DevBuf *b : bufs) b->release();
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
@@ -215,7 +268,8 @@ int gt_engine_synchronize(gt_engine *e) {
     for (size_t i = 0; i < e->events_used; ++i) {
         float ms = 0.f;
         CK(cudaEventElapsedTime(&ms, e->events[i].first, e->events[i].second));
-        e->ms_total += ms;
+        if (e->event_class[i] == 0) e->ms_total += ms;
+        e->ms_class[e->event_class[i] & 3] += ms;
     }
     e->events_used = 0;
     return 0;
@@ -224,6 +278,8 @@ int gt_engine_synchronize(gt_engine *e) {
 int gt_engine_set_option(gt_engine *e, const char *name, int value) {
     if (!e || !name) return fail(GT_E_ARG, "gt_engine_set_option: NULL argument");
     if (std::strcmp(name, "contract_tc") == 0) { e->use_tc = value != 0; return 0; }
+    if (std::strcmp(name, "tc_debug") == 0) { e->tc_dbg = value; return 0; }
+    if (std::strcmp(name, "split_corrections") == 0) { e->split_corr = value != 0; return 0; }
     return fail(GT_E_ARG, "gt_engine_set_option: unknown option '%s'", name);
 }
 
@@ -231,6 +287,7 @@ int gt_engine_enable_timing(gt_engine *e, int on) {
     if (!e) return fail(GT_E_ARG, "engine is NULL");
     e->timing = on != 0;
     e->ms_total = 0.0; e->launches = 0; e->all_launches = 0; e->events_used = 0;
+    for (double &m : e->ms_class) m = 0.0;
     return 0;
 }
 
@@ -243,6 +300,12 @@ int gt_engine_kernel_time(gt_engine *e, double *ms_total, int64_t *launches, int
 }
 
 const char *gt_engine_dominant_kernel(const gt_engine *e) { return e ? e->dominant.c_str() : ""; }
+
+int gt_engine_kernel_breakdown(gt_engine *e, double *ms4) {
+    if (!e || !ms4) return fail(GT_E_ARG, "gt_engine_kernel_breakdown: NULL argument");
+    for (int i = 0; i < 4; ++i) ms4[i] = e->ms_class[i];
+    return 0;
+}
 
 int gt_engine_num_params(const gt_engine *e) {
     if (!e || !e->have_design) return fail(GT_E_STATE, "no design set");
@@ -402,6 +465,14 @@ int gt_engine_set_design(gt_engine *e, const gt_design_desc *d) {
             if ((rc = e->dErr.reserve(16))) return rc;
             CK(cudaMemsetAsync(e->dErr.p, 0, 16, st));
             e->tc_N = N; e->tc_stages = n_st; e->tc_ncol = ncol;
+            int zl = 0;
+            while ((size_t)(zl + 1) * 128 <= mask.size()) {
+                bool zero = true;
+                for (int b = 0; b < 128 && zero; ++b) zero = mask[(size_t)zl * 128 + b] == 0;
+                if (!zero) break;
+                ++zl;
+            }
+            e->tc_mask_zero_lines = zl;
         }
         if ((rc = upload(e->dFF0, FF0.data(), FF0.size() * 8, st))) return rc;
         if ((rc = upload(e->dR, H.R.data(), H.R.size() * 8, st))) return rc;
@@ -440,13 +511,15 @@ int gt_engine_set_design(gt_engine *e, const gt_design_desc *d) {
 }  // extern "C"
 
 // ---------------------------------------------------------------------------
-static int time_begin(gt_engine *e) {
+static int time_begin(gt_engine *e, int cls = 0) {
     if (!e->timing) return -1;
     if (e->events_used == e->events.size()) {
         cudaEvent_t a, b;
         if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return -1;
         e->events.emplace_back(a, b);
+        e->event_class.push_back(0);
     }
+    e->event_class[e->events_used] = cls;
     cudaEventRecord(e->events[e->events_used].first, e->stream);
     return (int)e->events_used;
 }
@@ -454,7 +527,7 @@ static void time_end(gt_engine *e, int slot) {
     if (slot < 0) return;
     cudaEventRecord(e->events[slot].second, e->stream);
     e->events_used++;
-    e->launches++;
+    if (e->event_class[slot] == 0) e->launches++;
 }
 
 static int e_n_file(const gt_engine *e) { return e->model == GT_MODEL_LINEAR ? e->D.n_file : e->T.n_file; }
@@ -467,6 +540,7 @@ static int launch_contract_tc(gt_engine *e, const uint8_t *g, int64_t pitch, int
     P.S = (double *)e->dS.p; P.counts = (int *)e->dCounts.p; P.gsum = (double *)e->dGsum.p;
     P.error_flag = (int *)e->dErr.p;
     P.mlist = (int *)e->dMlist.p; P.mcap = e->mcap; P.mcount = (int *)e->dMcount.p;
+    P.mask_zero_lines = e->tc_mask_zero_lines; P.dbg = e->tc_dbg;
     const int grid = (nb + 127) / 128;
     const int NT = e->tc_N / 16;
     size_t smem = (size_t)gtk::kTcStages * e->tc_N * 128 + 1024 + 256 + 128 * 3 * 4;
@@ -496,17 +570,39 @@ static int launch_finish(gt_engine *e, int NT2, int grid, int threads, size_t sm
     const double *gs = (const double *)e->dGsum.p;
     const int *ml = use_list ? (const int *)e->dMlist.p : nullptr;
     const int *mc = (const int *)e->dMcount.p;
+    const double *corr = (use_list && e->split_corr) ? (const double *)e->dCorr.p : nullptr;
+    if (use_list && e->split_corr) {
+        const int cw = 8;
+        size_t csm = (size_t)cw * 32 * gtk::finish_stage_stride(NT2) * 8;
+        int cgrid = (nb + cw - 1) / cw;
+#define GT_COR(N)                                                                          \
+    case N:                                                                                \
+        gtk::missing_corr_kernel<N><<<cgrid, cw * 32, csm, e->stream>>>(                   \
+            D, nb, ml, e->mcap, mc, (double *)e->dCorr.p);                                 \
+        break;
+        int cslot = time_begin(e, 1);
+        switch (NT2) {
+            GT_COR(1) GT_COR(2) GT_COR(3) GT_COR(4) GT_COR(5)
+            default: return fail(GT_E_UNSUPPORTED, "correction kernel: design too wide");
+        }
+        time_end(e, cslot);
+#undef GT_COR
+        CK(cudaGetLastError());
+        e->all_launches += 1;
+    }
 #define GT_FIN(N)                                                                            \
     case N:                                                                                  \
         CK(cudaFuncSetAttribute((const void *)gtk::linear_finish_kernel<PACKED, N>,          \
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
         gtk::linear_finish_kernel<PACKED, N><<<grid, threads, smem, e->stream>>>(            \
-            D, g, pitch, nb, S, cnt, gs, ml, e->mcap, mc, out, iout, stride, wpc);                            \
+            D, g, pitch, nb, S, cnt, gs, ml, e->mcap, mc, corr, out, iout, stride, wpc);                            \
         break;
+    int fslot = time_begin(e, 2);
     switch (NT2) {
         GT_FIN(1) GT_FIN(2) GT_FIN(3) GT_FIN(4) GT_FIN(5)
         default: return fail(GT_E_UNSUPPORTED, "finish kernel: design too wide");
     }
+    time_end(e, fslot);
 #undef GT_FIN
     CK(cudaGetLastError());
     return 0;
@@ -531,6 +627,7 @@ static int run_linear(gt_engine *e, const void *geno, int64_t pitch, bool packed
         e->mcap = std::max(64, (D.n_file + 24) / 25) & ~1;
         if ((rc = e->dMlist.reserve((size_t)bmax * e->mcap * 4))) return rc;
         if ((rc = e->dMcount.reserve((size_t)bmax * 2 * 4))) return rc;
+        if ((rc = e->dCorr.reserve((size_t)bmax * D.L * D.L * 8))) return rc;
     }
     CK(cudaFuncSetAttribute((const void *)ce.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ce.smem));
     gtk::FinishLayout lay = gtk::finish_layout(D.L, D.p, D.I);

@@ -47,6 +47,8 @@ struct TcParams {
     int *mlist;               // [n_snps][2][mcap / 2] positions of the missing samples
     int mcap;                 // capacity per SNP (two halves)
     int *mcount;              // [n_snps][2] entries per half, -1 when a half overflowed
+    int mask_zero_lines;      // leading 128-B lines of ormask that are entirely zero
+    int dbg;                  // tuning only: 1 no list emission, 2 no MMA, 4 no TMEM store, 8 no loads, 16 no counts
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -157,29 +159,35 @@ contract_tc_kernel(TcParams P) {
         int *mrow = P.mlist + (long long)snp * P.mcap + half * hcap;
         int mcur = 0;
         // the thread's 16 B of four consecutive stages live in registers
-        uint4 cur[4], nxt[4];
+        uint4 cur[4], nxt[4], nx2[4];      // two lines of prefetch cover the DRAM latency
         const int n_lines = (n_stages + 3) / 4;
         auto load_line = [&](int line, uint4 *dst) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 long long off = (long long)line * 128 + q * 32;
-                dst[q] = (off + half * 16 + 16 <= P.pitch) ? ldg_stream16(grow + off)
+                dst[q] = (off + half * 16 + 16 <= P.pitch && !(P.dbg & 8)) ? ldg_stream16(grow + off)
                                                            : make_uint4(~0u, ~0u, ~0u, ~0u);
             }
         };
         load_line(0, cur);
+        if (n_lines > 1) load_line(1, nxt);
         for (int line = 0; line < n_lines; ++line) {
-            if (line + 1 < n_lines) load_line(line + 1, nxt);
 #pragma unroll
             for (int sub = 0; sub < 4; ++sub) {
+                // Prefetch two lines ahead, issued in the MIDDLE of the line: the
+                // scoreboard that guards `cur` at the top of the next line also
+                // counts these loads, so they must be old by then.
+                if (sub == 2 && line + 2 < n_lines) load_line(line + 2, nx2);
                 const int it = line * 4 + sub;
                 if (it >= n_stages) break;
                 const int s = it % kTcStages;
                 const uint32_t par = ((it / kTcStages) & 1) ^ 1;
                 // mask words of this half stage (same for every row: broadcast load)
                 const long long moff = (long long)it * 32 + half * 16;
-                const uint4 m4 = (moff + 16 <= P.pitch) ? __ldg((const uint4 *)(P.ormask + moff))
-                                                        : make_uint4(~0u, ~0u, ~0u, ~0u);
+                uint4 m4 = make_uint4(0u, 0u, 0u, 0u);       // every sample of the line is a design row
+                if (line >= P.mask_zero_lines)
+                    m4 = (moff + 16 <= P.pitch) ? __ldg((const uint4 *)(P.ormask + moff))
+                                                : make_uint4(~0u, ~0u, ~0u, ~0u);
                 const uint4 pw = cur[sub];
                 const uint32_t words[4] = {pw.x, pw.y, pw.z, pw.w};
                 const uint32_t masks[4] = {m4.x, m4.y, m4.z, m4.w};
@@ -191,9 +199,11 @@ contract_tc_kernel(TcParams P) {
                     const uint32_t wm = w | masks[j];
                     const uint32_t lo = wm & 0x55555555u, hi = (wm >> 1) & 0x55555555u;
                     const uint32_t mb = lo & ~hi;
-                    nmis += __popc(mb);
-                    nhet += __popc(hi & ~lo);
-                    nhom += __popc(~(lo | hi) & 0x55555555u);
+                    if (!(P.dbg & 16)) {
+                        nmis += __popc(mb);
+                        nhet += __popc(hi & ~lo);
+                        nhom += __popc(~(lo | hi) & 0x55555555u);
+                    }
                     // flags of two consecutive words share one 32-bit word
                     if (j & 1) mflag[j >> 1] |= mb << 1; else mflag[j >> 1] = mb;
                     // code -> dosage byte: 00 -> 2, 01 -> 0, 10 -> 1, 11 -> 0
@@ -203,7 +213,7 @@ contract_tc_kernel(TcParams P) {
                     a[j * 4 + 2] = prmt(0x00010002u, 0u, odd);
                     a[j * 4 + 3] = prmt(0x00010002u, 0u, odd >> 16);
                 }
-                if (owner) {        // emit the missing samples of this half stage, in order
+                if (owner && !(P.dbg & 1)) {        // emit the missing samples of this half stage, in order
                     unsigned long long m = (unsigned long long)mflag[0] | ((unsigned long long)mflag[1] << 32);
                     while (m) {
                         int b = __ffsll((long long)m) - 1;
@@ -223,6 +233,7 @@ contract_tc_kernel(TcParams P) {
                 if (it >= kTcStages && !mbar_wait(&empty[s], par, fail)) { *fail = 1; }
                 asm volatile("tcgen05.fence::after_thread_sync;\n");
                 const uint32_t taddr = tmem_a + lane_base + s * 32 + half * 16;
+                if (!(P.dbg & 4))
                 asm volatile(
                     "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
                     "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};\n"
@@ -232,7 +243,7 @@ contract_tc_kernel(TcParams P) {
                     : "memory");
             }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) cur[q] = nxt[q];
+            for (int q = 0; q < 4; ++q) { cur[q] = nxt[q]; nxt[q] = nx2[q]; }
         }
         if (n_stages > 0) {
             asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
@@ -309,6 +320,7 @@ contract_tc_kernel(TcParams P) {
                 const uint32_t bbase = smem_u32(sB + s * BSTAGE);
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {
+                    if (P.dbg & 2) break;
                     const uint64_t bdesc = tc_smem_desc(bbase + kk * 32);
                     const uint32_t acol = tmem_a + s * 32 + kk * 8;
                     const uint32_t accum = (it > 0 || kk > 0) ? 1u : 0u;

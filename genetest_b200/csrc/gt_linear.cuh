@@ -234,12 +234,100 @@ __device__ __forceinline__ void subtract_missing(const GtDesignDev &D, const voi
     __syncwarp();
 }
 
+// K3a: missing-sample corrections from the lists the tcgen05 contraction
+// emitted.  One warp per SNP, register-light (high occupancy hides the two
+// dependent loads index -> base vector); indices run two groups ahead, base
+// vectors one.  Writes Corr[snp][L*L] = sum over the missing samples of v v'.
+template <int NT2>
+__global__ void __launch_bounds__(256, 4)
+missing_corr_kernel(GtDesignDev D, int n_snps, const int *__restrict__ mlist, int mcap,
+                    const int *__restrict__ mcount, double *__restrict__ corr) {
+    constexpr int LS = finish_stage_stride(NT2);
+    constexpr int NV = 4 * NT2;
+    extern __shared__ __align__(16) double sm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int snp = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (snp >= n_snps) return;
+    const int L = D.L;
+    const int nlive = D.lean ? D.k + 1 : L;
+    const int nv = (nlive + 1) / 2;
+    double *stage = sm + (size_t)warp * 32 * LS;
+    const int mA = mcount[(long long)snp * 2], mB = mcount[(long long)snp * 2 + 1];
+    double *out = corr + (long long)snp * L * L;
+    if (mA < 0 || mB < 0) {          // a list overflowed: the finish kernel re-scans the row
+        if (lane == 0) out[0] = nan("");
+        return;
+    }
+    const int *ml = mlist + (long long)snp * mcap;
+    const int hcap = mcap >> 1, total = mA + mB;
+    double acc[NT2][NT2][2];
+#pragma unroll
+    for (int a = 0; a < NT2; ++a)
+#pragma unroll
+        for (int b = 0; b < NT2; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+    for (int t = lane; t < 32 * LS; t += 32) stage[t] = 0.0;
+    auto index_of = [&](int g) {
+        int t = g * 32 + lane;
+        return (t < total) ? (t < mA ? ml[t] : ml[hcap + t - mA]) : -1;
+    };
+    double2 regs[NV];
+    auto fetch = [&](int idx) {
+        const double2 *er = (const double2 *)(D.E + (long long)(idx < 0 ? 0 : idx) * D.NCP);
+#pragma unroll
+        for (int c = 0; c < NV; ++c) regs[c] = (idx >= 0 && c < nv) ? er[c] : make_double2(0.0, 0.0);
+    };
+    const int ngroups = (total + 31) / 32;
+    int idx_cur = ngroups > 0 ? index_of(0) : -1;
+    int idx_nxt = ngroups > 1 ? index_of(1) : -1;
+    if (ngroups > 0) fetch(idx_cur);
+    __syncwarp();
+    for (int g = 0; g < ngroups; ++g) {
+        double2 *s2 = (double2 *)(stage + lane * LS);
+#pragma unroll
+        for (int c = 0; c < NV; ++c) if (2 * c < LS) s2[c] = regs[c];
+        if (idx_cur >= 0) {
+            if (D.lean) stage[lane * LS + D.k + 1] = 1.0;
+            else if (nlive & 1) stage[lane * LS + nlive] = 0.0;
+        }
+        __syncwarp();
+        idx_cur = idx_nxt;
+        if (g + 1 < ngroups) fetch(idx_cur);
+        idx_nxt = (g + 2 < ngroups) ? index_of(g + 2) : -1;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+            const int e = ks * 4 + (lane & 3), c = lane >> 2;
+            double f[NT2];
+#pragma unroll
+            for (int t = 0; t < NT2; ++t) f[t] = stage[e * LS + t * 8 + c];
+#pragma unroll
+            for (int mt = 0; mt < NT2; ++mt)
+#pragma unroll
+                for (int nt = mt; nt < NT2; ++nt)
+                    dmma884_lin(acc[mt][nt][0], acc[mt][nt][1], f[mt], f[nt]);
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int mt = 0; mt < NT2; ++mt)
+#pragma unroll
+        for (int nt = mt; nt < NT2; ++nt)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                int r = mt * 8 + (lane >> 2), c = nt * 8 + 2 * (lane & 3) + j;
+                if (r < L && c < L && r <= c) {
+                    double v = acc[mt][nt][j];
+                    out[r * L + c] = v;
+                    if (r != c) out[c * L + r] = v;
+                }
+            }
+}
+
 template <bool PACKED, int NT2>
 __global__ void __launch_bounds__(256, 2)
 linear_finish_kernel(GtDesignDev D, const void *__restrict__ geno, long long pitch, int n_snps,
                      const double *__restrict__ S, const int *__restrict__ counts,
                      const double *__restrict__ gsum, const int *__restrict__ mlist, int mcap,
-                     const int *__restrict__ mcount,
+                     const int *__restrict__ mcount, const double *__restrict__ corr,
                      double *__restrict__ out, int *__restrict__ iout, long long ostride,
                      int wpc) {
     extern __shared__ __align__(16) double sm[];
@@ -268,7 +356,16 @@ linear_finish_kernel(GtDesignDev D, const void *__restrict__ geno, long long pit
     const int n_het = counts[(long long)snp * 4 + 0];
     const int n_hom = counts[(long long)snp * 4 + 1];
     const int n_miss = counts[(long long)snp * 4 + 2];
-    if (n_miss > 0) {
+    // corrections already accumulated by missing_corr_kernel (NaN marks a list overflow)
+    bool have_corr = false;
+    if (corr != nullptr && n_miss > 0) {
+        const double *cs = corr + (long long)snp * L * L;
+        have_corr = (cs[0] == cs[0]);
+        if (have_corr)
+            for (int t = lane; t < L * L; t += 32) S0[t] -= cs[t];
+        __syncwarp();
+    }
+    if (n_miss > 0 && !have_corr) {
         const void *rowp = PACKED ? (const void *)((const uint8_t *)geno + (long long)snp * pitch)
                                   : (const void *)((const double *)geno + (long long)snp * pitch);
         const int mA = mlist ? mcount[(long long)snp * 2] : -1;

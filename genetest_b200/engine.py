@@ -34,8 +34,8 @@ ABI_SYMBOLS = [
     "gt_packed_pitch", "gt_run_packed_dev", "gt_run_packed_host",
     "gt_run_dosage_dev", "gt_run_dosage_host", "gt_synth_packed_dev",
     "gt_engine_enable_timing", "gt_engine_kernel_time",
-    "gt_engine_dominant_kernel", "gt_measure_fp64_peak",
-    "gt_measure_dmma_peak",
+    "gt_engine_dominant_kernel", "gt_engine_kernel_breakdown", "gt_measure_fp64_peak",
+    "gt_measure_dmma_peak", "gt_debug_read_pattern",
 ]
 
 
@@ -101,8 +101,11 @@ def load_library():
                                           c.POINTER(i64), c.POINTER(i64)]
     lib.gt_engine_dominant_kernel.argtypes = [vp]
     lib.gt_engine_dominant_kernel.restype = c.c_char_p
+    lib.gt_engine_kernel_breakdown.argtypes = [vp, c.POINTER(dbl)]
     lib.gt_measure_fp64_peak.argtypes = [vp, c.POINTER(dbl)]
     lib.gt_measure_dmma_peak.argtypes = [vp, c.POINTER(dbl)]
+    lib.gt_debug_read_pattern.argtypes = [vp, vp, i64, i32, c.c_int, c.c_int,
+                                          c.c_int, c.POINTER(dbl)]
     for name in ABI_SYMBOLS:
         getattr(lib, name)
     _LIB = lib
@@ -350,10 +353,22 @@ class Engine(object):
         self._check(self.lib.gt_measure_fp64_peak(self._h, ctypes.byref(v)))
         return v.value
 
+    def read_pattern_gbs(self, packed, tpr, vec):
+        v = ctypes.c_double()
+        self._check(self.lib.gt_debug_read_pattern(
+            self._h, ctypes.c_void_p(packed.data_ptr()), packed.stride(0),
+            packed.shape[0], tpr, vec, 1, ctypes.byref(v)))
+        return v.value
+
     def dmma_peak_tflops(self):
         v = ctypes.c_double()
         self._check(self.lib.gt_measure_dmma_peak(self._h, ctypes.byref(v)))
         return v.value
+
+    def kernel_breakdown(self):
+        ms = (ctypes.c_double * 4)()
+        self._check(self.lib.gt_engine_kernel_breakdown(self._h, ms))
+        return {"contract": ms[0], "corrections": ms[1], "finish": ms[2]}
 
     def dominant_kernel(self):
         return self.lib.gt_engine_dominant_kernel(self._h).decode()

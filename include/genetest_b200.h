@@ -154,11 +154,19 @@ int gt_engine_enable_timing(gt_engine *e, int on);
 int gt_engine_kernel_time(gt_engine *e, double *ms_total, int64_t *launches,
                           int64_t *all_launches);
 const char *gt_engine_dominant_kernel(const gt_engine *e);
+/* ms[0] contraction, ms[1] missing-sample corrections, ms[2] finish / iterative
+ * kernels, ms[3] unused; accumulated while timing is enabled. */
+int gt_engine_kernel_breakdown(gt_engine *e, double *ms4);
 /* FP64 FMA throughput of the device (TFLOP/s), measured with a register-only
  * FMA kernel: the roofline denominator of the FP64-bound kernels. */
 int gt_measure_fp64_peak(gt_engine *e, double *tflops);
 /* same for the FP64 tensor-core path (mma.sync m8n8k4 f64). */
 int gt_measure_dmma_peak(gt_engine *e, double *tflops);
+/* tuning probe: bandwidth of the row-streaming access pattern (128 rows per
+ * CTA, `tpr` threads per row, `vec` x 16 B per thread and step). */
+int gt_debug_read_pattern(gt_engine *e, const uint8_t *packed_dev, int64_t pitch,
+                          int32_t n_rows, int tpr, int vec, int ctas_per_sm,
+                          double *gbs);
 
 #ifdef __cplusplus
 }
