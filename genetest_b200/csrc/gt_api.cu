@@ -27,7 +27,7 @@ struct gt_engine {
     gtk::IterDesignDev T{};           // logistic / coxph design
     DevBuf dE, dMask, dFF0, dR, dRinv, dTq, dIter;   // design
     DevBuf dBimg, dScale, dErr;                      // tcgen05 contraction (lean designs)
-    bool use_tc = false;
+    bool use_tc = true;        // lean linear designs run on the tcgen05 int8 contraction
     int tc_dbg = 0;
     bool split_corr = false;   // run the missing-sample corrections as their own kernel
     int tc_N = 0, tc_stages = 0, tc_ncol = 0, tc_mask_zero_lines = 0;
