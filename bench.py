@@ -345,6 +345,22 @@ def run_ours(args, rank, world, local_rank):
     else:
         flop_per_snp = float("nan")
     fp64_achieved = per_launch_snps * flop_per_snp / (kernel_ms * 1e-3) / 1e12
+    if args.model == "linear" and args.contract == "tc":
+        # exact fixed point on the int8 tensor cores: 8 digit planes per column
+        ops_per_snp = 2.0 * n * 8 * (p)
+        compute = {"pipe": "tcgen05 kind::i8",
+                   "achieved_tops": per_launch_snps * ops_per_snp /
+                   (kernel_ms * 1e-3) / 1e12,
+                   "nominal_dense_peak_tops": 4500.0,
+                   "ops_per_snp": ops_per_snp,
+                   "fp64_fma_peak_tflops_measured": fp64_peak,
+                   "fp64_dmma_peak_tflops_measured": dmma_peak}
+    else:
+        compute = {"pipe": "fp64", "achieved_tflops": fp64_achieved,
+                   "peak_tflops_measured": fp64_peak,
+                   "dmma_peak_tflops_measured": dmma_peak,
+                   "frac": fp64_achieved / fp64_peak if fp64_peak else None,
+                   "flop_per_snp": flop_per_snp}
 
     # ---- CPU baseline: restated reference path on the host cores ----
     cores = os.cpu_count() or 1
@@ -379,12 +395,7 @@ def run_ours(args, rank, world, local_rank):
                      "step_breakdown_ms": {k: v / args.steps
                                            for k, v in breakdown.items()},
                      "algorithmic_bytes_per_snp": bytes_per_snp,
-                     "fp64": {"achieved_tflops": fp64_achieved,
-                              "peak_tflops_measured": fp64_peak,
-                              "dmma_peak_tflops_measured": dmma_peak,
-                              "frac": fp64_achieved / fp64_peak
-                              if fp64_peak else None,
-                              "flop_per_snp": flop_per_snp}},
+                     "compute": compute},
         "cpu_baseline": {"value": cpu_value, "unit": "SNP-tests/s",
                          "cores": cores, "kind": "port",
                          "sample": "{} SNPs of the same synthetic workload in "
