@@ -247,6 +247,62 @@ class ResultBlock(object):
     def ok(self, i):
         return self.res.status[i] == 0
 
+    @property
+    def ok_mask(self):
+        return (self.res.status == 0).astype(np.uint8)
+
+    def column(self, path, subset_info=None):
+        """Values of one result path for every marker of the block: a float
+        or integer ndarray, a list of strings, or one string.  ``path`` is a
+        ``modelspec.result[...]`` path such as ``["SNPs", "coef"]``.  Raises
+        KeyError for a field the test does not produce (as a dict lookup
+        would)."""
+        from .statistics.models.survival import COX_FIELDS
+        entity, field = [getattr(x, "id", x) for x in path]
+        res = self.res
+        if entity == "MODEL":
+            if field == "nobs":
+                return (res.nobs.astype(np.int64) if self.model == "coxph"
+                        else res.nobs.astype(np.float64))
+            if field == "log_likelihood":
+                return res.llf
+            if field == "r_squared_adj" and self.model == "linear":
+                return res.stat
+            if field == "nevents" and self.model != "linear":
+                return res.stat
+            if field == "subset_info" and subset_info is not None:
+                return subset_info
+            raise KeyError(field)
+        if entity == "SNPs" and field in ("name", "chrom", "pos", "major",
+                                          "minor", "maf"):
+            flip = res.flip.astype(bool)
+            if field == "name":
+                return [str(m[0]) for m in self.meta]
+            if field == "chrom":
+                return [str(m[1]) for m in self.meta]
+            if field == "pos":
+                return [str(m[2]) for m in self.meta]
+            if field == "maf":
+                return res.maf
+            coded = [m[3] for m in self.meta]
+            ref = [m[4] for m in self.meta]
+            if field == "minor":
+                return [str(r if f else c) for c, r, f in zip(coded, ref, flip)]
+            return [str(c if f else r) for c, r, f in zip(coded, ref, flip)]
+        if entity not in self.columns:
+            raise KeyError(entity)
+        vals = res.param(self.columns.index(entity))
+        if self.model == "coxph":
+            if field not in COX_FIELDS:
+                raise KeyError(field)
+            coef, se, lo, hi, z, p = vals
+            return {"coef": coef, "std_err": se, "hr": np.exp(coef),
+                    "hr_lower_ci": np.exp(lo), "hr_upper_ci": np.exp(hi),
+                    "z_value": z, "p_value": p}[field]
+        if field not in PARAM_FIELDS:
+            raise KeyError(field)
+        return vals[PARAM_FIELDS.index(field)]
+
     def reason(self, i):
         return failure_reason(self.res, i, self.maf_t)
 
@@ -285,16 +341,29 @@ class ResultBlock(object):
 
 
 def _dispatch_block(block, subscribers, messages):
-    for i in range(len(block)):
-        if not block.ok(i):
-            reason = block.reason(i)
-            name = block.meta[i][0]
-            logger.warning("{}: {}".format(name, reason))
-            if name:
-                messages["failed"].append((name, reason))
-            continue
+    """Failures -> ``messages``; successes -> the subscribers: whole blocks
+    for sinks that define ``handle_block``, one dictionary per marker for the
+    others (the reference's protocol, ``analysis.py:659-664``)."""
+    for i in np.flatnonzero(block.res.status != 0):
+        reason = block.reason(i)
+        name = block.meta[i][0]
+        logger.warning("{}: {}".format(name, reason))
+        if name:
+            messages["failed"].append((name, reason))
+    dict_sinks = []
+    for subscriber in subscribers:
+        if hasattr(subscriber, "handle_block"):
+            try:
+                subscriber.handle_block(block)
+            except KeyError as e:
+                subscribers_module.subscriber_error(e.args[0])
+        else:
+            dict_sinks.append(subscriber)
+    if not dict_sinks:
+        return
+    for i in np.flatnonzero(block.res.status == 0):
         results = block.to_dict(i)
-        for subscriber in subscribers:
+        for subscriber in dict_sinks:
             try:
                 subscriber.handle(results)
             except KeyError as e:
@@ -448,13 +517,8 @@ def _execute_gwas(genotypes, modelspec, subscribers, y, X, variant_predicates,
                                  geno_index, rank, world)
 
     def consume(res, meta):
-        block = ResultBlock(model, fit_columns, res, meta, maf_t)
-        for s in subscribers:
-            if hasattr(s, "handle_block"):
-                s.handle_block(block)
-        _dispatch_block(
-            block, [s for s in subscribers if not hasattr(s, "handle_block")],
-            messages)
+        _dispatch_block(ResultBlock(model, fit_columns, res, meta, maf_t),
+                        subscribers, messages)
 
     if world == 1:
         for res, meta in blocks:            # stream batch by batch

@@ -17,6 +17,7 @@
 #include "gt_linear.cuh"
 #include "gt_logistic.cuh"
 #include "gt_cox.cuh"
+#include "gt_format.cuh"
 
 struct gt_engine {
     int device = 0;
@@ -206,6 +207,43 @@ int gt_debug_read_pattern(gt_engine *e, const uint8_t *packed_dev, int64_t pitch
 }
 
 int gt_abi_version(void) { return GT_ABI_VERSION; }
+
+int64_t gt_format_rows(int32_t n_rows, int32_t n_cols, const int32_t *col_type,
+                       const void *const *col_data, const uint8_t *keep, char sep,
+                       char *out, int64_t out_cap) {
+    if (!col_type || !col_data || !out) return fail(GT_E_ARG, "gt_format_rows: NULL argument");
+    std::vector<const char *> cursor(n_cols, nullptr);
+    for (int c = 0; c < n_cols; ++c)
+        if (col_type[c] == 0 || col_type[c] == 3) cursor[c] = (const char *)col_data[c];
+    char *p = out, *end = out + out_cap;
+    for (int r = 0; r < n_rows; ++r) {
+        const bool emit = !keep || keep[r];
+        for (int c = 0; c < n_cols; ++c) {
+            if (col_type[c] == 0) {                 // NUL-separated strings, one per row
+                const char *s = cursor[c];
+                size_t len = std::strlen(s);
+                cursor[c] = s + len + 1;
+                if (!emit) continue;
+                if (p + len + 2 > end) return fail(GT_E_ARG, "gt_format_rows: output buffer too small");
+                std::memcpy(p, s, len); p += len;
+            } else {
+                if (!emit) continue;
+                if (p + 48 > end) return fail(GT_E_ARG, "gt_format_rows: output buffer too small");
+                if (col_type[c] == 1) p = gtk::format_double_repr(((const double *)col_data[c])[r], p);
+                else if (col_type[c] == 2) {
+                    auto res = std::to_chars(p, p + 24, ((const int64_t *)col_data[c])[r]);
+                    p = res.ptr;
+                } else if (col_type[c] == 3) {      // one constant string for every row
+                    size_t len = std::strlen(cursor[c]);
+                    if (p + len + 2 > end) return fail(GT_E_ARG, "gt_format_rows: output buffer too small");
+                    std::memcpy(p, cursor[c], len); p += len;
+                } else return fail(GT_E_ARG, "gt_format_rows: bad column type %d", col_type[c]);
+            }
+            *p++ = (c + 1 < n_cols) ? sep : '\n';
+        }
+    }
+    return (int64_t)(p - out);
+}
 const char *gt_last_error(void) { return g_err.c_str(); }
 
 int64_t gt_packed_pitch(int32_t n_file) {

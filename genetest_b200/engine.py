@@ -35,7 +35,7 @@ ABI_SYMBOLS = [
     "gt_run_dosage_dev", "gt_run_dosage_host", "gt_synth_packed_dev",
     "gt_engine_enable_timing", "gt_engine_kernel_time",
     "gt_engine_dominant_kernel", "gt_engine_kernel_breakdown", "gt_measure_fp64_peak",
-    "gt_measure_dmma_peak", "gt_debug_read_pattern",
+    "gt_measure_dmma_peak", "gt_debug_read_pattern", "gt_format_rows",
 ]
 
 
@@ -106,6 +106,9 @@ def load_library():
     lib.gt_measure_dmma_peak.argtypes = [vp, c.POINTER(dbl)]
     lib.gt_debug_read_pattern.argtypes = [vp, vp, i64, i32, c.c_int, c.c_int,
                                           c.c_int, c.POINTER(dbl)]
+    lib.gt_format_rows.argtypes = [i32, i32, c.POINTER(i32), c.POINTER(vp), vp,
+                                   c.c_char, vp, i64]
+    lib.gt_format_rows.restype = i64
     for name in ABI_SYMBOLS:
         getattr(lib, name)
     _LIB = lib
@@ -383,3 +386,58 @@ def get_engine(device=0):
     if eng is None or eng._h is None:
         eng = _ENGINES[device] = Engine(device)
     return eng
+
+
+def format_rows(columns, keep=None, sep="\t"):
+    """Format result rows with the library's native formatter (no GPU needed).
+
+    ``columns``: list of ``list[str]`` (one string per row), float64 ndarray,
+    integer ndarray, or a plain ``str`` (repeated on every row).  Floats are
+    written like ``repr(float)``.  Returns ``bytes`` (one line per kept row).
+    """
+    lib = load_library()
+    n_rows = None
+    types, ptrs, hold = [], [], []
+    for col in columns:
+        if isinstance(col, str):
+            buf = col.encode() + b"\0"
+            types.append(3)
+        elif isinstance(col, np.ndarray) and col.dtype.kind == "f":
+            buf = np.ascontiguousarray(col, dtype=np.float64)
+            types.append(1)
+            n_rows = buf.shape[0]
+        elif isinstance(col, np.ndarray):
+            buf = np.ascontiguousarray(col, dtype=np.int64)
+            types.append(2)
+            n_rows = buf.shape[0]
+        else:
+            col = list(col)
+            n_rows = len(col)
+            buf = ("\0".join(col) + "\0").encode()
+            types.append(0)
+        hold.append(buf)
+        if isinstance(buf, bytes):
+            ptrs.append(ctypes.cast(ctypes.c_char_p(buf), ctypes.c_void_p).value)
+        else:
+            ptrs.append(buf.ctypes.data)
+    if n_rows is None:
+        raise ValueError("format_rows needs at least one per-row column")
+    width = 2
+    for t, b in zip(types, hold):
+        if t in (1, 2):
+            width += 26
+        elif t == 3:
+            width += len(b) + 1
+    strbytes = sum(len(b) for t, b in zip(types, hold) if t == 0)
+    cap = n_rows * width + strbytes + 64
+    out = ctypes.create_string_buffer(cap)
+    kp = None
+    if keep is not None:
+        keep = np.ascontiguousarray(keep, dtype=np.uint8)
+        kp = keep.ctypes.data
+    n = lib.gt_format_rows(
+        n_rows, len(columns), (ctypes.c_int32 * len(types))(*types),
+        (ctypes.c_void_p * len(ptrs))(*ptrs), kp, sep.encode(), out, cap)
+    if n < 0:
+        raise EngineError(lib.gt_last_error().decode())
+    return out.raw[:n]

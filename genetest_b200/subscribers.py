@@ -126,6 +126,23 @@ class RowWriter(Subscriber):
         if self._f is not None:
             self._f.flush()
 
+    def handle_block(self, block):
+        """Streaming sink: all successful markers of a result block at once,
+        formatted by the native row formatter (``gt_format_rows``) -- the same
+        bytes ``handle`` would write one dictionary at a time."""
+        from .engine import format_rows
+        info = getattr(self, "subset_info_str", None) \
+            if self.subset_info is not None else None
+        cols = [field if isinstance(field, str)
+                else block.column(field.path, info)
+                for _name, field in self.columns]
+        text = format_rows(cols, keep=block.ok_mask, sep=self.sep).decode()
+        if self._f is not None:
+            self._f.write(text)
+            self._f.flush()
+        else:
+            print(text, end="")
+
 
 _STAT_COLUMNS = {
     "linear": ([("coef", "coef"), ("se", "std_err"), ("lower", "lower_ci"),

@@ -168,6 +168,17 @@ int gt_debug_read_pattern(gt_engine *e, const uint8_t *packed_dev, int64_t pitch
                           int32_t n_rows, int tpr, int vec, int ctas_per_sm,
                           double *gbs);
 
+/* Streaming result sink (host only): format `n_rows` result rows as delimited
+ * text, the way GWASWriter / RowWriter.handle() does one dict at a time
+ * (genetest/subscribers.py:192-205).  Column types: 0 = NUL-separated strings
+ * (one per row), 1 = double[n_rows] printed like Python's repr(float) (what
+ * the reference's str(float) writes), 2 = int64[n_rows], 3 = one constant
+ * string.  `keep` (or NULL) selects the rows to emit.  Returns the number of
+ * bytes written, or a negative error. */
+int64_t gt_format_rows(int32_t n_rows, int32_t n_cols, const int32_t *col_type,
+                       const void *const *col_data, const uint8_t *keep, char sep,
+                       char *out, int64_t out_cap);
+
 #ifdef __cplusplus
 }
 #endif

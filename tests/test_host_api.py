@@ -362,3 +362,62 @@ def test_gather_results_two_ranks_gloo(tmp_path):
     mp.spawn(_gather_worker, args=(2, port, str(tmp_path)), nprocs=2,
              join=True)
     assert os.path.exists(str(tmp_path / "ok"))
+
+
+# ---- streaming result sink ---------------------------------------------------------------
+def test_native_formatter_matches_python_repr():
+    from genetest_b200.engine import format_rows
+    rng = np.random.default_rng(0)
+    x = np.concatenate([
+        rng.normal(size=20000) * 10.0 ** rng.integers(-12, 12, 20000),
+        [0.1, 1e-5, 1e16, 1e-4, 9.999e-5, 123456789.123, 5e-324, 1e22, np.nan,
+         np.inf, -np.inf, -0.0, 0.0, 60.0, 1234567890123456.0,
+         12345678901234567.0, 1.7976931348623157e308, 2.5, 1e15, 1e17]])
+    got = format_rows([x]).decode().split("\n")[:-1]
+    assert got == [repr(v) for v in x.tolist()]
+    keep = np.arange(x.shape[0]) % 3 != 0
+    names = ["rs{}".format(i) for i in range(x.shape[0])]
+    out = format_rows([names, "chr1", np.arange(x.shape[0]), x], keep=keep,
+                      sep=",").decode().splitlines()
+    assert len(out) == keep.sum()
+    assert out[0] == "rs1,chr1,1,{!r}".format(float(x[1]))
+
+
+@pytest.mark.parametrize("test", ["linear", "logistic", "coxph"])
+def test_block_sink_writes_the_same_bytes_as_the_row_sink(test, tmp_path):
+    """GWASWriter.handle_block (vectorised, native formatter) vs the
+    reference protocol handle(dict) once per marker."""
+    from genetest_b200.analysis import ResultBlock
+    from genetest_b200.engine import Results
+    rng = np.random.default_rng(1)
+    n, cols = 64, ["age", "intercept", "SNPs", "I:x"]
+    if test == "coxph":
+        cols.remove("intercept")
+    nf = 4 + 6 * len(cols)
+    out = rng.normal(size=(nf, n)) * 10.0 ** rng.integers(-5, 3, (nf, n))
+    out[0] = rng.random(n) / 2
+    iout = np.zeros((4, n), dtype=np.int32)
+    iout[0, ::7] = 3                      # failed markers are not written
+    iout[1] = rng.integers(50, 60, n)
+    iout[2] = rng.integers(0, 2, n)
+    meta = [("rs{}".format(i), i % 22 + 1, 1000 + i, "A", "G")
+            for i in range(n)]
+    block = ResultBlock(test, cols, Results(out, iout, len(cols)), meta, None)
+    paths = []
+    for name in ("a.txt", "b.txt"):
+        w = GWASWriter(str(tmp_path / name), test)
+        w.init(None)
+        w._update_gwas_interaction(["I:x"])
+        w._update_current_subset({"sex": 1})
+        if name == "a.txt":
+            w.handle_block(block)
+        else:
+            for i in range(n):
+                if block.ok(i):
+                    w.handle(block.to_dict(i))
+        w.close()
+        paths.append(str(tmp_path / name))
+    a, b = open(paths[0]).read(), open(paths[1]).read()
+    assert a == b and len(a.splitlines()) == 1 + int((iout[0] == 0).sum())
+    with pytest.raises(KeyError):
+        block.column(["SNPs", "no_such_field"])
