@@ -35,6 +35,9 @@ struct gt_engine {
     DevBuf dS, dCounts, dGsum, dMlist, dMcount, dCorr; // per-batch workspace
     int mcap = 0;
     DevBuf dGeno, dOut, dIout;                 // staging of the *_host entry points
+    cudaStream_t s_in = nullptr, s_out = nullptr;     // copy streams of the *_host pipeline
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_start = nullptr;
+    int host_chunk = 0;        // option "host_chunk": SNPs per pipeline stage (0 = automatic)
     int contract_idx = -1;
     // timing
     bool timing = false;
@@ -279,6 +282,13 @@ int gt_engine_destroy(gt_engine *e) {
                       &e->dS, &e->dCounts, &e->dGsum, &e->dMlist, &e->dMcount, &e->dCorr, &e->dGeno, &e->dOut, &e->dIout};
     for (DevBuf *b : bufs) b->release();
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    if (e->s_in) cudaStreamDestroy(e->s_in);
+    if (e->s_out) cudaStreamDestroy(e->s_out);
+    for (int i = 0; i < 2; ++i) {
+        if (e->ev_in[i]) cudaEventDestroy(e->ev_in[i]);
+        if (e->ev_done[i]) cudaEventDestroy(e->ev_done[i]);
+    }
+    if (e->ev_start) cudaEventDestroy(e->ev_start);
     delete e;
     return 0;
 }
@@ -318,6 +328,7 @@ int gt_engine_set_option(gt_engine *e, const char *name, int value) {
     if (std::strcmp(name, "contract_tc") == 0) { e->use_tc = value != 0; return 0; }
     if (std::strcmp(name, "tc_debug") == 0) { e->tc_dbg = value; return 0; }
     if (std::strcmp(name, "split_corrections") == 0) { e->split_corr = value != 0; return 0; }
+    if (std::strcmp(name, "host_chunk") == 0) { e->host_chunk = (int)std::max<int64_t>(0, value); return 0; }
     return fail(GT_E_ARG, "gt_engine_set_option: unknown option '%s'", name);
 }
 
@@ -647,7 +658,7 @@ static int launch_finish(gt_engine *e, int NT2, int grid, int threads, size_t sm
 }
 
 static int run_linear(gt_engine *e, const void *geno, int64_t pitch, bool packed, int32_t n_snps,
-                      double *out, int32_t *iout) {
+                      double *out, int32_t *iout, long long ldo) {
     const GtDesignDev &D = e->D;
     const ContractEntry &ce = kContract[e->contract_idx];
     const int tile = 32 * ce.rows;
@@ -693,22 +704,25 @@ static int run_linear(gt_engine *e, const void *geno, int64_t pitch, bool packed
             time_end(e, slot);
             CK(cudaGetLastError());
             if ((rc = launch_finish<true>(e, NT2, grid, wpc * 32, fsmem, g, pitch, nb, out + s0,
-                                          iout + s0, (long long)n_snps, wpc, tc))) return rc;
+                                          iout + s0, ldo, wpc, tc))) return rc;
         } else {
             const double *g = (const double *)geno + (int64_t)s0 * pitch;
             gtk::contract_dosage_kernel<<<(nb + 7) / 8, 256, 0, e->stream>>>(
                 g, pitch, nb, D.n, D.E, D.NCA, D.NCB, D.NC1, D.NC2, S, cnt, gs);
             CK(cudaGetLastError());
             if ((rc = launch_finish<false>(e, NT2, grid, wpc * 32, fsmem, g, pitch, nb, out + s0,
-                                           iout + s0, (long long)n_snps, wpc, false))) return rc;
+                                           iout + s0, ldo, wpc, false))) return rc;
         }
         e->all_launches += 2;
     }
     return 0;
 }
 
+// out[field][ldo], iout[field][ldo]: ldo >= n_snps (0 selects n_snps) lets a
+// caller fill a column range of larger result blocks
 static int run_any(gt_engine *e, const void *geno, int64_t pitch, bool packed, int32_t n_snps,
-                   double *out, int32_t *iout) {
+                   double *out, int32_t *iout, long long ldo = 0) {
+    if (ldo <= 0) ldo = n_snps;
     if (!e || !e->have_design) return fail(GT_E_STATE, "no design set");
     if (n_snps < 0 || !out || !iout || (n_snps > 0 && !geno)) return fail(GT_E_ARG, "run: bad arguments");
     if (n_snps == 0) return 0;
@@ -717,8 +731,8 @@ static int run_any(gt_engine *e, const void *geno, int64_t pitch, bool packed, i
         if (pitch % 16 != 0 || pitch < ((int64_t)e_n_file(e) + 3) / 4)
             return fail(GT_E_ARG, "run: pitch %lld must be a multiple of 16 and >= ceil(n_file/4)", (long long)pitch);
     }
-    if (e->model == GT_MODEL_LINEAR) return run_linear(e, geno, pitch, packed, n_snps, out, iout);
-    return gtk::iter_run(e->T, e->model, geno, pitch, packed, n_snps, out, iout, e->stream, e->timing,
+    if (e->model == GT_MODEL_LINEAR) return run_linear(e, geno, pitch, packed, n_snps, out, iout, ldo);
+    return gtk::iter_run(e->T, e->model, geno, pitch, packed, n_snps, out, iout, ldo, e->stream, e->timing,
                          [&]() { return time_begin(e); }, [&](int s) { time_end(e, s); },
                          e->all_launches, g_err);
 }
@@ -738,23 +752,68 @@ int gt_run_dosage_dev(gt_engine *e, const double *dosage_dev, int64_t ld, int32_
     return run_any(e, dosage_dev, ld, false, n_snps, out_dev, iout_dev);
 }
 
+// Host-buffer entry points: a two-slot pipeline.  While chunk c computes on
+// the engine's stream, chunk c+1 crosses PCIe on s_in and the results of chunk
+// c-1 return on s_out; the order of the calls below also overlaps when the
+// host buffers are pageable (those copies block the calling thread).
 static int run_host(gt_engine *e, const void *src, int64_t src_pitch_bytes, int64_t dev_pitch_bytes,
                     int64_t width_bytes, int64_t dev_pitch_arg, bool packed, int32_t n_snps,
                     double *out_host, int32_t *iout_host) {
     if (!e || !e->have_design) return fail(GT_E_STATE, "no design set");
     if (n_snps <= 0) return n_snps == 0 ? 0 : fail(GT_E_ARG, "n_snps < 0");
+    if (!src || !out_host || !iout_host) return fail(GT_E_ARG, "run_host: NULL buffer");
     CK(cudaSetDevice(e->device));
-    int nf = gt_engine_num_fields(e);
+    const int nf = gt_engine_num_fields(e);
+    if (!e->s_in) {
+        CK(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CK(cudaEventCreateWithFlags(&e->ev_in[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming));
+        }
+        CK(cudaEventCreateWithFlags(&e->ev_start, cudaEventDisableTiming));
+    }
+    // stage size: about an eighth of the call, at least 8192 markers (every
+    // SM busy) and at most 512 MiB of genotypes per slot
+    int64_t chunk = e->host_chunk > 0 ? e->host_chunk : (((int64_t)n_snps + 7) / 8 + 1023) / 1024 * 1024;
+    if (e->host_chunk <= 0) {
+        chunk = std::max<int64_t>(chunk, 8192);
+        chunk = std::min<int64_t>(chunk, std::max<int64_t>(1024, ((int64_t)512 << 20) / dev_pitch_bytes / 1024 * 1024));
+    }
+    chunk = std::min<int64_t>(chunk, n_snps);
     int rc;
-    if ((rc = e->dGeno.reserve((size_t)dev_pitch_bytes * n_snps))) return rc;
+    if ((rc = e->dGeno.reserve((size_t)dev_pitch_bytes * chunk * 2))) return rc;
     if ((rc = e->dOut.reserve((size_t)nf * n_snps * 8))) return rc;
     if ((rc = e->dIout.reserve((size_t)GT_NUM_IFIELDS * n_snps * 4))) return rc;
-    CK(cudaMemcpy2DAsync(e->dGeno.p, dev_pitch_bytes, src, src_pitch_bytes, width_bytes, n_snps,
-                         cudaMemcpyHostToDevice, e->stream));
-    rc = run_any(e, e->dGeno.p, dev_pitch_arg, packed, n_snps, (double *)e->dOut.p, (int32_t *)e->dIout.p);
-    if (rc) return rc;
-    CK(cudaMemcpyAsync(out_host, e->dOut.p, (size_t)nf * n_snps * 8, cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaMemcpyAsync(iout_host, e->dIout.p, (size_t)GT_NUM_IFIELDS * n_snps * 4, cudaMemcpyDeviceToHost, e->stream));
+    double *dout = (double *)e->dOut.p;
+    int32_t *diout = (int32_t *)e->dIout.p;
+    CK(cudaEventRecord(e->ev_start, e->stream));       // earlier work on the engine's stream
+    CK(cudaStreamWaitEvent(e->s_in, e->ev_start, 0));
+    auto copy_back = [&](int64_t c0, int nb, int slot) -> int {
+        CK(cudaStreamWaitEvent(e->s_out, e->ev_done[slot], 0));
+        CK(cudaMemcpy2DAsync(out_host + c0, (size_t)n_snps * 8, dout + c0, (size_t)n_snps * 8,
+                             (size_t)nb * 8, nf, cudaMemcpyDeviceToHost, e->s_out));
+        CK(cudaMemcpy2DAsync(iout_host + c0, (size_t)n_snps * 4, diout + c0, (size_t)n_snps * 4,
+                             (size_t)nb * 4, GT_NUM_IFIELDS, cudaMemcpyDeviceToHost, e->s_out));
+        return 0;
+    };
+    int64_t prev0 = -1;
+    int prev_nb = 0, prev_slot = 0, c = 0;
+    for (int64_t c0 = 0; c0 < n_snps; c0 += chunk, ++c) {
+        const int nb = (int)std::min<int64_t>(chunk, n_snps - c0), slot = c & 1;
+        char *dg = (char *)e->dGeno.p + (size_t)slot * dev_pitch_bytes * chunk;
+        if (c >= 2) CK(cudaStreamWaitEvent(e->s_in, e->ev_done[slot], 0));   // slot read by chunk c-2
+        CK(cudaMemcpy2DAsync(dg, dev_pitch_bytes, (const char *)src + c0 * src_pitch_bytes, src_pitch_bytes,
+                             width_bytes, nb, cudaMemcpyHostToDevice, e->s_in));
+        CK(cudaEventRecord(e->ev_in[slot], e->s_in));
+        CK(cudaStreamWaitEvent(e->stream, e->ev_in[slot], 0));
+        if ((rc = run_any(e, dg, dev_pitch_arg, packed, nb, dout + c0, diout + c0, n_snps))) return rc;
+        CK(cudaEventRecord(e->ev_done[slot], e->stream));
+        if (prev0 >= 0 && (rc = copy_back(prev0, prev_nb, prev_slot))) return rc;
+        prev0 = c0; prev_nb = nb; prev_slot = slot;
+    }
+    if ((rc = copy_back(prev0, prev_nb, prev_slot))) return rc;
+    CK(cudaStreamSynchronize(e->s_out));
     return gt_engine_synchronize(e);
 }
 

@@ -119,21 +119,21 @@ static int iter_set_design(const gt_design_desc *d, const std::vector<int> &pos,
 
 template <bool PACKED, int NT>
 static int launch_logistic(const IterDesignDev &T, const void *geno, int64_t pitch, int n_snps,
-                           double *out, int32_t *iout, cudaStream_t st) {
+                      double *out, int32_t *iout, long long ldo, cudaStream_t st) {
     using Cfg = LogitCfg<NT>;
     const int wpc = 8;
     size_t smem = (size_t)wpc * Cfg::perWarp * 8;   // NT = 2: 92 KB -> two CTAs per SM
     CK(cudaFuncSetAttribute((const void *)logistic_irls_kernel<PACKED, NT>,
                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     logistic_irls_kernel<PACKED, NT><<<(n_snps + wpc - 1) / wpc, wpc * 32, smem, st>>>(
-        T, geno, pitch, n_snps, out, iout, (long long)n_snps);
+        T, geno, pitch, n_snps, out, iout, ldo);
     CK(cudaGetLastError());
     return 0;
 }
 
 template <bool PACKED, int NT>
 static int launch_cox(const IterDesignDev &T, const void *geno, int64_t pitch, int n_snps,
-                      double *out, int32_t *iout, cudaStream_t st) {
+                      double *out, int32_t *iout, long long ldo, cudaStream_t st) {
     using Cfg = CoxCfg<NT>;
     int wpc = 8;
     while (wpc > 1 && (size_t)wpc * Cfg::perWarp * 8 > 200 * 1024) wpc >>= 1;
@@ -141,13 +141,13 @@ static int launch_cox(const IterDesignDev &T, const void *geno, int64_t pitch, i
     CK(cudaFuncSetAttribute((const void *)cox_newton_kernel<PACKED, NT>,
                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cox_newton_kernel<PACKED, NT><<<(n_snps + wpc - 1) / wpc, wpc * 32, smem, st>>>(
-        T, geno, pitch, n_snps, out, iout, (long long)n_snps);
+        T, geno, pitch, n_snps, out, iout, ldo);
     CK(cudaGetLastError());
     return 0;
 }
 
 static int iter_run(const IterDesignDev &T, int model, const void *geno, int64_t pitch, bool packed,
-                    int32_t n_snps, double *out, int32_t *iout, cudaStream_t st, bool timing,
+                    int32_t n_snps, double *out, int32_t *iout, long long ldo, cudaStream_t st, bool timing,
                     const std::function<int()> &tbegin, const std::function<void(int)> &tend,
                     int64_t &all_launches, std::string &err) {
     (void)timing; (void)err;
@@ -156,22 +156,22 @@ static int iter_run(const IterDesignDev &T, int model, const void *geno, int64_t
     int rc;
     if (model == GT_MODEL_COXPH) {
         if (packed) {
-            rc = NT == 1 ? launch_cox<true, 1>(T, geno, pitch, n_snps, out, iout, st)
-               : NT == 2 ? launch_cox<true, 2>(T, geno, pitch, n_snps, out, iout, st)
-                         : launch_cox<true, 3>(T, geno, pitch, n_snps, out, iout, st);
+            rc = NT == 1 ? launch_cox<true, 1>(T, geno, pitch, n_snps, out, iout, ldo, st)
+               : NT == 2 ? launch_cox<true, 2>(T, geno, pitch, n_snps, out, iout, ldo, st)
+                         : launch_cox<true, 3>(T, geno, pitch, n_snps, out, iout, ldo, st);
         } else {
-            rc = NT == 1 ? launch_cox<false, 1>(T, geno, pitch, n_snps, out, iout, st)
-               : NT == 2 ? launch_cox<false, 2>(T, geno, pitch, n_snps, out, iout, st)
-                         : launch_cox<false, 3>(T, geno, pitch, n_snps, out, iout, st);
+            rc = NT == 1 ? launch_cox<false, 1>(T, geno, pitch, n_snps, out, iout, ldo, st)
+               : NT == 2 ? launch_cox<false, 2>(T, geno, pitch, n_snps, out, iout, ldo, st)
+                         : launch_cox<false, 3>(T, geno, pitch, n_snps, out, iout, ldo, st);
         }
     } else if (packed) {
-        rc = NT == 1 ? launch_logistic<true, 1>(T, geno, pitch, n_snps, out, iout, st)
-           : NT == 2 ? launch_logistic<true, 2>(T, geno, pitch, n_snps, out, iout, st)
-                     : launch_logistic<true, 3>(T, geno, pitch, n_snps, out, iout, st);
+        rc = NT == 1 ? launch_logistic<true, 1>(T, geno, pitch, n_snps, out, iout, ldo, st)
+           : NT == 2 ? launch_logistic<true, 2>(T, geno, pitch, n_snps, out, iout, ldo, st)
+                     : launch_logistic<true, 3>(T, geno, pitch, n_snps, out, iout, ldo, st);
     } else {
-        rc = NT == 1 ? launch_logistic<false, 1>(T, geno, pitch, n_snps, out, iout, st)
-           : NT == 2 ? launch_logistic<false, 2>(T, geno, pitch, n_snps, out, iout, st)
-                     : launch_logistic<false, 3>(T, geno, pitch, n_snps, out, iout, st);
+        rc = NT == 1 ? launch_logistic<false, 1>(T, geno, pitch, n_snps, out, iout, ldo, st)
+           : NT == 2 ? launch_logistic<false, 2>(T, geno, pitch, n_snps, out, iout, ldo, st)
+                     : launch_logistic<false, 3>(T, geno, pitch, n_snps, out, iout, ldo, st);
     }
     tend(slot);
     all_launches += 1;

@@ -164,16 +164,16 @@ class Engine(object):
     """One engine per GPU (``gt_engine``)."""
 
     def __init__(self, device=0):
-        import torch
-        if not torch.cuda.is_available():
-            raise EngineError("no CUDA device: genetest_b200 has no CPU "
-                              "fallback (needs an sm_100a GPU)")
-        self._torch = torch
+        # no torch here: a single-process analysis only needs the C ABI
+        # (importing torch costs seconds); gt_engine_create itself refuses
+        # to run without an sm_100 device
         self.lib = load_library()
         self.device = int(device)
         self._h = ctypes.c_void_p()
-        self._check(self.lib.gt_engine_create(self.device,
-                                              ctypes.byref(self._h)))
+        if self.lib.gt_engine_create(self.device, ctypes.byref(self._h)) < 0:
+            raise EngineError(
+                "{} -- genetest_b200 has no CPU fallback (needs an sm_100a "
+                "GPU)".format(self.lib.gt_last_error().decode()))
         self.n_params = None
         self.n_fields = None
         self.model = None
@@ -204,7 +204,8 @@ class Engine(object):
 
     def use_torch_stream(self):
         """Launch on torch's current stream (so torch.cuda.Event times it)."""
-        s = self._torch.cuda.current_stream(self.device).cuda_stream
+        import torch
+        s = torch.cuda.current_stream(self.device).cuda_stream
         if s == 0:
             s = 1       # cudaStreamLegacy: torch's default stream
         self._check(self.lib.gt_engine_set_stream(self._h, ctypes.c_void_p(s)))
@@ -268,7 +269,7 @@ class Engine(object):
 
     # -- runs -------------------------------------------------------------
     def alloc_results(self, n_snps):
-        t = self._torch
+        import torch as t
         dev = "cuda:{}".format(self.device)
         out = t.empty((self.n_fields, n_snps), dtype=t.float64, device=dev)
         iout = t.empty((NUM_IFIELDS, n_snps), dtype=t.int32, device=dev)
@@ -329,7 +330,7 @@ class Engine(object):
     def synth_packed(self, n_file, n_snps, seed=20261019, maf_lo=0.05,
                      maf_hi=0.5, missing_rate=0.0):
         """Synthetic .bed rows generated on the device (bench / tests)."""
-        t = self._torch
+        import torch as t
         pitch = self.packed_pitch(n_file)
         buf = t.empty((n_snps, pitch), dtype=t.uint8,
                       device="cuda:{}".format(self.device))

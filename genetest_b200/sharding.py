@@ -9,6 +9,7 @@ tests).  No statistic spans markers, so no other collective exists.
 """
 
 import os
+import sys
 
 import numpy as np
 
@@ -17,6 +18,10 @@ __all__ = ["rank_world", "is_primary", "local_device", "shard_range",
 
 
 def _dist():
+    # a process that joined a process group has imported torch already;
+    # single-process runs never pay for the import
+    if "torch" not in sys.modules:
+        return None
     try:
         import torch.distributed as dist
     except ImportError:         # pragma: no cover

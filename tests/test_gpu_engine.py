@@ -404,3 +404,49 @@ def test_linear_tcgen05_contraction_matches_fp64_and_oracle(engine, shape):
     problems, worst, n_ok = compare("linear", res, oracle, names, rtol=LIN_TOL)
     assert not problems, problems[:10]
     print("tcgen05 contraction worst rel err vs oracle", worst)
+
+
+@pytest.mark.parametrize("model", ["linear", "logistic", "coxph"])
+def test_host_pipeline_chunks_are_bit_identical(engine, model):
+    """The *_host entry points pipeline copy-in / compute / copy-back in
+    chunks; any chunking must give the bits of one whole-batch call."""
+    import torch
+    rng = np.random.default_rng(77)
+    n, n_snps = 1203, 2777
+    C, names = synth_design(rng, n, k_extra=4)
+    G = synth_genotypes(rng, n_snps, n, missing=0.02)
+    event = None
+    if model == "linear":
+        y = _linear_y(rng, C)
+    elif model == "logistic":
+        y = (rng.random(n) < 0.4).astype(float)
+    else:
+        C = C[:, :-1]
+        y, event = _cox_data(rng, n, C, False)
+    engine.set_design(model, y, C, event=event)
+    packed = pack_rows(G)
+    pitch = engine.packed_pitch()
+    buf = np.zeros((n_snps, pitch), dtype=np.uint8)
+    buf[:, :packed.shape[1]] = packed
+    out, iout = engine.run_packed_dev(torch.from_numpy(buf).cuda(), n_snps)
+    ref = engine.fetch(out, iout)
+    pinned = torch.from_numpy(packed).pin_memory().numpy()
+    try:
+        for chunk, src in ((0, packed), (500, packed), (1024, pinned),
+                           (2777, packed), (1, packed[:40])):
+            engine.set_option("host_chunk", chunk)
+            got = engine.run_packed_host(src)
+            m = src.shape[0]
+            np.testing.assert_array_equal(got.iout, ref.iout[:, :m])
+            np.testing.assert_array_equal(got.out.view(np.int64),
+                                          ref.out[:, :m].view(np.int64))
+        engine.set_option("host_chunk", 700)
+        dos = G[:1500].copy()
+        a = engine.run_dosage_host(dos)
+        engine.set_option("host_chunk", 0)
+        b = engine.run_dosage_host(dos)
+        np.testing.assert_array_equal(a.iout, b.iout)
+        np.testing.assert_array_equal(a.out.view(np.int64),
+                                      b.out.view(np.int64))
+    finally:
+        engine.set_option("host_chunk", 0)
