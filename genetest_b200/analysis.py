@@ -521,9 +521,20 @@ def _execute_gwas(genotypes, modelspec, subscribers, y, X, variant_predicates,
                         subscribers, messages)
 
     if world == 1:
-        for res, meta in blocks:            # stream batch by batch
-            if res is not None:
-                consume(res, meta)
+        # stream batch by batch; the sinks of batch i run on one helper
+        # thread (so rows stay in marker order) while the GPU works on batch
+        # i + 1 -- both sides spend their time outside the GIL
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=1) as pool:
+            pending = []
+            for res, meta in blocks:
+                if res is None:
+                    continue
+                pending.append(pool.submit(consume, res, meta))
+                while len(pending) > 1:
+                    pending.pop(0).result()
+            for f in pending:
+                f.result()
     else:
         # every rank finishes its range, then ONE gather of the fixed-size
         # result blocks to rank 0 (the only collective of the analysis)

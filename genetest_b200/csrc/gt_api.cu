@@ -539,6 +539,8 @@ int gt_engine_set_design(gt_engine *e, const gt_design_desc *d) {
         D.use_maf_t = d->use_maf_t; D.degenerate = H.degenerate ? 1 : 0;
         D.lean = lean ? 1 : 0;
         D.icpt_shift = H.icpt_shift;
+        D.trG0 = 0.0;
+        for (double r : H.R) D.trG0 += r * r;
         D.cond_t = d->condition_value_t; D.eig_t = d->eigenvals_t; D.maf_t = d->maf_t;
         D.E = (const double *)e->dE.p; D.ormask = (const uint8_t *)e->dMask.p;
         D.FF0 = (const double *)e->dFF0.p; D.R = (const double *)e->dR.p;

@@ -36,6 +36,7 @@ struct GtDesignDev {
     int degenerate;    // covariates alone are rank deficient
     int lean;          // no interaction: E rows are [q | y] only (NC1 = k + 1, NC2 = 0)
     double icpt_shift; // ybar / value of the constant column
+    double trG0;       // trace of the covariates' full-sample Gram matrix = |R|_F^2
     double cond_t, eig_t, maf_t;
     const double *E;        // [n_chunks*256][NCP]
     const uint8_t *ormask;  // [pitch] 2-bit pairs: 11 = sample not in design

@@ -136,46 +136,71 @@ __device__ __forceinline__ void subtract_missing(const GtDesignDev &D, const voi
     };
 
     if (mlist != nullptr && mcountA >= 0 && mcountB >= 0) {
+        // The contraction kernel already listed the missing samples.  Each
+        // lane loads its own MMA fragment elements straight from E (no
+        // shared staging): lane (c = lane / 4, e = lane % 4) of k-step ks
+        // needs elements t * 8 + c of sample 4 ks + e, so the eight lanes of
+        // one sample read 64 contiguous bytes -- whole 32 B sectors.  Group
+        // g + 1 is in flight while the tensor cores work on group g; the
+        // indices run two groups ahead.
         const int mcount = mcountA + mcountB;
-        // the contraction kernel already listed the missing samples: gather
-        // group g + 1 while the tensor cores work on group g
-        constexpr int NV = 4 * NT2;                      // double2 per base vector
-        const int nv = (nlive + 1) / 2;
-        double2 regs[NV];
-        auto fetch = [&](int g) {
-            int t = g * 32 + lane;
-            int idx = (t < mcount) ? (t < mcountA ? mlist[t] : mlist[hcap + t - mcountA]) : -1;
-            const double2 *er = (const double2 *)(D.E + (long long)(idx < 0 ? 0 : idx) * D.NCP);
-#pragma unroll
-            for (int c = 0; c < NV; ++c)
-                regs[c] = (idx >= 0 && c < nv) ? er[c] : make_double2(0.0, 0.0);
-            return idx >= 0;
-        };
         const int ngroups = (mcount + 31) / 32;
-        bool valid = ngroups > 0 ? fetch(0) : false;
-        for (int g = 0; g < ngroups; ++g) {
-            double2 *s2 = (double2 *)(stage + lane * LS);
-#pragma unroll
-            for (int c = 0; c < NV; ++c) if (2 * c < LS) s2[c] = regs[c];
-            if (valid) {
-                if (D.lean) stage[lane * LS + D.k + 1] = 1.0;
-                else if (nlive & 1) stage[lane * LS + nlive] = 0.0;
-            }
-            __syncwarp();
-            if (g + 1 < ngroups) valid = fetch(g + 1);
+        const int c = lane >> 2, e4 = lane & 3;
+        const int one_col = D.lean ? D.k + 1 : -1;
+        auto index_of = [&](int g) {
+            int t = g * 32 + lane;
+            return (t < mcount) ? (t < mcountA ? mlist[t] : mlist[hcap + t - mcountA]) : -1;
+        };
+        auto gather = [&](int idx_lane, double (&f)[8 * NT2]) {
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks) {
-                const int e = ks * 4 + (lane & 3), c = lane >> 2;
-                double f[NT2];
+                const int idx = __shfl_sync(GT_FULL, idx_lane, ks * 4 + e4);
+                const double *er = D.E + (long long)(idx < 0 ? 0 : idx) * D.NCP;
 #pragma unroll
-                for (int t = 0; t < NT2; ++t) f[t] = stage[e * LS + t * 8 + c];
+                for (int t = 0; t < NT2; ++t) {
+                    const int el = t * 8 + c;
+                    double v = 0.0;
+                    if (idx >= 0) {
+                        if (el < nlive) v = __ldg(er + el);
+                        else if (el == one_col) v = 1.0;
+                    }
+                    f[ks * NT2 + t] = v;
+                }
+            }
+        };
+        auto mma = [&](const double (&f)[8 * NT2]) {
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
 #pragma unroll
                 for (int mt = 0; mt < NT2; ++mt)
 #pragma unroll
                     for (int nt = mt; nt < NT2; ++nt)
-                        dmma884_lin(acc[mt][nt][0], acc[mt][nt][1], f[mt], f[nt]);
+                        dmma884_lin(acc[mt][nt][0], acc[mt][nt][1], f[ks * NT2 + mt], f[ks * NT2 + nt]);
+        };
+        if (NT2 <= 2) {
+            double fa[8 * NT2], fb[8 * NT2];
+            int i1 = ngroups > 1 ? index_of(1) : -1;
+            int i2 = ngroups > 2 ? index_of(2) : -1;
+            if (ngroups > 0) gather(index_of(0), fa);
+            for (int g = 0; g < ngroups; g += 2) {
+                const bool second = g + 1 < ngroups;
+                if (second) gather(i1, fb);
+                i1 = (g + 3 < ngroups) ? index_of(g + 3) : -1;
+                mma(fa);
+                if (second) {
+                    if (g + 2 < ngroups) gather(i2, fa);
+                    i2 = (g + 4 < ngroups) ? index_of(g + 4) : -1;
+                    mma(fb);
+                }
             }
-            __syncwarp();
+        } else {
+            double fa[8 * NT2];
+            int inext = ngroups > 0 ? index_of(0) : -1;
+            for (int g = 0; g < ngroups; ++g) {
+                gather(inext, fa);
+                inext = (g + 1 < ngroups) ? index_of(g + 1) : -1;
+                mma(fa);
+            }
         }
     } else if (PACKED) {
         const int nwords = (D.n_file + 15) / 16;         // 32-bit words of 16 samples
@@ -445,42 +470,68 @@ linear_finish_kernel(GtDesignDev D, const void *__restrict__ geno, long long pit
     bool need_jacobi = !chol_ok;
     double ssr = 0.0;
     if (chol_ok) {
-        gt_warp_chol_inverse(Mc, p, p, Mi, lane);
-        for (int i = lane; i < p; i += 32) {
-            double s = 0.0;
-            for (int j = 0; j < p; ++j) s = fma(Mi[i * p + j], rhs[j], s);
-            bq[i] = s;
-        }
+        // M = Lc Lc'.  Only Z = Lc^-1 is formed (one forward substitution per
+        // column): with u = Z rhs, bq = Z' u and ssr = yy - u'u; back in the
+        // reference's parameterisation beta = T bq and var_i = |column i of
+        // Z T'|^2 with T = blockdiag(R^-1, I).
+        double *Z = Mi, *invd = tmpv, *u = gdiag, *W2 = Mc;
+        for (int i = lane; i < p; i += 32) invd[i] = 1.0 / Mc[i * p + i];
+        for (int t = lane; t < p * p; t += 32) Z[t] = 0.0;
+        __syncwarp();
+        for (int c = lane; c < p; c += 32)
+            for (int i = c; i < p; ++i) {
+                double s = (i == c) ? 1.0 : 0.0;
+                for (int j = c; j < i; ++j) s = fma(-Mc[i * p + j], Z[j * p + c], s);
+                Z[i * p + c] = s * invd[i];
+            }
         __syncwarp();
         double part = 0.0;
-        for (int i = lane; i < p; i += 32) part = fma(rhs[i], bq[i], part);
+        for (int r = lane; r < p; r += 32) {
+            double s = 0.0;
+            for (int a = 0; a <= r; ++a) s = fma(Z[r * p + a], rhs[a], s);
+            u[r] = s;
+            part = fma(s, s, part);
+        }
         ssr = yy - gt_warp_sum(part);
-        // back to the reference's parameterisation: beta = T bq, cov = T Mi T'
+        __syncwarp();
         for (int i = lane; i < p; i += 32) {
-            double b = 0.0, v = 0.0, gd = 0.0;
+            double s = 0.0;
+            for (int r = i; r < p; ++r) s = fma(Z[r * p + i], u[r], s);
+            bq[i] = s;
+        }
+        // squares of W = Z T' (the Cholesky factor is not needed any more)
+        for (int t = lane; t < p * p; t += 32) {
+            const int r = t / p, i = t - r * p;
+            double w;
             if (i < k) {
-                for (int a = i; a < k; ++a) {
-                    double ria = D.Rinv[i * k + a];
-                    b = fma(ria, bq[a], b);
-                    double s = 0.0;
-                    for (int c = i; c < k; ++c) s = fma(Mi[a * p + c], D.Rinv[i * k + c], s);
-                    v = fma(ria, s, v);
-                }
-                for (int a = 0; a <= i; ++a) {
-                    double rai = D.R[a * k + i];
-                    double s = 0.0;
-                    for (int c = 0; c <= i; ++c) s = fma(Mo[a * p + c], D.R[c * k + i], s);
-                    gd = fma(rai, s, gd);
-                }
+                w = 0.0;
+                const int hi = r < k - 1 ? r : k - 1;
+                for (int a = i; a <= hi; ++a) w = fma(Z[r * p + a], D.Rinv[i * k + a], w);
             } else {
-                b = bq[i]; v = Mi[i * p + i]; gd = Mo[i * p + i];
+                w = Z[r * p + i];
             }
-            beta[i] = b; var[i] = v; gdiag[i] = gd;
+            W2[t] = w * w;
         }
         __syncwarp();
         double tv = 0.0, tg = 0.0;
-        for (int i = lane; i < p; i += 32) { tv += var[i]; tg += gdiag[i]; }
-        tv = gt_warp_sum(tv); tg = gt_warp_sum(tg);
+        for (int i = lane; i < p; i += 32) {
+            double v = 0.0, b;
+            for (int r = 0; r < p; ++r) v += W2[r * p + i];
+            if (i < k) {
+                b = 0.0;
+                for (int a = i; a < k; ++a) b = fma(D.Rinv[i * k + a], bq[a], b);
+            } else {
+                b = bq[i];
+                tg += Mo[i * p + i];
+            }
+            beta[i] = b; var[i] = v;
+            tv += v;
+        }
+        __syncwarp();
+        tv = gt_warp_sum(tv);
+        // trace of the Gram matrix of the original columns: dropping samples
+        // only lowers the covariates' diagonal, so |R|_F^2 bounds it
+        tg = gt_warp_sum(tg) + D.trG0;
         // cond^2 <= trace(G) trace(G^-1),  lambda_min >= 1 / trace(G^-1)
         bool cond_safe = tg * tv <= D.cond_t * D.cond_t * (1.0 - 1e-9);
         bool eig_safe = 1.0 / tv >= D.eig_t * (1.0 + 1e-9);
