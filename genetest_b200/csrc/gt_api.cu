@@ -453,7 +453,9 @@ int gt_engine_set_design(gt_engine *e, const gt_design_desc *d) {
         for (int a = 0; a < L; ++a)
             for (int b = a; b < L; ++b) FF0[(size_t)a * L + b] = FF0[(size_t)b * L + a] = (double)ff[(size_t)a * L + b];
 
-        std::vector<double> E(n_pad * NCP, 0.0);
+        // two constants follow the rows: [0.0, 1.0] (see subtract_missing)
+        std::vector<double> E(n_pad * NCP + 2, 0.0);
+        E[n_pad * NCP + 1] = 1.0;
         for (int i = 0; i < n; ++i) {
             const double *v = &V[(size_t)i * L];
             double *er = &E[(size_t)pos[i] * NCP];
@@ -542,7 +544,7 @@ int gt_engine_set_design(gt_engine *e, const gt_design_desc *d) {
         D.trG0 = 0.0;
         for (double r : H.R) D.trG0 += r * r;
         D.cond_t = d->condition_value_t; D.eig_t = d->eigenvals_t; D.maf_t = d->maf_t;
-        D.E = (const double *)e->dE.p; D.ormask = (const uint8_t *)e->dMask.p;
+        D.E = (const double *)e->dE.p; D.zero_one = D.E + n_pad * NCP; D.ormask = (const uint8_t *)e->dMask.p;
         D.FF0 = (const double *)e->dFF0.p; D.R = (const double *)e->dR.p;
         D.Rinv = (const double *)e->dRinv.p; D.tq = (const double *)e->dTq.p;
         e->dominant = "contract_packed_kernel";

@@ -39,6 +39,7 @@ struct GtDesignDev {
     double trG0;       // trace of the covariates' full-sample Gram matrix = |R|_F^2
     double cond_t, eig_t, maf_t;
     const double *E;        // [n_chunks*256][NCP]
+    const double *zero_one; // {0.0, 1.0}: targets of the gather for padding lanes
     const uint8_t *ormask;  // [pitch] 2-bit pairs: 11 = sample not in design
     const double *FF0;      // [L*L]   sum over design rows of v v'
     const double *R;        // [k*k]   row-major upper triangular

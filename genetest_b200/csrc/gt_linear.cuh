@@ -151,20 +151,28 @@ __device__ __forceinline__ void subtract_missing(const GtDesignDev &D, const voi
             int t = g * 32 + lane;
             return (t < mcount) ? (t < mcountA ? mlist[t] : mlist[hcap + t - mcountA]) : -1;
         };
+        // every load is unconditional: lanes without an element (padding
+        // columns, samples past the end of the list) read the constant 0.0,
+        // the lane of the ones column reads the constant 1.0 -- a predicated
+        // load would be followed by a select that waits for it
+        long long off[NT2];
+#pragma unroll
+        for (int t = 0; t < NT2; ++t) {
+            const int el = t * 8 + c;
+            off[t] = el < nlive ? (long long)el : (el == one_col ? -2 : -1);
+        }
+        const double *zero_one = D.zero_one;
         auto gather = [&](int idx_lane, double (&f)[8 * NT2]) {
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks) {
                 const int idx = __shfl_sync(GT_FULL, idx_lane, ks * 4 + e4);
-                const double *er = D.E + (long long)(idx < 0 ? 0 : idx) * D.NCP;
+                const double *er = D.E + (long long)idx * D.NCP;
 #pragma unroll
                 for (int t = 0; t < NT2; ++t) {
-                    const int el = t * 8 + c;
-                    double v = 0.0;
-                    if (idx >= 0) {
-                        if (el < nlive) v = __ldg(er + el);
-                        else if (el == one_col) v = 1.0;
-                    }
-                    f[ks * NT2 + t] = v;
+                    const double *ptr = er + off[t];
+                    if (off[t] < 0) ptr = zero_one + (off[t] == -2 ? 1 : 0);
+                    if (idx < 0) ptr = zero_one;
+                    f[ks * NT2 + t] = __ldg(ptr);
                 }
             }
         };
@@ -178,27 +186,26 @@ __device__ __forceinline__ void subtract_missing(const GtDesignDev &D, const voi
                         dmma884_lin(acc[mt][nt][0], acc[mt][nt][1], f[ks * NT2 + mt], f[ks * NT2 + nt]);
         };
         if (NT2 <= 2) {
+            // branch-free software pipeline: groups past the end gather zeros
+            // (index -1), so no conditional copy sits between a load and the
+            // MMAs two stages later
             double fa[8 * NT2], fb[8 * NT2];
-            int i1 = ngroups > 1 ? index_of(1) : -1;
-            int i2 = ngroups > 2 ? index_of(2) : -1;
-            if (ngroups > 0) gather(index_of(0), fa);
+            int i1 = index_of(1), i2 = index_of(2);
+            gather(index_of(0), fa);
             for (int g = 0; g < ngroups; g += 2) {
-                const bool second = g + 1 < ngroups;
-                if (second) gather(i1, fb);
-                i1 = (g + 3 < ngroups) ? index_of(g + 3) : -1;
+                gather(i1, fb);
+                i1 = index_of(g + 3);
                 mma(fa);
-                if (second) {
-                    if (g + 2 < ngroups) gather(i2, fa);
-                    i2 = (g + 4 < ngroups) ? index_of(g + 4) : -1;
-                    mma(fb);
-                }
+                gather(i2, fa);
+                i2 = index_of(g + 4);
+                mma(fb);
             }
         } else {
             double fa[8 * NT2];
-            int inext = ngroups > 0 ? index_of(0) : -1;
+            int inext = index_of(0);
             for (int g = 0; g < ngroups; ++g) {
                 gather(inext, fa);
-                inext = (g + 1 < ngroups) ? index_of(g + 1) : -1;
+                inext = index_of(g + 1);
                 mma(fa);
             }
         }
