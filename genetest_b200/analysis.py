@@ -458,10 +458,6 @@ def _execute_gwas(genotypes, modelspec, subscribers, y, X, variant_predicates,
         return _host_fit_loop(genotypes, test, subscribers, y, X,
                               variant_predicates, messages, maf_t,
                               gwas_interaction, sample_sex)
-    if sample_sex is not None:
-        raise NotImplementedError(
-            "sexual_chromosome=True (sex-aware MAF) is not implemented on "
-            "the B200 engine yet")
 
     # ---- sample alignment (analysis.py:43-65, 97-116) ----
     samples = list(genotypes.get_samples())
@@ -503,13 +499,24 @@ def _execute_gwas(genotypes, modelspec, subscribers, y, X, variant_predicates,
 
     rank, world = sharding.rank_world()
     eng = get_engine(sharding.local_device())
-    eng.set_design(model, y_main, C, W=W, event=event,
-                   sample_pos=geno_index.astype(np.int32), n_file=n_file,
-                   maf_t=maf_t, **options)
-
     names_only = all(isinstance(f, _name_filter_type())
                      for f in variant_predicates)
-    if hasattr(genotypes, "packed") and names_only:
+    packed_path = hasattr(genotypes, "packed") and names_only
+    if packed_path:
+        # raw .bed rows go to the GPU as they are: the engine aligns them
+        eng.set_design(model, y_main, C, W=W, event=event,
+                       sample_pos=geno_index.astype(np.int32), n_file=n_file,
+                       maf_t=maf_t, **options)
+    else:
+        # decoded genotypes are aligned to the design rows on the host
+        eng.set_design(model, y_main, C, W=W, event=event, maf_t=maf_t,
+                       **options)
+    if sample_sex is not None:
+        # analysis.py:141-148: get_sex_maf on the complete cases
+        eng.set_sample_sex(
+            sample_sex.reindex(Xd.index).values.astype(float))
+
+    if packed_path:
         blocks = _packed_blocks(genotypes, eng, variant_predicates, messages,
                                 rank, world)
     else:
@@ -595,13 +602,12 @@ def _decoded_blocks(reader, eng, predicates, messages, geno_index, rank,
     rows, meta = [], []
 
     def flush():
-        block = np.vstack(rows)
+        block = np.ascontiguousarray(np.vstack(rows)[:, geno_index])
         if _integer_valued(block):
             from .genotypes.plink import pack_rows
             res = eng.run_packed_host(pack_rows(block))
         else:
-            res = eng.run_dosage_host(
-                np.ascontiguousarray(block[:, geno_index]))
+            res = eng.run_dosage_host(block)
         out = (res, list(meta))
         del rows[:], meta[:]
         return out

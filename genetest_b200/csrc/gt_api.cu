@@ -18,6 +18,7 @@
 #include "gt_logistic.cuh"
 #include "gt_cox.cuh"
 #include "gt_format.cuh"
+#include "gt_sexmaf.cuh"
 
 struct gt_engine {
     int device = 0;
@@ -39,6 +40,10 @@ struct gt_engine {
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_start = nullptr;
     int host_chunk = 0;        // option "host_chunk": SNPs per pipeline stage (0 = automatic)
     int contract_idx = -1;
+    // sample alignment of the current design; sex-aware MAF (sexual_chromosome=True)
+    std::vector<int> pos;
+    bool identity_pos = true, sex_maf = false;
+    DevBuf dSexM, dSexF, dSexRow, dMafO, dFlipO;
     // timing
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
@@ -279,7 +284,8 @@ int gt_engine_destroy(gt_engine *e) {
     cudaStreamSynchronize(e->stream);
     for (auto &ev : e->events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     DevBuf *bufs[] = {&e->dE, &e->dMask, &e->dFF0, &e->dR, &e->dRinv, &e->dTq, &e->dIter, &e->dBimg, &e->dScale, &e->dErr,
-                      &e->dS, &e->dCounts, &e->dGsum, &e->dMlist, &e->dMcount, &e->dCorr, &e->dGeno, &e->dOut, &e->dIout};
+                      &e->dS, &e->dCounts, &e->dGsum, &e->dMlist, &e->dMcount, &e->dCorr, &e->dGeno, &e->dOut, &e->dIout,
+                      &e->dSexM, &e->dSexF, &e->dSexRow, &e->dMafO, &e->dFlipO};
     for (DevBuf *b : bufs) b->release();
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     if (e->s_in) cudaStreamDestroy(e->s_in);
@@ -330,6 +336,32 @@ int gt_engine_set_option(gt_engine *e, const char *name, int value) {
     if (std::strcmp(name, "split_corrections") == 0) { e->split_corr = value != 0; return 0; }
     if (std::strcmp(name, "host_chunk") == 0) { e->host_chunk = (int)std::max<int64_t>(0, value); return 0; }
     return fail(GT_E_ARG, "gt_engine_set_option: unknown option '%s'", name);
+}
+
+static int e_n_file(const gt_engine *e) { return e->model == GT_MODEL_LINEAR ? e->D.n_file : e->T.n_file; }
+
+int gt_engine_set_sample_sex(gt_engine *e, const double *sex) {
+    if (!e || !e->have_design) return fail(GT_E_STATE, "gt_engine_set_sample_sex: no design set");
+    if (!sex) { e->sex_maf = false; return 0; }
+    CK(cudaSetDevice(e->device));
+    const int n = (int)e->pos.size();
+    const int64_t pitch = gt_packed_pitch(e_n_file(e));
+    std::vector<uint8_t> male((size_t)pitch, 0), female((size_t)pitch, 0);
+    for (int i = 0; i < n; ++i) {
+        const int ps = e->pos[i];
+        const uint8_t bit = (uint8_t)(1u << (2 * (ps & 3)));
+        if (sex[i] == 1.0) male[ps >> 2] |= bit;
+        else if (sex[i] == 0.0) female[ps >> 2] |= bit;
+        else if (sex[i] == sex[i])
+            return fail(GT_E_ARG, "gt_engine_set_sample_sex: sex[%d]=%g (expected 0, 1 or NaN)", i, sex[i]);
+    }
+    int rc;
+    if ((rc = upload(e->dSexM, male.data(), male.size(), e->stream))) return rc;
+    if ((rc = upload(e->dSexF, female.data(), female.size(), e->stream))) return rc;
+    if ((rc = upload(e->dSexRow, sex, (size_t)n * 8, e->stream))) return rc;
+    CK(cudaStreamSynchronize(e->stream));
+    e->sex_maf = true;
+    return 0;
 }
 
 int gt_engine_enable_timing(gt_engine *e, int on) {
@@ -389,6 +421,10 @@ int gt_engine_set_design(gt_engine *e, const gt_design_desc *d) {
     }
     e->have_design = false;
     e->model = d->model;
+    e->sex_maf = false;
+    e->identity_pos = (n_file == n);
+    for (int i = 0; i < n && e->identity_pos; ++i) e->identity_pos = pos[i] == i;
+    e->pos = pos;
     cudaStream_t st = e->stream;
     const int64_t pitch = gt_packed_pitch(n_file);
     const int n_chunks = (n_file + gtk::kChunk - 1) / gtk::kChunk;
@@ -547,6 +583,7 @@ int gt_engine_set_design(gt_engine *e, const gt_design_desc *d) {
         D.E = (const double *)e->dE.p; D.zero_one = D.E + n_pad * NCP; D.ormask = (const uint8_t *)e->dMask.p;
         D.FF0 = (const double *)e->dFF0.p; D.R = (const double *)e->dR.p;
         D.Rinv = (const double *)e->dRinv.p; D.tq = (const double *)e->dTq.p;
+        D.maf_o = nullptr; D.flip_o = nullptr;
         e->dominant = "contract_packed_kernel";
         CK(cudaStreamSynchronize(st));   // host vectors go out of scope
     } else if (d->model == GT_MODEL_LOGISTIC || d->model == GT_MODEL_COXPH) {
@@ -583,7 +620,6 @@ static void time_end(gt_engine *e, int slot) {
     if (e->event_class[slot] == 0) e->launches++;
 }
 
-static int e_n_file(const gt_engine *e) { return e->model == GT_MODEL_LINEAR ? e->D.n_file : e->T.n_file; }
 
 static int launch_contract_tc(gt_engine *e, const uint8_t *g, int64_t pitch, int nb) {
     gtk::TcParams P;
@@ -616,8 +652,12 @@ static int launch_contract_tc(gt_engine *e, const uint8_t *g, int64_t pitch, int
 template <bool PACKED>
 static int launch_finish(gt_engine *e, int NT2, int grid, int threads, size_t smem,
                          const void *g, int64_t pitch, int nb, double *out, int32_t *iout,
-                         long long stride, int wpc, bool use_list) {
-    const GtDesignDev &D = e->D;
+                         long long stride, int wpc, bool use_list, int64_t s0) {
+    GtDesignDev D = e->D;
+    if (e->sex_maf && !D.raw_mode) {
+        D.maf_o = (const double *)e->dMafO.p + s0;
+        D.flip_o = (const int *)e->dFlipO.p + s0;
+    }
     const double *S = (const double *)e->dS.p;
     const int *cnt = (const int *)e->dCounts.p;
     const double *gs = (const double *)e->dGsum.p;
@@ -708,14 +748,14 @@ static int run_linear(gt_engine *e, const void *geno, int64_t pitch, bool packed
             time_end(e, slot);
             CK(cudaGetLastError());
             if ((rc = launch_finish<true>(e, NT2, grid, wpc * 32, fsmem, g, pitch, nb, out + s0,
-                                          iout + s0, ldo, wpc, tc))) return rc;
+                                          iout + s0, ldo, wpc, tc, s0))) return rc;
         } else {
             const double *g = (const double *)geno + (int64_t)s0 * pitch;
             gtk::contract_dosage_kernel<<<(nb + 7) / 8, 256, 0, e->stream>>>(
                 g, pitch, nb, D.n, D.E, D.NCA, D.NCB, D.NC1, D.NC2, S, cnt, gs);
             CK(cudaGetLastError());
             if ((rc = launch_finish<false>(e, NT2, grid, wpc * 32, fsmem, g, pitch, nb, out + s0,
-                                           iout + s0, ldo, wpc, false))) return rc;
+                                           iout + s0, ldo, wpc, false, s0))) return rc;
         }
         e->all_launches += 2;
     }
@@ -735,8 +775,29 @@ static int run_any(gt_engine *e, const void *geno, int64_t pitch, bool packed, i
         if (pitch % 16 != 0 || pitch < ((int64_t)e_n_file(e) + 3) / 4)
             return fail(GT_E_ARG, "run: pitch %lld must be a multiple of 16 and >= ceil(n_file/4)", (long long)pitch);
     }
+    if (!packed && !e->identity_pos)
+        return fail(GT_E_STATE, "dosage rows are aligned to the design rows: set the design without sample_pos / n_file");
+    gtk::IterDesignDev T = e->T;
+    if (e->sex_maf) {
+        int rc;
+        if ((rc = e->dMafO.reserve((size_t)n_snps * 8))) return rc;
+        if ((rc = e->dFlipO.reserve((size_t)n_snps * 4))) return rc;
+        if (packed)
+            gtk::sex_maf_packed_kernel<<<(n_snps + 7) / 8, 256, 0, e->stream>>>(
+                (const uint8_t *)geno, pitch, n_snps, e_n_file(e), (const uint8_t *)e->dMask.p,
+                (const uint8_t *)e->dSexM.p, (const uint8_t *)e->dSexF.p, (double *)e->dMafO.p,
+                (int *)e->dFlipO.p);
+        else
+            gtk::sex_maf_dosage_kernel<<<(n_snps + 7) / 8, 256, 0, e->stream>>>(
+                (const double *)geno, pitch, n_snps, (int)e->pos.size(), (const double *)e->dSexRow.p,
+                (double *)e->dMafO.p, (int *)e->dFlipO.p);
+        CK(cudaGetLastError());
+        e->all_launches += 1;
+        T.maf_o = (const double *)e->dMafO.p;
+        T.flip_o = (const int *)e->dFlipO.p;
+    }
     if (e->model == GT_MODEL_LINEAR) return run_linear(e, geno, pitch, packed, n_snps, out, iout, ldo);
-    return gtk::iter_run(e->T, e->model, geno, pitch, packed, n_snps, out, iout, ldo, e->stream, e->timing,
+    return gtk::iter_run(T, e->model, geno, pitch, packed, n_snps, out, iout, ldo, e->stream, e->timing,
                          [&]() { return time_begin(e); }, [&](int s) { time_end(e, s); },
                          e->all_launches, g_err);
 }

@@ -45,6 +45,10 @@ struct GtDesignDev {
     const double *R;        // [k*k]   row-major upper triangular
     const double *Rinv;     // [k*k]
     const double *tq;       // [n+1]   t.ppf(0.975, df)
+    // sexual_chromosome=True: MAF / flip of every marker of the launch come
+    // from sex_maf_*_kernel (NULL = nanmean(g) / 2)
+    const double *maf_o;
+    const int *flip_o;
 };
 
 // ---------------------------------------------------------------------------

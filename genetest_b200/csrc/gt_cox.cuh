@@ -104,6 +104,7 @@ static int iter_set_design(const gt_design_desc *d, const std::vector<int> &pos,
     T.n_file = n_file; T.n = n; T.k = k; T.I = I; T.p = p; T.XS = XSs; T.n_pad = (int)n_pad;
     T.raw_mode = d->raw_mode; T.use_maf_t = d->use_maf_t; T.maf_t = d->maf_t;
     T.degenerate = H.degenerate ? 1 : 0;
+    T.maf_o = nullptr; T.flip_o = nullptr;
     T.X = (const double *)buf.p; T.y = T.X + n_pad * XSs; T.Rinv = T.y + n_pad;
     if (d->model == GT_MODEL_COXPH) {
         const double *xs = T.Rinv + (size_t)k * k + 2;

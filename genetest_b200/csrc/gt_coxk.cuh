@@ -106,6 +106,7 @@ cox_newton_kernel(IterDesignDev T, const void *__restrict__ geno, long long pitc
     if (!T.raw_mode) {
         maf = (sum_g / (double)nj) / 2.0;
         if (maf > 0.5) { maf = 1.0 - maf; flip = 1; }
+        if (T.maf_o != nullptr) { maf = T.maf_o[snp]; flip = T.flip_o[snp]; }
         if (T.use_maf_t && maf < T.maf_t) { write_fail(GT_MAF_BELOW, flip, maf, maf, 0); return; }
     }
 

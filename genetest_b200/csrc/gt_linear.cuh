@@ -436,6 +436,7 @@ linear_finish_kernel(GtDesignDev D, const void *__restrict__ geno, long long pit
         double sum_g = sum_g_all;
         maf = (sum_g / (double)nj) / 2.0;
         if (maf > 0.5) { maf = 1.0 - maf; flip = 1; }
+        if (D.maf_o != nullptr) { maf = D.maf_o[snp]; flip = D.flip_o[snp]; }
         if (D.use_maf_t && maf < D.maf_t) {
             finish_write_fail(out, iout, ostride, snp, nf, GT_MAF_BELOW, nj, flip, maf, maf, lane);
             return;

@@ -38,6 +38,8 @@ struct IterDesignDev {
     const int *slot_info;   // [n_slots] bits 0-4 first lane of the tie group, 5-9 last lane,
                             //           bit 10 event, bit 11 block has a tie group
     const double *Xs;       // [n_slots][XS] q | w in slot order
+    const double *maf_o;    // sex-aware MAF / flip per marker of the launch, or NULL
+    const int *flip_o;
 };
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
@@ -127,6 +129,7 @@ logistic_irls_kernel(IterDesignDev T, const void *__restrict__ geno, long long p
     if (!T.raw_mode) {
         maf = (sum_g / (double)nj) / 2.0;
         if (maf > 0.5) { maf = 1.0 - maf; flip = 1; }
+        if (T.maf_o != nullptr) { maf = T.maf_o[snp]; flip = T.flip_o[snp]; }
         if (T.use_maf_t && maf < T.maf_t) { write_fail(GT_MAF_BELOW, flip, maf, maf, 0); return; }
     }
 

@@ -30,7 +30,7 @@ ABI_SYMBOLS = [
     "gt_abi_version", "gt_last_error", "gt_engine_create",
     "gt_engine_destroy", "gt_engine_set_stream", "gt_engine_synchronize",
     "gt_engine_set_option",
-    "gt_engine_set_design", "gt_engine_num_params", "gt_engine_num_fields",
+    "gt_engine_set_design", "gt_engine_set_sample_sex", "gt_engine_num_params", "gt_engine_num_fields",
     "gt_packed_pitch", "gt_run_packed_dev", "gt_run_packed_host",
     "gt_run_dosage_dev", "gt_run_dosage_host", "gt_synth_packed_dev",
     "gt_engine_enable_timing", "gt_engine_kernel_time",
@@ -86,6 +86,7 @@ def load_library():
     lib.gt_engine_synchronize.argtypes = [vp]
     lib.gt_engine_set_option.argtypes = [vp, c.c_char_p, c.c_int]
     lib.gt_engine_set_design.argtypes = [vp, c.POINTER(_DesignDesc)]
+    lib.gt_engine_set_sample_sex.argtypes = [vp, vp]
     lib.gt_engine_num_params.argtypes = [vp]
     lib.gt_engine_num_fields.argtypes = [vp]
     lib.gt_packed_pitch.argtypes = [i32]
@@ -262,6 +263,20 @@ class Engine(object):
         self.n_file = d.n_file
         self.n_params = self._check(self.lib.gt_engine_num_params(self._h))
         self.n_fields = self._check(self.lib.gt_engine_num_fields(self._h))
+
+    def set_sample_sex(self, sex):
+        """Sex of every design row (0 female, 1 male, NaN unknown) for the
+        sex-aware MAF of ``execute(sexual_chromosome=True)``; None switches
+        back to ``nanmean(g) / 2``.  Call after :meth:`set_design`."""
+        if sex is None:
+            self._check(self.lib.gt_engine_set_sample_sex(self._h, None))
+            return
+        sex = np.ascontiguousarray(sex, dtype=np.float64)
+        if sex.shape != (self.n,):
+            raise ValueError("sex: expected {} values, got {}".format(
+                self.n, sex.shape))
+        self._check(self.lib.gt_engine_set_sample_sex(self._h,
+                                                      sex.ctypes.data))
 
     def packed_pitch(self, n_file=None):
         return int(self.lib.gt_packed_pitch(

@@ -116,6 +116,11 @@ int gt_engine_set_option(gt_engine *e, const char *name, int value);
 /* Replaces the per-worker setup of _gwas_worker (analysis.py:68-106) and the
  * once-per-analysis part of Stats*.fit. */
 int gt_engine_set_design(gt_engine *e, const gt_design_desc *d);
+/* sexual_chromosome=True (analysis.py:294-300, 141-148): sex of every design
+ * row (host, n doubles: 0 = female, 1 = male, NaN = unknown), after
+ * gt_engine_set_design.  MAF and the flip decision of every marker then follow
+ * get_sex_maf (statistics/descriptive.py:51-93).  NULL switches it off. */
+int gt_engine_set_sample_sex(gt_engine *e, const double *sex);
 int gt_engine_num_params(const gt_engine *e);   /* p = k + 1 + n_inter (coxph: without the constant column) */
 int gt_engine_num_fields(const gt_engine *e);   /* GT_F_PARAM0 + 6 p        */
 /* row pitch (bytes) the engine wants for device-resident packed genotypes */

@@ -450,3 +450,119 @@ def test_host_pipeline_chunks_are_bit_identical(engine, model):
                                       b.out.view(np.int64))
     finally:
         engine.set_option("host_chunk", 0)
+
+
+@pytest.mark.parametrize("config", ["3-logistic", "4-linear-gxe", "5-coxph"])
+def test_baseline_config_shapes_sampled_parity(engine, config):
+    """BASELINE configs 3-5 at their full sample sizes: markers
+    generated on the device, a stratified sample (lowest MAF, fewest
+    observations, random draw) checked against the oracle; nobs is checked
+    on every marker."""
+    rng = np.random.default_rng(20261019)
+    inter, W, event, kwargs = None, None, None, {}
+    if config == "3-logistic":
+        model, n, n_snps, miss, n_pick, tol = "logistic", 50000, 1024, 0.0, 4, LOGIT_TOL
+        C, names = synth_design(rng, n, k_extra=8)
+        y = (rng.random(n) < 1 / (1 + np.exp(0.5 - 0.2 * C[:, 0]))).astype(float)
+        Y = y[:, None]
+    elif config == "4-linear-gxe":
+        model, n, n_snps, miss, n_pick, tol = "linear", 100000, 2048, 0.01, 6, LIN_TOL
+        C, names = synth_design(rng, n, k_extra=8)
+        y = 0.1 * C[:, 0] + rng.normal(size=n)
+        Y = y[:, None]
+        inter, W = {"I:age": ["age"]}, C[:, [0]]
+    else:
+        model, n, n_snps, miss, n_pick, tol = "coxph", 20000, 512, 0.0, 3, LOGIT_TOL
+        C, names = synth_design(rng, n, k_extra=8)
+        C, names = C[:, :-1], names[:-1]
+        y, event = _cox_data(rng, n, C)
+        Y = np.column_stack((y, event))
+    pos = rng.permutation(n).astype(np.int32)
+    engine.set_design(model, y, C, W=W, event=event, sample_pos=pos, n_file=n)
+    dev = engine.synth_packed(n, n_snps, seed=11, missing_rate=miss)
+    out, iout = engine.run_packed_dev(dev, n_snps)
+    res = engine.fetch(out, iout)
+    assert (res.status == 0).all()
+    G = unpack_rows(dev.cpu().numpy()[:, :(n + 3) // 4], n)
+    np.testing.assert_array_equal(res.nobs, n - np.isnan(G).sum(axis=1))
+    pick = np.unique(np.concatenate([
+        np.argsort(res.maf)[:n_pick], np.argsort(res.nobs)[:n_pick],
+        rng.choice(n_snps, n_pick, replace=False)]))
+    sub = type(res)(res.out[:, pick], res.iout[:, pick], res.n_params)
+    oracle = run_oracle(model, Y, C, names, G[pick][:, pos], interaction=inter)
+    problems, worst, n_ok = compare(model, sub, oracle, names,
+                                    inter_keys=list(inter or ()), rtol=tol)
+    assert not problems, problems[:10]
+    assert n_ok == len(pick)
+    print("config {}: {} markers vs oracle, worst rel err {:.2e}".format(
+        config, n_ok, worst))
+
+
+@pytest.mark.parametrize("model", ["linear", "logistic", "coxph"])
+def test_sex_aware_maf(engine, model):
+    """sexual_chromosome=True: MAF / flip follow get_sex_maf
+    (descriptive.py:51-93) -- bit-exact for .bed rows, including unknown
+    sexes, a subset of permuted samples, the MAF threshold and a marker whose
+    genotyped samples all have an unknown sex (MAF = NaN, no flip)."""
+    rng = np.random.default_rng(91)
+    n_file, n, n_snps = 1100, 1000, 96
+    C, names = synth_design(rng, n, k_extra=2)
+    event = None
+    if model == "linear":
+        y = _linear_y(rng, C)
+        Y = y[:, None]
+    elif model == "logistic":
+        y = (rng.random(n) < 0.45).astype(float)
+        Y = y[:, None]
+    else:
+        C, names = C[:, :-1], names[:-1]
+        y, event = _cox_data(rng, n, C)
+        Y = np.column_stack((y, event))
+    sex = rng.integers(0, 2, n).astype(float)
+    sex[rng.random(n) < 0.05] = np.nan
+    pos = rng.permutation(n_file)[:n].astype(np.int32)
+    Gfile = synth_genotypes(rng, n_snps, n_file, missing=0.02, maf_lo=0.02,
+                            maf_hi=0.98)
+    Gfile[0, pos[~np.isnan(sex)]] = np.nan       # only unknown sexes genotyped
+    males = pos[sex == 1]
+    Gfile[1:40][:, males] = np.where(Gfile[1:40][:, males] == 1, 2,
+                                     Gfile[1:40][:, males])   # hemizygous males
+    engine.set_design(model, y, C, event=event, sample_pos=pos, n_file=n_file,
+                      maf_t=0.05)
+    engine.set_sample_sex(sex)
+    res = engine.run_packed_host(pack_rows(Gfile))
+    G = Gfile[:, pos]
+    oracle = run_oracle(model, Y, C, names, G, maf_t=0.05, sexes=sex)
+    tol = LIN_TOL if model == "linear" else LOGIT_TOL
+    problems, worst, n_ok = compare(model, res, oracle, names, rtol=tol)
+    assert not problems, problems[:10]
+    assert np.isnan(res.maf[0]) and res.flip[0] == 0
+    assert (res.status == 2).sum() >= 1 and res.flip.sum() > 5
+    # autosomal MAF differs on most markers: the override really ran
+    engine.set_sample_sex(None)
+    plain = engine.run_packed_host(pack_rows(Gfile))
+    assert (plain.maf[1:] != res.maf[1:]).mean() > 0.5
+    # real-valued dosages, aligned to the design rows
+    D = np.clip(G[:32] + rng.normal(0, 0.03, G[:32].shape), 0, 2)
+    engine.set_design(model, y, C, event=event)
+    engine.set_sample_sex(sex)
+    res = engine.run_dosage_host(D)
+    oracle = run_oracle(model, Y, C, names, D, sexes=sex)
+    for j, (st, o) in enumerate(oracle):
+        if st == "ok" and not np.isnan(o["SNPs"]["maf"]):
+            assert abs(res.maf[j] - o["SNPs"]["maf"]) < 1e-14
+            o["SNPs"]["maf"] = res.maf[j]
+    problems, worst, n_ok = compare(model, res, oracle, names, rtol=tol)
+    assert not problems, problems[:10]
+    engine.set_sample_sex(None)
+
+
+def test_dosage_rows_need_an_identity_alignment(engine):
+    from genetest_b200.engine import EngineError
+    rng = np.random.default_rng(3)
+    C, names = synth_design(rng, 50)
+    engine.set_design("linear", _linear_y(rng, C), C,
+                      sample_pos=np.arange(50, dtype=np.int32)[::-1].copy(),
+                      n_file=50)
+    with pytest.raises(EngineError, match="aligned to the design rows"):
+        engine.run_dosage_host(np.zeros((2, 50)))

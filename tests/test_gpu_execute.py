@@ -273,3 +273,65 @@ def test_name_filter_and_maf_threshold(tmp_path):
         ["snp3", "snp5"]
     assert open(prefix + "_failed_snps.txt").read().splitlines() == \
         ["snp1\tMAF: 0.016666666666666666 < 0.05"]
+
+
+@pytest.mark.parametrize("reader", ["plink", "dataframe"])
+def test_sexual_chromosome_maf_through_execute(tmp_path, reader):
+    """execute(sexual_chromosome=True): MAF, minor / major and the flip of
+    every marker follow get_sex_maf (analysis.py:141-148); checked against the
+    oracle's loop body for a .bed source and a decoded source whose samples
+    are a permuted superset of the phenotypes'."""
+    import oracle.gwas as og
+    from genetest_b200.phenotypes import DataFramePhenotypes
+    rng = np.random.default_rng(17)
+    n_file, n, n_snps = 260, 200, 24
+    ids = np.array(["s{:03d}".format(i) for i in range(n_file)])
+    pheno = pd.DataFrame({
+        "y": rng.normal(size=n), "age": rng.normal(50, 10, n),
+        "sex": rng.integers(0, 2, n).astype(float)},
+        index=rng.permutation(ids)[:n])
+    pheno.loc[pheno.index[:7], "sex"] = np.nan
+    G = rng.binomial(2, rng.uniform(0.1, 0.9, n_snps)[:, None],
+                     (n_snps, n_file)).astype(float)
+    G[rng.random(G.shape) < 0.03] = np.nan
+    names = ["rs{}".format(j) for j in range(n_snps)]
+    if reader == "plink":
+        with PlinkWriter(str(tmp_path / "x")) as w:
+            for j in range(n_snps):
+                w.write_genotypes(np.nan_to_num(G[j], nan=-1))
+            w.write_bim([(23, nm, 100 + j, "A", "G")
+                         for j, nm in enumerate(names)])
+            w.write_fam(list(ids))
+        geno = PlinkReader(str(tmp_path / "x"))
+    else:
+        info = pd.DataFrame({"chrom": 23, "pos": np.arange(n_snps) + 100,
+                             "a1": "A", "a2": "G"}, index=names)
+        geno = DataFrameReader(pd.DataFrame(G.T, index=ids, columns=names),
+                               info)
+    spec._reset()
+    sub = subscribers.ResultsMemory()
+    analysis.execute_formula(
+        DataFramePhenotypes(pheno, sex_column="sex"), geno,
+        "y ~ SNPs + age", "linear", subscribers=[sub],
+        output_prefix=str(tmp_path / "out"), sexual_chromosome=True)
+    got = sub._get_gwas_results()
+    # the oracle's loop body on the complete cases, design rows in file order
+    keep = pheno.dropna(subset=["y", "age"])
+    order = [s for s in ids if s in set(keep.index)]
+    cols = np.array([np.flatnonzero(ids == s)[0] for s in order])
+    C = np.column_stack((keep.loc[order, "age"].values, np.ones(len(order))))
+    sexes = keep.loc[order, "sex"].values
+    assert len(got) == n_snps
+    flips = 0
+    for j, nm in enumerate(names):
+        st, o = og.gwas_one("linear", keep.loc[order, ["y"]].values, C,
+                            ["age", "intercept"], G[j, cols], sexes=sexes,
+                            coded="A", reference="G")
+        assert st == "ok"
+        r = got[nm]["SNPs"]
+        assert r["maf"] == o["SNPs"]["maf"]
+        assert (r["minor"], r["major"]) == (o["SNPs"]["minor"],
+                                            o["SNPs"]["major"])
+        assert abs(r["coef"] - o["SNPs"]["coef"]) <= 1e-8 * abs(r["coef"])
+        flips += o["_flip"]
+    assert 3 < flips < n_snps - 3
