@@ -136,8 +136,9 @@ template <bool PACKED, int NT>
 static int launch_cox(const IterDesignDev &T, const void *geno, int64_t pitch, int n_snps,
                       double *out, int32_t *iout, long long ldo, cudaStream_t st) {
     using Cfg = CoxCfg<NT>;
+    // two CTAs per SM: as many warps as fit half of the shared memory
     int wpc = 8;
-    while (wpc > 1 && (size_t)wpc * Cfg::perWarp * 8 > 200 * 1024) wpc >>= 1;
+    while (wpc > 1 && (size_t)wpc * Cfg::perWarp * 8 > 112 * 1024) --wpc;
     size_t smem = (size_t)wpc * Cfg::perWarp * 8;
     CK(cudaFuncSetAttribute((const void *)cox_newton_kernel<PACKED, NT>,
                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -44,10 +44,13 @@ __device__ __forceinline__ int warp_scan_incl_int(int v, int lane) {
 
 template <int NT>
 struct CoxCfg {
-    static constexpr int PS = (NT <= 2) ? 20 : 36;
     static constexpr int PH = 8 * NT;
-    // xs, wxs, us, H, Hc, Hinv, beta, step, carry, coef, var
-    static constexpr int perWarp = 3 * 32 * PS + 3 * PH * PH + 6 * PH;
+    // staging tiles are TRANSPOSED: row a (design column) holds the 32
+    // samples of the block; a row stride of 36 doubles keeps the per-lane
+    // stores and the MMA fragment loads bank-conflict free
+    static constexpr int XT = 36;
+    // xT, uT, per-sample weights (W, G), H, Hc, Hinv, beta, step, carry, coef, var, prev
+    static constexpr int perWarp = 2 * PH * XT + 64 + 3 * PH * PH + 6 * PH;
 };
 
 template <bool PACKED, int NT>
@@ -55,7 +58,7 @@ __global__ void __launch_bounds__(256)
 cox_newton_kernel(IterDesignDev T, const void *__restrict__ geno, long long pitch, int n_snps,
                   double *__restrict__ out, int *__restrict__ iout, long long ostride) {
     using Cfg = CoxCfg<NT>;
-    constexpr int PS = Cfg::PS, PH = Cfg::PH;
+    constexpr int XT = Cfg::XT, PH = Cfg::PH;
     extern __shared__ __align__(16) double sm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int snp = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -64,7 +67,7 @@ cox_newton_kernel(IterDesignDev T, const void *__restrict__ geno, long long pitc
     const int nf = GT_F_PARAM0 + 6 * p;
 
     double *W = sm + (size_t)warp * Cfg::perWarp;
-    double *xs = W, *wxs = xs + 32 * PS, *us = wxs + 32 * PS, *H = us + 32 * PS,
+    double *xT = W, *uT = xT + PH * XT, *wv = uT + PH * XT, *gv = wv + 32, *H = gv + 32,
            *Hc = H + PH * PH, *Hinv = Hc + PH * PH, *beta = Hinv + PH * PH, *step = beta + PH,
            *carry = step + PH, *coef = carry + PH, *var = coef + PH, *prev = var + PH;
 
@@ -113,27 +116,27 @@ cox_newton_kernel(IterDesignDev T, const void *__restrict__ geno, long long pitc
     // rank-deficient covariates: inv(-H) fails in the reference ("Singular matrix")
     if (T.degenerate) { write_fail(GT_SINGULAR, flip, maf, nan(""), 0); return; }
 
-    for (int t = lane; t < 3 * 32 * PS; t += 32) xs[t] = 0.0;    // xs, wxs, us
+    for (int t = lane; t < 2 * PH * XT; t += 32) xT[t] = 0.0;    // xT, uT (rows >= p stay 0)
     for (int t = lane; t < PH; t += 32) { beta[t] = 0.0; prev[t] = INFINITY; }
     __syncwarp();
 
-    // design row of a slot into xs[lane][0..p), returns eta and validity
+    // design row of a slot into xT[0..p)[lane], returns eta and validity
     auto load_row = [&](int slot, double &eta, int &info) -> bool {
         int pos = T.slot_pos[slot];
         info = T.slot_info[slot];
         double g = 0.0;
         bool ok = pos >= 0;
         if (ok) ok = load_geno<PACKED>(rowp, pos, g);
-        double *xr = xs + lane * PS;
+        double *xr = xT + lane;
         eta = 0.0;
         if (ok) {
             if (flip) g = 2.0 - g;
             const double *xi = T.Xs + (long long)slot * T.XS;
-            for (int a = 0; a < k; ++a) { double v = xi[a]; xr[a] = v; eta = fma(v, beta[a], eta); }
-            xr[k] = g; eta = fma(g, beta[k], eta);
-            for (int j = 0; j < I; ++j) { double v = g * xi[k + j]; xr[k + 1 + j] = v; eta = fma(v, beta[k + 1 + j], eta); }
+            for (int a = 0; a < k; ++a) { double v = xi[a]; xr[a * XT] = v; eta = fma(v, beta[a], eta); }
+            xr[k * XT] = g; eta = fma(g, beta[k], eta);
+            for (int j = 0; j < I; ++j) { double v = g * xi[k + j]; xr[(k + 1 + j) * XT] = v; eta = fma(v, beta[k + 1 + j], eta); }
         } else {
-            for (int a = 0; a < p; ++a) xr[a] = 0.0;
+            for (int a = 0; a < p; ++a) xr[a * XT] = 0.0;
         }
         return ok;
     };
@@ -214,10 +217,10 @@ cox_newton_kernel(IterDesignDev T, const void *__restrict__ geno, long long pitc
             if (la == 0) PCIa = 0.0;
             double Wi = e * ((Ttot - PIa) - (ev ? (PCIb - PCIa) : 0.0));
             double Gi = (ev ? 1.0 : 0.0) - Wi;
-            double *xr = xs + lane * PS, *wr = wxs + lane * PS, *ur = us + lane * PS;
+            double *xr = xT + lane, *ur = uT + lane;
+            wv[lane] = Wi; gv[lane] = Gi;
             for (int a = 0; a < p; ++a) {
-                double xa = xr[a];
-                wr[a] = Wi * xa;
+                double xa = xr[a * XT];
                 // running S1 (risk set) and F1 (tied events of the group)
                 double s1 = warp_scan_incl(e * xa, lane) + carry[a];
                 double s1g = __shfl_sync(GT_FULL, s1, lb);
@@ -229,20 +232,22 @@ cox_newton_kernel(IterDesignDev T, const void *__restrict__ geno, long long pitc
                     if (la == 0) fa = 0.0;
                     f1g = fb - fa;
                 }
-                ur[a] = ev ? (s1g - c * f1g) * inv : 0.0;
+                ur[a * XT] = ev ? (s1g - c * f1g) * inv : 0.0;
                 if (lane == 0) carry[a] = s1_last;     // read above, before the scan's shuffles
             }
-            wr[p] = Gi;
             __syncwarp();
+            // A = x, B = [W x | G]: the weights are applied while the
+            // fragments are loaded (column p of B carries the score)
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks) {
                 const int e4 = ks * 4 + (lane & 3), cc = lane >> 2;
+                const double wsc = wv[e4], gsc = gv[e4];
                 double xf[NT], wf[NT], uf[NT];
 #pragma unroll
                 for (int t = 0; t < NT; ++t) {
-                    xf[t] = xs[e4 * PS + t * 8 + cc];
-                    wf[t] = wxs[e4 * PS + t * 8 + cc];
-                    uf[t] = us[e4 * PS + t * 8 + cc];
+                    xf[t] = xT[(t * 8 + cc) * XT + e4];
+                    uf[t] = uT[(t * 8 + cc) * XT + e4];
+                    wf[t] = (t * 8 + cc == p) ? gsc : wsc * xf[t];
                 }
 #pragma unroll
                 for (int mt = 0; mt < NT; ++mt)
