@@ -138,8 +138,8 @@ static int launch_cox(const IterDesignDev &T, const void *geno, int64_t pitch, i
     using Cfg = CoxCfg<NT>;
     // two CTAs per SM: as many warps as fit half of the shared memory
     int wpc = 8;
-    while (wpc > 1 && (size_t)wpc * Cfg::perWarp * 8 > 112 * 1024) --wpc;
-    size_t smem = (size_t)wpc * Cfg::perWarp * 8;
+    while (wpc > 1 && (size_t)wpc * Cfg::perWarp(T.p) * 8 > 112 * 1024) --wpc;
+    size_t smem = (size_t)wpc * Cfg::perWarp(T.p) * 8;
     CK(cudaFuncSetAttribute((const void *)cox_newton_kernel<PACKED, NT>,
                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cox_newton_kernel<PACKED, NT><<<(n_snps + wpc - 1) / wpc, wpc * 32, smem, st>>>(

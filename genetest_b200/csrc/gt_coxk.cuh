@@ -49,8 +49,11 @@ struct CoxCfg {
     // samples of the block; a row stride of 36 doubles keeps the per-lane
     // stores and the MMA fragment loads bank-conflict free
     static constexpr int XT = 36;
-    // xT, uT, per-sample weights (W, G), H, Hc, Hinv, beta, step, carry, coef, var, prev
-    static constexpr int perWarp = 2 * PH * XT + 64 + 3 * PH * PH + 6 * PH;
+    // xT, uT (p rows each: the MMA fragment loads of rows p .. PH-1 run into
+    // the arrays that follow and only feed ignored outputs), per-sample
+    // weights (W, G), H, Hc, Hinv, beta, step, carry, coef, var, prev
+    static constexpr int fixed = 64 + 3 * PH * PH + 6 * PH;
+    __host__ __device__ static constexpr int perWarp(int p) { return 2 * p * XT + fixed; }
 };
 
 template <bool PACKED, int NT>
@@ -66,8 +69,8 @@ cox_newton_kernel(IterDesignDev T, const void *__restrict__ geno, long long pitc
     const int k = T.k, I = T.I, p = T.p;
     const int nf = GT_F_PARAM0 + 6 * p;
 
-    double *W = sm + (size_t)warp * Cfg::perWarp;
-    double *xT = W, *uT = xT + PH * XT, *wv = uT + PH * XT, *gv = wv + 32, *H = gv + 32,
+    double *W = sm + (size_t)warp * Cfg::perWarp(p);
+    double *xT = W, *uT = xT + p * XT, *wv = uT + p * XT, *gv = wv + 32, *H = gv + 32,
            *Hc = H + PH * PH, *Hinv = Hc + PH * PH, *beta = Hinv + PH * PH, *step = beta + PH,
            *carry = step + PH, *coef = carry + PH, *var = coef + PH, *prev = var + PH;
 
@@ -116,7 +119,8 @@ cox_newton_kernel(IterDesignDev T, const void *__restrict__ geno, long long pitc
     // rank-deficient covariates: inv(-H) fails in the reference ("Singular matrix")
     if (T.degenerate) { write_fail(GT_SINGULAR, flip, maf, nan(""), 0); return; }
 
-    for (int t = lane; t < 2 * PH * XT; t += 32) xT[t] = 0.0;    // xT, uT (rows >= p stay 0)
+    for (int t = lane; t < Cfg::perWarp(p); t += 32) xT[t] = 0.0;   // nothing non-finite behind the tiles
+    __syncwarp();
     for (int t = lane; t < PH; t += 32) { beta[t] = 0.0; prev[t] = INFINITY; }
     __syncwarp();
 
