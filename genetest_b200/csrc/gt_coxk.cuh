@@ -223,21 +223,63 @@ cox_newton_kernel(IterDesignDev T, const void *__restrict__ geno, long long pitc
             double Gi = (ev ? 1.0 : 0.0) - Wi;
             double *xr = xT + lane, *ur = uT + lane;
             wv[lane] = Wi; gv[lane] = Gi;
-            for (int a = 0; a < p; ++a) {
-                double xa = xr[a * XT];
-                // running S1 (risk set) and F1 (tied events of the group)
-                double s1 = warp_scan_incl(e * xa, lane) + carry[a];
-                double s1g = __shfl_sync(GT_FULL, s1, lb);
-                double s1_last = __shfl_sync(GT_FULL, s1, 31);
-                double f1g = ev ? e * xa : 0.0;
-                if (ties) {
-                    double f1 = warp_scan_incl(ev ? e * xa : 0.0, lane);
-                    double fb = __shfl_sync(GT_FULL, f1, lb), fa = __shfl_sync(GT_FULL, f1, lam1);
-                    if (la == 0) fa = 0.0;
-                    f1g = fb - fa;
+            // running S1 (risk set) and F1 (tied events of the group), CV
+            // design columns at a time so that their scans overlap
+            constexpr int CV = 4;
+            for (int a0 = 0; a0 < p; a0 += CV) {
+                double z[CV], cr[CV];
+#pragma unroll
+                for (int j = 0; j < CV; ++j) {
+                    const int a = a0 + j < p ? a0 + j : p - 1;
+                    z[j] = e * xr[a * XT];
+                    cr[j] = carry[a];
                 }
-                ur[a * XT] = ev ? (s1g - c * f1g) * inv : 0.0;
-                if (lane == 0) carry[a] = s1_last;     // read above, before the scan's shuffles
+                double s1[CV];
+#pragma unroll
+                for (int j = 0; j < CV; ++j) s1[j] = z[j];
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    double t[CV];
+#pragma unroll
+                    for (int j = 0; j < CV; ++j) t[j] = __shfl_up_sync(GT_FULL, s1[j], o);
+                    if (lane >= o) {
+#pragma unroll
+                        for (int j = 0; j < CV; ++j) s1[j] += t[j];
+                    }
+                }
+                double f1g[CV];
+#pragma unroll
+                for (int j = 0; j < CV; ++j) { s1[j] += cr[j]; f1g[j] = ev ? z[j] : 0.0; }
+                if (ties) {
+                    double f1[CV];
+#pragma unroll
+                    for (int j = 0; j < CV; ++j) f1[j] = f1g[j];
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        double t[CV];
+#pragma unroll
+                        for (int j = 0; j < CV; ++j) t[j] = __shfl_up_sync(GT_FULL, f1[j], o);
+                        if (lane >= o) {
+#pragma unroll
+                            for (int j = 0; j < CV; ++j) f1[j] += t[j];
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < CV; ++j) {
+                        double fb = __shfl_sync(GT_FULL, f1[j], lb), fa = __shfl_sync(GT_FULL, f1[j], lam1);
+                        if (la == 0) fa = 0.0;
+                        f1g[j] = fb - fa;
+                    }
+                }
+                __syncwarp();              // every lane has read carry[a0 ..]
+#pragma unroll
+                for (int j = 0; j < CV; ++j) {
+                    const double s1g = __shfl_sync(GT_FULL, s1[j], lb);
+                    if (a0 + j < p) {
+                        ur[(a0 + j) * XT] = ev ? (s1g - c * f1g[j]) * inv : 0.0;
+                        if (lane == 31) carry[a0 + j] = s1[j];
+                    }
+                }
             }
             __syncwarp();
             // A = x, B = [W x | G]: the weights are applied while the
