@@ -95,6 +95,16 @@ static int iter_set_design(const gt_design_desc *d, const std::vector<int> &pos,
         int *ip = (int *)&host[base + Xs.size()];
         std::memcpy(ip, slot_pos.data(), ns * 4);
         std::memcpy(ip + ns, slot_info.data(), ns * 4);
+        // max |x| per design column (q | g | g w): bounds the change of the
+        // linear predictor after a Newton step
+        size_t cm = host.size();
+        host.resize(cm + p, 0.0);
+        for (int j = 0; j < k; ++j)
+            for (int i = 0; i < n; ++i) host[cm + j] = std::max(host[cm + j], std::fabs(H.Q[(size_t)j * n + i]));
+        host[cm + k] = 2.0;
+        for (int j = 0; j < I; ++j)
+            for (int i = 0; i < n; ++i)
+                host[cm + k + 1 + j] = std::max(host[cm + k + 1 + j], 2.0 * std::fabs(d->W[(size_t)j * n + i]));
         // pointers may have moved
         X = host.data(); y = X + n_pad * XSs; Rinv = y + n_pad;
         T.n_slots = (int)ns;
@@ -111,8 +121,9 @@ static int iter_set_design(const gt_design_desc *d, const std::vector<int> &pos,
         T.Xs = xs;
         T.slot_pos = (const int *)(xs + (size_t)T.n_slots * XSs);
         T.slot_info = T.slot_pos + T.n_slots;
+        T.colmax = (const double *)buf.p + (host.size() - p);
     } else {
-        T.n_slots = 0; T.Xs = nullptr; T.slot_pos = nullptr; T.slot_info = nullptr;
+        T.n_slots = 0; T.Xs = nullptr; T.slot_pos = nullptr; T.slot_info = nullptr; T.colmax = nullptr;
     }
     CK(cudaStreamSynchronize(st));
     return 0;

@@ -148,14 +148,23 @@ cox_newton_kernel(IterDesignDev T, const void *__restrict__ geno, long long pitc
     int status = GT_OK, niter = 0;
     double llf = 0.0;
     bool final_eval = false;
+    // Shift of the linear predictor (the reference subtracts its maximum).
+    // At beta = 0 the maximum is 0; after a step it grows by at most
+    // sum_a |step_a| max|x_a|, so the pass that finds the exact maximum only
+    // runs once that bound has drifted by more than 20.
+    double emax = 0.0, slack = 0.0;
     while (true) {
         // ---- pass 0: max of the linear predictor ----
-        double emax = -INFINITY;
-        for (int b = 0; b < nblk; ++b) {
-            double eta; int info;
-            if (load_row(b * 32 + lane, eta, info)) emax = fmax(emax, eta);
+        // (real-valued / raw columns are not bounded by 2: always exact)
+        if (!PACKED || T.raw_mode || slack > 20.0 || !(slack == slack)) {
+            emax = -INFINITY;
+            for (int b = 0; b < nblk; ++b) {
+                double eta; int info;
+                if (load_row(b * 32 + lane, eta, info)) emax = fmax(emax, eta);
+            }
+            emax = gt_warp_max(emax);
+            slack = 0.0;
         }
-        emax = gt_warp_max(emax);
         // ---- pass 1: total of 1/den over all event terms ----
         double Ttot = 0.0;
         {
@@ -168,6 +177,10 @@ cox_newton_kernel(IterDesignDev T, const void *__restrict__ geno, long long pitc
                 double e = ok ? exp(eta - emax) : 0.0;
                 double S0 = warp_scan_incl(e, lane) + c0;
                 c0 = __shfl_sync(GT_FULL, S0, 31);
+                if (!((info >> 11) & 1)) {      // no tie group in this block (warp-uniform)
+                    if (ev) Ttot += 1.0 / S0;
+                    continue;
+                }
                 double PF = warp_scan_incl(ev ? e : 0.0, lane);
                 int PD = warp_scan_incl_int(ev ? 1 : 0, lane);
                 double S0g = __shfl_sync(GT_FULL, S0, lb);
@@ -199,27 +212,37 @@ cox_newton_kernel(IterDesignDev T, const void *__restrict__ geno, long long pitc
             double e = ok ? exp(eta - emax) : 0.0;
             double S0 = warp_scan_incl(e, lane) + c0;
             c0 = __shfl_sync(GT_FULL, S0, 31);
-            double PF = warp_scan_incl(ev ? e : 0.0, lane);
-            int PD = warp_scan_incl_int(ev ? 1 : 0, lane);
-            double S0g = __shfl_sync(GT_FULL, S0, lb);
-            double PFb = __shfl_sync(GT_FULL, PF, lb), PFa = __shfl_sync(GT_FULL, PF, lam1);
-            int PDb = __shfl_sync(GT_FULL, PD, lb), PDa = __shfl_sync(GT_FULL, PD, lam1);
-            if (la == 0) { PFa = 0.0; PDa = 0; }
-            double c = 0.0, inv = 0.0;
+            // without a tie group in the block (warp-uniform flag) every
+            // sample is its own group: c = 0, den = S0 of its own lane
+            double c = 0.0, inv = 0.0, den = S0;
+            if (ties) {
+                double PF = warp_scan_incl(ev ? e : 0.0, lane);
+                int PD = warp_scan_incl_int(ev ? 1 : 0, lane);
+                double S0g = __shfl_sync(GT_FULL, S0, lb);
+                double PFb = __shfl_sync(GT_FULL, PF, lb), PFa = __shfl_sync(GT_FULL, PF, lam1);
+                int PDb = __shfl_sync(GT_FULL, PD, lb), PDa = __shfl_sync(GT_FULL, PD, lam1);
+                if (la == 0) { PFa = 0.0; PDa = 0; }
+                if (ev) {
+                    c = (double)(PD - 1 - PDa) / (double)(PDb - PDa);
+                    den = S0g - c * (PFb - PFa);
+                }
+            }
             if (ev) {
-                c = (double)(PD - 1 - PDa) / (double)(PDb - PDa);
-                double den = S0g - c * (PFb - PFa);
                 inv = 1.0 / den;
-                ll += (eta - emax) - log(den);
+                if (final_eval) ll += (eta - emax) - log(den);    // only the last pass reports it
             }
             double PI = warp_scan_incl(inv, lane) + cI;
             double PIa = __shfl_sync(GT_FULL, PI, lam1);
             if (la == 0) PIa = cI;
             cI = __shfl_sync(GT_FULL, PI, 31);
-            double PCI = warp_scan_incl(c * inv, lane);
-            double PCIb = __shfl_sync(GT_FULL, PCI, lb), PCIa = __shfl_sync(GT_FULL, PCI, lam1);
-            if (la == 0) PCIa = 0.0;
-            double Wi = e * ((Ttot - PIa) - (ev ? (PCIb - PCIa) : 0.0));
+            double tie_term = 0.0;
+            if (ties) {
+                double PCI = warp_scan_incl(c * inv, lane);
+                double PCIb = __shfl_sync(GT_FULL, PCI, lb), PCIa = __shfl_sync(GT_FULL, PCI, lam1);
+                if (la == 0) PCIa = 0.0;
+                if (ev) tie_term = PCIb - PCIa;
+            }
+            double Wi = e * ((Ttot - PIa) - tie_term);
             double Gi = (ev ? 1.0 : 0.0) - Wi;
             double *xr = xT + lane, *ur = uT + lane;
             wv[lane] = Wi; gv[lane] = Gi;
@@ -274,7 +297,7 @@ cox_newton_kernel(IterDesignDev T, const void *__restrict__ geno, long long pitc
                 __syncwarp();              // every lane has read carry[a0 ..]
 #pragma unroll
                 for (int j = 0; j < CV; ++j) {
-                    const double s1g = __shfl_sync(GT_FULL, s1[j], lb);
+                    const double s1g = ties ? __shfl_sync(GT_FULL, s1[j], lb) : s1[j];
                     if (a0 + j < p) {
                         ur[(a0 + j) * XT] = ev ? (s1g - c * f1g[j]) * inv : 0.0;
                         if (lane == 31) carry[a0 + j] = s1[j];
@@ -358,6 +381,10 @@ cox_newton_kernel(IterDesignDev T, const void *__restrict__ geno, long long pitc
             worst = fmax(worst, fabs(d));
         }
         worst = gt_warp_max(worst);
+        double grow = 0.0;
+        for (int i = lane; i < p; i += 32) grow = fma(fabs(step[i]), T.colmax[i], grow);
+        grow = gt_warp_sum(grow);
+        emax += grow; slack += grow;
         for (int i = lane; i < p; i += 32) beta[i] += step[i];
         __syncwarp();
         niter += 1;
