@@ -37,45 +37,66 @@ static int iter_set_design(const gt_design_desc *d, const std::vector<int> &pos,
         y[pos[i]] = d->y[i];
     }
     for (int t = 0; t < k * k; ++t) Rinv[t] = H.Rinv[t];
-    // coxph: schedule in descending time, tie groups inside 32-slot blocks
-    std::vector<int> slot_pos, slot_info;
+    // coxph: schedule in descending time.  At one time point the censored
+    // samples come first, each on its own (they only have to be in the risk
+    // set of the events tied with them); the events of that time form one
+    // Efron group: inside one 32-slot block when there are at most 32, else
+    // over whole blocks of their own ("big group": blk_info = block count on
+    // the first block).
+    std::vector<int> slot_pos, slot_info, blk_info;
     std::vector<double> Xs;
     if (d->model == GT_MODEL_COXPH) {
         std::vector<int> order(n);
         for (int i = 0; i < n; ++i) order[i] = i;
         std::stable_sort(order.begin(), order.end(),
                          [&](int a, int b) { return d->y[a] > d->y[b]; });
+        auto pad_block = [&]() {
+            for (int fill = (int)(slot_pos.size() % 32); fill != 0 && fill < 32; ++fill) {
+                slot_pos.push_back(-1);
+                slot_info.push_back(fill | (fill << 5));
+            }
+        };
+        auto push = [&](int row, int la, int lb, int ev) {
+            slot_pos.push_back(pos[row]);
+            slot_info.push_back(la | (lb << 5) | (ev << 10));
+        };
+        std::vector<int> big_first, big_blocks;
         int i0 = 0;
         while (i0 < n) {
             int i1 = i0;
             while (i1 + 1 < n && d->y[order[i1 + 1]] == d->y[order[i0]]) ++i1;
-            int size = i1 - i0 + 1;
-            if (size > 32)
-                return fail(GT_E_UNSUPPORTED, "coxph: %d samples share one time; at most 32 tied samples are supported", size);
-            int fill = (int)(slot_pos.size() % 32);
-            if (fill + size > 32)
-                for (; fill < 32; ++fill) {      // pad: singleton empty slots
-                    slot_pos.push_back(-1);
-                    slot_info.push_back(fill | (fill << 5));
-                }
-            int la = (int)(slot_pos.size() % 32), lb = la + size - 1;
+            std::vector<int> events;
             for (int t = i0; t <= i1; ++t) {
                 int row = order[t];
-                slot_pos.push_back(pos[row]);
-                int ev = d->event[row] != 0.0 ? 1 : 0;
-                slot_info.push_back(la | (lb << 5) | (ev << 10));
+                if (d->event[row] != 0.0) { events.push_back(row); continue; }
+                int l = (int)(slot_pos.size() % 32);
+                push(row, l, l, 0);
+            }
+            const int m = (int)events.size();
+            if (m > 32) {
+                pad_block();
+                big_first.push_back((int)(slot_pos.size() / 32));
+                big_blocks.push_back((m + 31) / 32);
+                for (int row : events) { int l = (int)(slot_pos.size() % 32); push(row, l, l, 1); }
+                pad_block();
+            } else if (m > 0) {
+                if ((int)(slot_pos.size() % 32) + m > 32) pad_block();
+                int la = (int)(slot_pos.size() % 32), lb = la + m - 1;
+                for (int row : events) push(row, la, lb, 1);
             }
             i0 = i1 + 1;
         }
-        for (int fill = (int)(slot_pos.size() % 32); fill != 0 && fill < 32; ++fill) {
-            slot_pos.push_back(-1);
-            slot_info.push_back(fill | (fill << 5));
-        }
+        pad_block();
         const size_t ns = slot_pos.size();
         for (size_t b = 0; b < ns; b += 32) {
             bool ties = false;
             for (int t = 0; t < 32; ++t) ties |= ((slot_info[b + t] & 31) != ((slot_info[b + t] >> 5) & 31));
             if (ties) for (int t = 0; t < 32; ++t) slot_info[b + t] |= 1 << 11;
+        }
+        blk_info.assign(ns / 32, 1);
+        for (size_t g = 0; g < big_first.size(); ++g) {
+            blk_info[big_first[g]] = big_blocks[g];
+            for (int t = 1; t < big_blocks[g]; ++t) blk_info[big_first[g] + t] = -1;
         }
         Xs.assign(ns * XSs, 0.0);
         // slot -> design row: rebuild from the sorted order
@@ -88,13 +109,14 @@ static int iter_set_design(const gt_design_desc *d, const std::vector<int> &pos,
             for (int j = 0; j < k; ++j) Xs[s * XSs + j] = H.Q[(size_t)j * n + row];
             for (int j = 0; j < I; ++j) Xs[s * XSs + k + j] = d->W[(size_t)j * n + row];
         }
-        // append: Xs | slot_pos | slot_info  (ints packed two per double)
+        // append: Xs | slot_pos | slot_info | blk_info  (ints packed two per double)
         size_t base = host.size();
-        host.resize(base + Xs.size() + ns + 2, 0.0);
+        host.resize(base + Xs.size() + ns + ns / 64 + 2, 0.0);
         std::memcpy(&host[base], Xs.data(), Xs.size() * 8);
         int *ip = (int *)&host[base + Xs.size()];
         std::memcpy(ip, slot_pos.data(), ns * 4);
         std::memcpy(ip + ns, slot_info.data(), ns * 4);
+        std::memcpy(ip + 2 * ns, blk_info.data(), (ns / 32) * 4);
         // max |x| per design column (q | g | g w): bounds the change of the
         // linear predictor after a Newton step
         size_t cm = host.size();
@@ -121,9 +143,10 @@ static int iter_set_design(const gt_design_desc *d, const std::vector<int> &pos,
         T.Xs = xs;
         T.slot_pos = (const int *)(xs + (size_t)T.n_slots * XSs);
         T.slot_info = T.slot_pos + T.n_slots;
+        T.blk_info = T.slot_info + T.n_slots;
         T.colmax = (const double *)buf.p + (host.size() - p);
     } else {
-        T.n_slots = 0; T.Xs = nullptr; T.slot_pos = nullptr; T.slot_info = nullptr; T.colmax = nullptr;
+        T.n_slots = 0; T.Xs = nullptr; T.slot_pos = nullptr; T.slot_info = nullptr; T.blk_info = nullptr; T.colmax = nullptr;
     }
     CK(cudaStreamSynchronize(st));
     return 0;

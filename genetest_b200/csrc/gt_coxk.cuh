@@ -170,6 +170,23 @@ cox_newton_kernel(IterDesignDev T, const void *__restrict__ geno, long long pitc
         {
             double c0 = 0.0;
             for (int b = 0; b < nblk; ++b) {
+                const int nbig = T.blk_info[b];
+                if (nbig > 1) {
+                    // tied events over several blocks: den_j = S0g - (j/d) EG
+                    double EG = 0.0; int dg = 0;
+                    for (int bb = b; bb < b + nbig; ++bb) {
+                        double eta; int info;
+                        bool ok = load_row(bb * 32 + lane, eta, info);
+                        if (ok) { EG += exp(eta - emax); dg += 1; }
+                    }
+                    EG = gt_warp_sum(EG); dg = gt_warp_sum_int(dg);
+                    const double S0g = c0 + EG;
+                    for (int j = lane; j < dg; j += 32)
+                        Ttot += 1.0 / (S0g - ((double)j / (double)dg) * EG);
+                    c0 = S0g;
+                    b += nbig - 1;
+                    continue;
+                }
                 double eta; int info;
                 bool ok = load_row(b * 32 + lane, eta, info);
                 const int la = info & 31, lb = (info >> 5) & 31;
@@ -203,7 +220,87 @@ cox_newton_kernel(IterDesignDev T, const void *__restrict__ geno, long long pitc
         double ll = 0.0, c0 = 0.0, cI = 0.0;
         for (int t = lane; t < PH; t += 32) carry[t] = 0.0;
         __syncwarp();
+        // A = x, B = [W x | G]: the weights are applied while the fragments
+        // are loaded (column p of B carries the score); U accumulates u u'
+        auto mma_block = [&]() {
+            __syncwarp();
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+                const int e4 = ks * 4 + (lane & 3), cc = lane >> 2;
+                const double wsc = wv[e4], gsc = gv[e4];
+                double xf[NT], wf[NT], uf[NT];
+#pragma unroll
+                for (int t = 0; t < NT; ++t) {
+                    xf[t] = xT[(t * 8 + cc) * XT + e4];
+                    uf[t] = uT[(t * 8 + cc) * XT + e4];
+                    wf[t] = (t * 8 + cc == p) ? gsc : wsc * xf[t];
+                }
+#pragma unroll
+                for (int mt = 0; mt < NT; ++mt)
+#pragma unroll
+                    for (int nt = mt; nt < NT; ++nt) {
+                        dmma884(accH[mt][nt][0], accH[mt][nt][1], xf[mt], wf[nt]);
+                        dmma884(accU[mt][nt][0], accU[mt][nt][1], uf[mt], uf[nt]);
+                    }
+            }
+            __syncwarp();
+        };
         for (int b = 0; b < nblk; ++b) {
+            const int nbig = T.blk_info[b];
+            if (nbig > 1) {
+                // ---- tied events over several blocks (all members are events) ----
+                // totals of the group first: EG = sum e, d, S1 at its end
+                double *s1_before = coef;             // free during the passes
+                for (int a = lane; a < p; a += 32) s1_before[a] = carry[a];
+                __syncwarp();
+                double EG = 0.0; int dg = 0;
+                for (int bb = b; bb < b + nbig; ++bb) {
+                    double eta; int info;
+                    bool ok = load_row(bb * 32 + lane, eta, info);
+                    double e = ok ? exp(eta - emax) : 0.0;
+                    EG += e; dg += ok ? 1 : 0;
+                    for (int a = 0; a < p; ++a) {
+                        double z = gt_warp_sum(e * xT[a * XT + lane]);
+                        if (lane == 0) carry[a] += z;
+                    }
+                    __syncwarp();
+                }
+                EG = gt_warp_sum(EG); dg = gt_warp_sum_int(dg);
+                const double S0g = c0 + EG;
+                // the d Efron terms, 32 at a time: u_j = (S1g - c_j F1g) / den_j
+                double Ag = 0.0, Cg = 0.0;
+                for (int j0 = 0; j0 < dg; j0 += 32) {
+                    const int j = j0 + lane;
+                    const bool valid = j < dg;
+                    const double cj = valid ? (double)j / (double)dg : 0.0;
+                    const double den = S0g - cj * EG;
+                    const double inv = valid ? 1.0 / den : 0.0;
+                    Ag += inv; Cg += cj * inv;
+                    if (valid && final_eval) ll -= log(den);
+                    for (int a = 0; a < p; ++a) {
+                        const double s1g = carry[a];
+                        uT[a * XT + lane] = (s1g - cj * (s1g - s1_before[a])) * inv;
+                    }
+                    wv[lane] = 0.0; gv[lane] = 0.0;
+                    mma_block();
+                }
+                Ag = gt_warp_sum(Ag); Cg = gt_warp_sum(Cg);
+                // the members: W_i = e_i (sum of 1/den over the terms at or after
+                // the group - sum_j c_j / den_j)
+                const double Mg = (Ttot - cI) - Cg;
+                for (int bb = b; bb < b + nbig; ++bb) {
+                    double eta; int info;
+                    bool ok = load_row(bb * 32 + lane, eta, info);
+                    const double Wi = ok ? exp(eta - emax) * Mg : 0.0;
+                    if (ok && final_eval) ll += eta - emax;
+                    wv[lane] = Wi; gv[lane] = (ok ? 1.0 : 0.0) - Wi;
+                    for (int a = 0; a < p; ++a) uT[a * XT + lane] = 0.0;
+                    mma_block();
+                }
+                c0 = S0g; cI += Ag;
+                b += nbig - 1;
+                continue;
+            }
             double eta; int info;
             bool ok = load_row(b * 32 + lane, eta, info);
             const int la = info & 31, lb = (info >> 5) & 31, lam1 = (la + 31) & 31;
@@ -304,29 +401,7 @@ cox_newton_kernel(IterDesignDev T, const void *__restrict__ geno, long long pitc
                     }
                 }
             }
-            __syncwarp();
-            // A = x, B = [W x | G]: the weights are applied while the
-            // fragments are loaded (column p of B carries the score)
-#pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {
-                const int e4 = ks * 4 + (lane & 3), cc = lane >> 2;
-                const double wsc = wv[e4], gsc = gv[e4];
-                double xf[NT], wf[NT], uf[NT];
-#pragma unroll
-                for (int t = 0; t < NT; ++t) {
-                    xf[t] = xT[(t * 8 + cc) * XT + e4];
-                    uf[t] = uT[(t * 8 + cc) * XT + e4];
-                    wf[t] = (t * 8 + cc == p) ? gsc : wsc * xf[t];
-                }
-#pragma unroll
-                for (int mt = 0; mt < NT; ++mt)
-#pragma unroll
-                    for (int nt = mt; nt < NT; ++nt) {
-                        dmma884(accH[mt][nt][0], accH[mt][nt][1], xf[mt], wf[nt]);
-                        dmma884(accU[mt][nt][0], accU[mt][nt][1], uf[mt], uf[nt]);
-                    }
-            }
-            __syncwarp();
+            mma_block();
         }
         ll = gt_warp_sum(ll);
         // -H = accH[:p,:p] - accU ; score = accH[:, p]

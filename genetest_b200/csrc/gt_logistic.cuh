@@ -38,6 +38,7 @@ struct IterDesignDev {
     const int *slot_info;   // [n_slots] bits 0-4 first lane of the tie group, 5-9 last lane,
                             //           bit 10 event, bit 11 block has a tie group
     const double *Xs;       // [n_slots][XS] q | w in slot order
+    const int *blk_info;    // [n_slots/32] 1, or the block count of a big tie group on its first block
     const double *colmax;   // [p] coxph: max |x| of every design column (q, g, g w)
     const double *maf_o;    // sex-aware MAF / flip per marker of the launch, or NULL
     const int *flip_o;

@@ -263,20 +263,27 @@ def _cox_data(rng, n, C, ties=False):
     return tte, event
 
 
-@pytest.mark.parametrize("ties", [False, True])
+@pytest.mark.parametrize("ties", [False, True, "heavy"])
 def test_coxph_packed(engine, ties):
-    rng = np.random.default_rng(31 + ties)
+    rng = np.random.default_rng(31 + bool(ties) + 2 * (ties == "heavy"))
     n, n_snps = 1500, 120
     C, names = synth_design(rng, n, k_extra=3)
     C, names = C[:, :-1], names[:-1]          # StatsCoxPH drops the intercept
     G = synth_genotypes(rng, n_snps, n, missing=0.01, maf_lo=0.05,
                         maf_hi=0.95)
     G[0] = 0.0                                # monomorphic -> Singular matrix
-    tte, event = _cox_data(rng, n, C, ties)
-    if ties:
-        # the engine keeps at most 32 tied samples in a block
+    tte, event = _cox_data(rng, n, C, bool(ties))
+    if ties == "heavy":
+        # a few distinct times with hundreds of tied events each (Efron groups
+        # spanning several 32-slot blocks) and administrative censoring
+        tte = np.ceil(tte * 3) / 3
+        late = tte > 1.0
+        tte[late], event[late] = 1.0, 0.0
+        _, counts = np.unique(tte[event == 1], return_counts=True)
+        assert counts.max() > 200 and late.sum() > 100
+    elif ties:
         _, counts = np.unique(tte, return_counts=True)
-        assert counts.max() <= 32 and counts.max() > 3
+        assert counts.max() > 3
     engine.set_design("coxph", tte, C, event=event)
     res = engine.run_packed_host(pack_rows(G))
     oracle = run_oracle("coxph", np.column_stack((tte, event)), C, names, G)
