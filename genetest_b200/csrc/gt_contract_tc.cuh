@@ -66,6 +66,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
 }
 // bounded wait: never hangs the GPU; gives up after ~0.2 s or as soon as
 // another thread of the CTA has flagged a failure
+// BACKOFF: the single-lane producer / MMA warps sleep between polls so that
+// their spinning does not take issue slots from the expansion warps.
+template <bool BACKOFF = false>
 __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, volatile int *fail) {
     uint32_t done = 0;
     for (int spin = 0; spin < (1 << 23); ++spin) {
@@ -76,6 +79,7 @@ __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, volati
             "selp.u32 %0, 1, 0, p;\n\t}\n"
             : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
         if (done) return true;
+        if (BACKOFF) __nanosleep(64);
     }
     return false;
 }
@@ -300,7 +304,7 @@ contract_tc_kernel(TcParams P) {
             for (int it = 0; it < n_stages; ++it) {
                 const int s = it % kTcStages;
                 const uint32_t par = ((it / kTcStages) & 1) ^ 1;
-                if (it >= kTcStages && !mbar_wait(&empty[s], par, fail)) { *fail = 1; }
+                if (it >= kTcStages && !mbar_wait<true>(&empty[s], par, fail)) { *fail = 1; }
                 mbar_expect_tx(&b_full[s], BSTAGE);
                 bulk_g2s(sB + s * BSTAGE, P.Bimg + (long long)it * BSTAGE, BSTAGE, &b_full[s]);
             }
@@ -314,8 +318,8 @@ contract_tc_kernel(TcParams P) {
             for (int it = 0; it < n_stages; ++it) {
                 const int s = it % kTcStages;
                 const uint32_t par = (it / kTcStages) & 1;
-                if (!mbar_wait(&a_full[s], par, fail)) *fail = 1;
-                if (!mbar_wait(&b_full[s], par, fail)) *fail = 1;
+                if (!mbar_wait<true>(&a_full[s], par, fail)) *fail = 1;
+                if (!mbar_wait<true>(&b_full[s], par, fail)) *fail = 1;
                 asm volatile("tcgen05.fence::after_thread_sync;\n");
                 const uint32_t bbase = smem_u32(sB + s * BSTAGE);
 #pragma unroll
