@@ -27,7 +27,9 @@ static int iter_set_design(const gt_design_desc *d, const std::vector<int> &pos,
     const size_t n_pad = (size_t)n_chunks * 256;
     const int XS = (k + I + 1) & ~1;
     const int XSs = XS > 0 ? XS : 2;
-    std::vector<double> host(n_pad * XSs + n_pad + (size_t)k * k + 2, 0.0);
+    // (k * k rounded up to even: what follows stays 16 B aligned)
+    const size_t kk2 = ((size_t)k * k + 1) & ~(size_t)1;
+    std::vector<double> host(n_pad * XSs + n_pad + kk2 + 2, 0.0);
     double *X = host.data(), *y = X + n_pad * XSs, *Rinv = y + n_pad;
     for (size_t i = 0; i < n_pad; ++i) y[i] = nan("");
     for (int i = 0; i < n; ++i) {
@@ -139,7 +141,7 @@ static int iter_set_design(const gt_design_desc *d, const std::vector<int> &pos,
     T.maf_o = nullptr; T.flip_o = nullptr;
     T.X = (const double *)buf.p; T.y = T.X + n_pad * XSs; T.Rinv = T.y + n_pad;
     if (d->model == GT_MODEL_COXPH) {
-        const double *xs = T.Rinv + (size_t)k * k + 2;
+        const double *xs = T.Rinv + kk2 + 2;
         T.Xs = xs;
         T.slot_pos = (const int *)(xs + (size_t)T.n_slots * XSs);
         T.slot_info = T.slot_pos + T.n_slots;

@@ -20,6 +20,8 @@
 // (m8n8k4) accumulations per 32 samples.
 #pragma once
 
+#include <type_traits>
+
 #include "gt_common.cuh"
 #include "gt_logistic.cuh"
 
@@ -124,8 +126,10 @@ cox_newton_kernel(IterDesignDev T, const void *__restrict__ geno, long long pitc
     for (int t = lane; t < PH; t += 32) { beta[t] = 0.0; prev[t] = INFINITY; }
     __syncwarp();
 
-    // design row of a slot into xT[0..p)[lane], returns eta and validity
-    auto load_row = [&](int slot, double &eta, int &info) -> bool {
+    // design row of a slot: eta = x'beta and validity; STORE also writes the
+    // row into xT[0..p)[lane]
+    auto load_row_impl = [&](int slot, double &eta, int &info, auto store_tag) -> bool {
+        constexpr bool STORE = decltype(store_tag)::value;
         int pos = T.slot_pos[slot];
         info = T.slot_info[slot];
         double g = 0.0;
@@ -136,13 +140,28 @@ cox_newton_kernel(IterDesignDev T, const void *__restrict__ geno, long long pitc
         if (ok) {
             if (flip) g = 2.0 - g;
             const double *xi = T.Xs + (long long)slot * T.XS;
-            for (int a = 0; a < k; ++a) { double v = xi[a]; xr[a * XT] = v; eta = fma(v, beta[a], eta); }
-            xr[k * XT] = g; eta = fma(g, beta[k], eta);
-            for (int j = 0; j < I; ++j) { double v = g * xi[k + j]; xr[(k + 1 + j) * XT] = v; eta = fma(v, beta[k + 1 + j], eta); }
-        } else {
+            for (int a = 0; a < k; ++a) {
+                double v = xi[a];
+                if (STORE) xr[a * XT] = v;
+                eta = fma(v, beta[a], eta);
+            }
+            if (STORE) xr[k * XT] = g;
+            eta = fma(g, beta[k], eta);
+            for (int j = 0; j < I; ++j) {
+                double v = g * xi[k + j];
+                if (STORE) xr[(k + 1 + j) * XT] = v;
+                eta = fma(v, beta[k + 1 + j], eta);
+            }
+        } else if (STORE) {
             for (int a = 0; a < p; ++a) xr[a * XT] = 0.0;
         }
         return ok;
+    };
+    auto load_row = [&](int slot, double &eta, int &info) {
+        return load_row_impl(slot, eta, info, std::true_type{});
+    };
+    auto load_eta = [&](int slot, double &eta, int &info) {
+        return load_row_impl(slot, eta, info, std::false_type{});
     };
 
     int status = GT_OK, niter = 0;
@@ -160,7 +179,7 @@ cox_newton_kernel(IterDesignDev T, const void *__restrict__ geno, long long pitc
             emax = -INFINITY;
             for (int b = 0; b < nblk; ++b) {
                 double eta; int info;
-                if (load_row(b * 32 + lane, eta, info)) emax = fmax(emax, eta);
+                if (load_eta(b * 32 + lane, eta, info)) emax = fmax(emax, eta);
             }
             emax = gt_warp_max(emax);
             slack = 0.0;
@@ -176,7 +195,7 @@ cox_newton_kernel(IterDesignDev T, const void *__restrict__ geno, long long pitc
                     double EG = 0.0; int dg = 0;
                     for (int bb = b; bb < b + nbig; ++bb) {
                         double eta; int info;
-                        bool ok = load_row(bb * 32 + lane, eta, info);
+                        bool ok = load_eta(bb * 32 + lane, eta, info);
                         if (ok) { EG += exp(eta - emax); dg += 1; }
                     }
                     EG = gt_warp_sum(EG); dg = gt_warp_sum_int(dg);
@@ -188,7 +207,7 @@ cox_newton_kernel(IterDesignDev T, const void *__restrict__ geno, long long pitc
                     continue;
                 }
                 double eta; int info;
-                bool ok = load_row(b * 32 + lane, eta, info);
+                bool ok = load_eta(b * 32 + lane, eta, info);
                 const int la = info & 31, lb = (info >> 5) & 31;
                 const bool ev = ok && ((info >> 10) & 1);
                 double e = ok ? exp(eta - emax) : 0.0;
