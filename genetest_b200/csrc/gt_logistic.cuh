@@ -143,6 +143,11 @@ logistic_irls_kernel(IterDesignDev T, const void *__restrict__ geno, long long p
     for (int t = lane; t < PH; t += 32) beta[t] = 0.0;
     __syncwarp();
 
+    // pass-0 values of a binary outcome, by the formulas of the general branch
+    const double mu1 = (1.0 + 0.5) / 2.0, mu0 = (0.0 + 0.5) / 2.0;
+    const double eta1 = log(mu1 / (1.0 - mu1)), eta0 = log(mu0 / (1.0 - mu0));
+    const double dev1 = 2.0 * (1.0 * log(fmax(1.0 / (mu1 + 1e-20), EPS)) + 0.0 * log(fmax(0.0 / (1.0 - mu1 + 1e-20), EPS)));
+    const double dev0 = 2.0 * (0.0 * log(fmax(0.0 / (mu0 + 1e-20), EPS)) + 1.0 * log(fmax(1.0 / (1.0 - mu0 + 1e-20), EPS)));
     double dev_prev = 0.0, llf = 0.0;
     int niter = 0;
     int status = GT_OK;
@@ -156,30 +161,61 @@ logistic_irls_kernel(IterDesignDev T, const void *__restrict__ geno, long long p
             for (int b = 0; b < NT; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
         double dev = 0.0, ll = 0.0;
         int sep = 1;
+        // The outcome, genotype and design row of block b + 1 are loaded into
+        // registers while block b is being worked on (X and y have n_pad >=
+        // 32 nblk rows; rows of excluded samples are zero / NaN).
+        double ny, nx[PH], ngd = 0.0;
+        uint32_t nbyte = 0;
+        auto prefetch = [&](int b) {
+            const int i = b * 32 + lane;
+            ny = T.y[i];
+            if (PACKED) nbyte = ((const uint8_t *)rowp)[i >> 2];
+            else ngd = (i < T.n_file) ? ((const double *)rowp)[i] : nan("");
+            const double *xi = T.X + (long long)i * T.XS;
+#pragma unroll
+            for (int a = 0; a < PH; ++a)
+                if (a < k + I) nx[a] = xi[a];
+        };
+        prefetch(0);
         for (int b = 0; b < nblk; ++b) {
-            int i = b * 32 + lane;
-            double yv = (i < T.n_file) ? T.y[i] : nan("");
+            const int i = b * 32 + lane;
+            const double yv = (i < T.n_file) ? ny : nan("");
             double g = 0.0;
             bool ok = (yv == yv);
-            if (ok) ok = load_geno<PACKED>(rowp, i, g);
+            if (PACKED) {
+                const uint32_t code = (nbyte >> (2 * (i & 3))) & 3u;
+                g = (code == 0) ? 2.0 : ((code == 2) ? 1.0 : 0.0);
+                ok = ok && code != 1;
+            } else {
+                g = ngd;
+                ok = ok && g == g;
+            }
             if (!ok) g = 0.0;
             else if (flip) g = 2.0 - g;
             // design row [q | g | g w] into the transposed staging tile, eta = x'beta
-            const double *xi = T.X + (long long)(ok ? i : 0) * T.XS;
-            double eta = 0.0;
+            double eta = g * beta[k];
+            xsT[k * XT + lane] = g;
 #pragma unroll
-            for (int a = 0; a < PH; ++a)
-                if (a < k) { double v = xi[a]; xsT[a * XT + lane] = v; eta = fma(v, beta[a], eta); }
-            xsT[k * XT + lane] = g; eta = fma(g, beta[k], eta);
-            for (int j = 0; j < I; ++j) {
-                double v = g * xi[k + j];
-                xsT[(k + 1 + j) * XT + lane] = v; eta = fma(v, beta[k + 1 + j], eta);
+            for (int a = 0; a < PH; ++a) {
+                if (a < k) {
+                    const double v = nx[a];
+                    xsT[a * XT + lane] = v; eta = fma(v, beta[a], eta);
+                } else if (a < k + I) {
+                    const double v = g * nx[a];
+                    xsT[(a + 1) * XT + lane] = v; eta = fma(v, beta[a + 1], eta);
+                }
             }
+            if (b + 1 < nblk) prefetch(b + 1);
             double w = 0.0, z = 0.0;
             if (ok) {
                 double mu;
                 const bool binary = (yv == 0.0) || (yv == 1.0);
-                if (pass == 0) {
+                if (pass == 0 && binary) {
+                    // statsmodels' start for y in {0, 1}: the same constants for every sample
+                    mu = yv != 0.0 ? mu1 : mu0;
+                    eta = yv != 0.0 ? eta1 : eta0;
+                    dev += yv != 0.0 ? dev1 : dev0;
+                } else if (pass == 0) {
                     mu = (yv + 0.5) / 2.0;
                     eta = log(mu / (1.0 - mu));
                     double e1 = fmax(yv / (mu + 1e-20), EPS), e0 = fmax((1.0 - yv) / (1.0 - mu + 1e-20), EPS);
@@ -191,7 +227,8 @@ logistic_irls_kernel(IterDesignDev T, const void *__restrict__ geno, long long p
                     mu = (eta >= 0.0) ? inv : t * inv;
                     if (binary) {
                         // y in {0, 1}: loglike_i = y eta + log(1 - mu), deviance_i = -2 loglike_i
-                        double li = yv * eta - (fmax(eta, 0.0) + log1p(t));
+                        // log(1 + t), t in (0, 1]: absolute error <= 1e-16 per sample
+                        double li = yv * eta - (fmax(eta, 0.0) + log(1.0 + t));
                         ll += li;
                         dev -= 2.0 * li;
                     } else {
