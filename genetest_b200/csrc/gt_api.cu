@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "gt_common.cuh"
@@ -216,15 +217,14 @@ int gt_debug_read_pattern(gt_engine *e, const uint8_t *packed_dev, int64_t pitch
 
 int gt_abi_version(void) { return GT_ABI_VERSION; }
 
-int64_t gt_format_rows(int32_t n_rows, int32_t n_cols, const int32_t *col_type,
-                       const void *const *col_data, const uint8_t *keep, char sep,
-                       char *out, int64_t out_cap) {
-    if (!col_type || !col_data || !out) return fail(GT_E_ARG, "gt_format_rows: NULL argument");
-    std::vector<const char *> cursor(n_cols, nullptr);
-    for (int c = 0; c < n_cols; ++c)
-        if (col_type[c] == 0 || col_type[c] == 3) cursor[c] = (const char *)col_data[c];
-    char *p = out, *end = out + out_cap;
-    for (int r = 0; r < n_rows; ++r) {
+// rows [r0, r1) into [p, end); cursor[c] = first string of row r0 for the
+// string columns.  Returns the end of the text, or NULL (bad column type /
+// out of room; *bad = offending type or 0).
+static char *format_row_range(int r0, int r1, int32_t n_cols, const int32_t *col_type,
+                              const void *const *col_data, const uint8_t *keep, char sep,
+                              std::vector<const char *> cursor, char *p, char *end, int *bad) {
+    *bad = 0;
+    for (int r = r0; r < r1; ++r) {
         const bool emit = !keep || keep[r];
         for (int c = 0; c < n_cols; ++c) {
             if (col_type[c] == 0) {                 // NUL-separated strings, one per row
@@ -232,23 +232,83 @@ int64_t gt_format_rows(int32_t n_rows, int32_t n_cols, const int32_t *col_type,
                 size_t len = std::strlen(s);
                 cursor[c] = s + len + 1;
                 if (!emit) continue;
-                if (p + len + 2 > end) return fail(GT_E_ARG, "gt_format_rows: output buffer too small");
+                if (p + len + 2 > end) return nullptr;
                 std::memcpy(p, s, len); p += len;
             } else {
                 if (!emit) continue;
-                if (p + 48 > end) return fail(GT_E_ARG, "gt_format_rows: output buffer too small");
+                if (p + 48 > end) return nullptr;
                 if (col_type[c] == 1) p = gtk::format_double_repr(((const double *)col_data[c])[r], p);
                 else if (col_type[c] == 2) {
                     auto res = std::to_chars(p, p + 24, ((const int64_t *)col_data[c])[r]);
                     p = res.ptr;
                 } else if (col_type[c] == 3) {      // one constant string for every row
-                    size_t len = std::strlen(cursor[c]);
-                    if (p + len + 2 > end) return fail(GT_E_ARG, "gt_format_rows: output buffer too small");
-                    std::memcpy(p, cursor[c], len); p += len;
-                } else return fail(GT_E_ARG, "gt_format_rows: bad column type %d", col_type[c]);
+                    const char *s = (const char *)col_data[c];
+                    size_t len = std::strlen(s);
+                    if (p + len + 2 > end) return nullptr;
+                    std::memcpy(p, s, len); p += len;
+                } else { *bad = col_type[c] ? col_type[c] : -1; return nullptr; }
             }
             *p++ = (c + 1 < n_cols) ? sep : '\n';
         }
+    }
+    return p;
+}
+
+int64_t gt_format_rows(int32_t n_rows, int32_t n_cols, const int32_t *col_type,
+                       const void *const *col_data, const uint8_t *keep, char sep,
+                       char *out, int64_t out_cap) {
+    if (!col_type || !col_data || !out) return fail(GT_E_ARG, "gt_format_rows: NULL argument");
+    if (n_rows <= 0) return 0;
+    // Row ranges are formatted by a few host threads, each into its own
+    // worst-case slice of `out`; the slices are then closed up in order.
+    int nt = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 8u);
+    nt = std::max(1, std::min(nt, n_rows / 4096));
+    int64_t fixed = 2;                              // worst-case bytes of a row without its strings
+    for (int c = 0; c < n_cols; ++c) {
+        if (col_type[c] == 1 || col_type[c] == 2) fixed += 26;
+        else if (col_type[c] == 3) fixed += (int64_t)std::strlen((const char *)col_data[c]) + 1;
+        else if (col_type[c] == 0) fixed += 0;          // text + NUL are counted from the cursors
+        else return fail(GT_E_ARG, "gt_format_rows: bad column type %d", col_type[c]);
+    }
+    std::vector<std::vector<const char *>> starts(nt + 1, std::vector<const char *>(n_cols, nullptr));
+    {
+        std::vector<const char *> cursor(n_cols, nullptr);
+        for (int c = 0; c < n_cols; ++c)
+            if (col_type[c] == 0) cursor[c] = (const char *)col_data[c];
+        int next = 0;
+        for (int r = 0;; ++r) {
+            while (next <= nt && r == (int)((int64_t)n_rows * next / nt)) starts[next++] = cursor;
+            if (next > nt) break;               // r == n_rows: every boundary is set
+            for (int c = 0; c < n_cols; ++c)
+                if (col_type[c] == 0) cursor[c] += std::strlen(cursor[c]) + 1;
+        }
+    }
+    std::vector<int64_t> off(nt + 1, 0);
+    for (int t = 0; t < nt; ++t) {
+        const int r0 = (int)((int64_t)n_rows * t / nt), r1 = (int)((int64_t)n_rows * (t + 1) / nt);
+        int64_t cap = (int64_t)(r1 - r0) * fixed + 64;
+        for (int c = 0; c < n_cols; ++c)
+            if (col_type[c] == 0) cap += starts[t + 1][c] - starts[t][c];
+        off[t + 1] = off[t] + cap;
+    }
+    if (off[nt] > out_cap) return fail(GT_E_ARG, "gt_format_rows: output buffer too small (%lld < %lld)", (long long)out_cap, (long long)off[nt]);
+    std::vector<char *> ends(nt, nullptr);
+    std::vector<int> bad(nt, 0);
+    auto work = [&](int t) {
+        const int r0 = (int)((int64_t)n_rows * t / nt), r1 = (int)((int64_t)n_rows * (t + 1) / nt);
+        ends[t] = format_row_range(r0, r1, n_cols, col_type, col_data, keep, sep, starts[t],
+                                   out + off[t], out + off[t + 1], &bad[t]);
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; ++t) pool.emplace_back(work, t);
+    work(0);
+    for (auto &th : pool) th.join();
+    char *p = out;
+    for (int t = 0; t < nt; ++t) {
+        if (!ends[t]) return fail(GT_E_ARG, "gt_format_rows: formatting failed (column type %d)", bad[t]);
+        const size_t len = (size_t)(ends[t] - (out + off[t]));
+        if (p != out + off[t]) std::memmove(p, out + off[t], len);
+        p += len;
     }
     return (int64_t)(p - out);
 }

@@ -445,7 +445,7 @@ def format_rows(columns, keep=None, sep="\t"):
         elif t == 3:
             width += len(b) + 1
     strbytes = sum(len(b) for t, b in zip(types, hold) if t == 0)
-    cap = n_rows * width + strbytes + 64
+    cap = n_rows * width + strbytes + 64 * 17     # + slack per formatter thread
     out = ctypes.create_string_buffer(cap)
     kp = None
     if keep is not None:
@@ -456,4 +456,4 @@ def format_rows(columns, keep=None, sep="\t"):
         (ctypes.c_void_p * len(ptrs))(*ptrs), kp, sep.encode(), out, cap)
     if n < 0:
         raise EngineError(lib.gt_last_error().decode())
-    return out.raw[:n]
+    return ctypes.string_at(out, n)

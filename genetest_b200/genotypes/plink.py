@@ -15,6 +15,7 @@ alleles: A1 is ``coded``, A2 is ``reference``.
 import os
 
 import numpy as np
+import pandas as pd
 
 from .core import Genotypes, GenotypesReader, Variant
 
@@ -74,16 +75,19 @@ class PlinkReader(GenotypesReader):
             self._samples = iids
         else:
             self._samples = ["{}_{}".format(a, b) for a, b in zip(fids, iids)]
-        self._bim = []
-        with open(prefix + ".bim") as f:
-            for line in f:
-                row = line.split()
-                if row:
-                    chrom, name, _cm, pos, a1, a2 = row[:6]
-                    self._bim.append((name, chrom, int(pos), a1, a2))
-        self._index = {}
-        for i, b in enumerate(self._bim):
-            self._index.setdefault(b[0], []).append(i)
+        # [(name, chrom, pos, a1, a2)]; the C parser keeps million-marker
+        # .bim files off the critical path
+        if os.path.getsize(prefix + ".bim"):
+            bim = pd.read_csv(prefix + ".bim", sep=r"\s+", header=None,
+                              usecols=[0, 1, 3, 4, 5], dtype=str,
+                              keep_default_na=False, na_filter=False,
+                              engine="c")
+            self._bim = list(zip(bim[1].tolist(), bim[0].tolist(),
+                                 bim[3].astype(np.int64).tolist(),
+                                 bim[4].tolist(), bim[5].tolist()))
+        else:
+            self._bim = []
+        self._index_cache = None
         self.n_samples = len(self._samples)
         self.n_variants = len(self._bim)
         self.row_bytes = (self.n_samples + 3) // 4
@@ -133,6 +137,15 @@ class PlinkReader(GenotypesReader):
     def iter_variants(self):
         for name, chrom, pos, a1, a2 in self._bim:
             yield Variant(name, chrom, pos, (a1, a2))
+
+    @property
+    def _index(self):
+        if self._index_cache is None:
+            index = {}
+            for i, b in enumerate(self._bim):
+                index.setdefault(b[0], []).append(i)
+            self._index_cache = index
+        return self._index_cache
 
     def get_variant_by_name(self, name):
         return [self._make(i) for i in self._index.get(name, [])]
