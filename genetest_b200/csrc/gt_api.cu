@@ -575,9 +575,13 @@ int gt_engine_set_design(gt_engine *e, const gt_design_desc *d) {
         e->tc_N = 0;
         std::vector<uint8_t> Bimg;
         std::vector<double> scale;
-        if (lean && 8 * NC1 <= 192) {
+        if (lean && 8 * NC1 + 1 <= 192) {
             const int ncol = NC1;
-            const int N = (8 * ncol + 15) / 16 * 16;
+            // 8 digit planes per column + one plane of ones over the design
+            // rows (its D column is the exact sum of the dosages)
+            const int N = (8 * ncol + 1 + 15) / 16 * 16;
+            std::vector<char> is_design(n_pad, 0);
+            for (int i = 0; i < n; ++i) is_design[pos[i]] = 1;
             const int n_st = (n_file + gtk::kTcStageK - 1) / gtk::kTcStageK;
             static const int perm16[16] = {0, 2, 4, 6, 8, 10, 12, 14, 1, 3, 5, 7, 9, 11, 13, 15};
             scale.assign(ncol, 1.0);
@@ -593,6 +597,10 @@ int gt_engine_set_design(gt_engine *e, const gt_design_desc *d) {
                     long long smp = (long long)st_i * 128 + (kk / 16) * 16 + perm16[kk % 16];
                     if (smp >= (long long)n_pad) continue;
                     const double *er = &E[(size_t)smp * NCP];
+                    if (is_design[smp]) {
+                        int nrow = 8 * ncol, grp = nrow >> 3, r = nrow & 7, chunk = kk >> 4, b = kk & 15;
+                        img[(size_t)grp * 1024 + r * 128 + ((chunk ^ r) << 4) + b] = 1;
+                    }
                     for (int c = 0; c < ncol; ++c) {
                         double x = er[c] / scale[c];
                         long long Z = llround(std::ldexp(x, 54));
@@ -685,14 +693,14 @@ static int launch_contract_tc(gt_engine *e, const uint8_t *g, int64_t pitch, int
     gtk::TcParams P;
     P.geno = g; P.pitch = pitch; P.n_snps = nb; P.ormask = e->D.ormask;
     P.Bimg = (const uint8_t *)e->dBimg.p; P.scale = (const double *)e->dScale.p;
-    P.n_stages = e->tc_stages; P.ncol = e->tc_ncol; P.N = e->tc_N; P.NCP = e->D.NCP;
+    P.n_stages = e->tc_stages; P.ncol = e->tc_ncol; P.ones_col = 8 * e->tc_ncol; P.N = e->tc_N; P.NCP = e->D.NCP;
     P.S = (double *)e->dS.p; P.counts = (int *)e->dCounts.p; P.gsum = (double *)e->dGsum.p;
     P.error_flag = (int *)e->dErr.p;
     P.mlist = (int *)e->dMlist.p; P.mcap = e->mcap; P.mcount = (int *)e->dMcount.p;
     P.mask_zero_lines = e->tc_mask_zero_lines; P.dbg = e->tc_dbg;
     const int grid = (nb + 127) / 128;
     const int NT = e->tc_N / 16;
-    size_t smem = (size_t)gtk::kTcStages * e->tc_N * 128 + 1024 + 256 + 128 * 3 * 4;
+    size_t smem = (size_t)gtk::kTcStages * e->tc_N * 128 + 1024 + 256 + 128 * 4 * 4;
 #define GT_TC(T)                                                                               \
     case T:                                                                                    \
         CK(cudaFuncSetAttribute((const void *)gtk::contract_tc_kernel<T>,                      \

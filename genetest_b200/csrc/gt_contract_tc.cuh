@@ -37,7 +37,8 @@ struct TcParams {
     const uint8_t *Bimg;      // [n_stages][N*128] pre-swizzled digit planes
     const double *scale;      // [ncol] column scale * 2^-54
     int n_stages;
-    int ncol;                 // live E columns (N = 8 * ncol rounded up to 16)
+    int ncol;                 // live E columns (N = 8 * ncol + 1 rounded up to 16)
+    int ones_col;             // D column of the ones plane (design indicator): sum of the dosages
     int N;
     int NCP;                  // S row stride
     double *S;
@@ -126,7 +127,7 @@ contract_tc_kernel(TcParams P) {
              *d_full = bars + 3 * kTcStages;
     uint32_t *tmem_slot = (uint32_t *)(bars + 3 * kTcStages + 1);
     int *fail = (int *)(tmem_slot + 1);
-    int *cnt_s = (int *)(tmem_slot + 2);                 // [128][3] counts of the second half
+    int *cnt_s = (int *)(tmem_slot + 2);                 // [2][128][2]: n_hom, list length of each half row
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
@@ -155,7 +156,7 @@ contract_tc_kernel(TcParams P) {
         const int snp = min(blockIdx.x * 128 + row, P.n_snps - 1);
         const unsigned char *grow = P.geno + (long long)snp * P.pitch + half * 16;
         const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
-        int nhet = 0, nhom = 0, nmis = 0;
+        int nhom = 0;
         // the two threads of a row see disjoint samples: each emits its own
         // in-order list of missing samples, no atomics
         const bool owner = blockIdx.x * 128 + row < P.n_snps;
@@ -203,11 +204,9 @@ contract_tc_kernel(TcParams P) {
                     const uint32_t wm = w | masks[j];
                     const uint32_t lo = wm & 0x55555555u, hi = (wm >> 1) & 0x55555555u;
                     const uint32_t mb = lo & ~hi;
-                    if (!(P.dbg & 16)) {
-                        nmis += __popc(mb);
-                        nhet += __popc(hi & ~lo);
-                        nhom += __popc(~(lo | hi) & 0x55555555u);
-                    }
+                    // the only class count taken here: sum g comes from the
+                    // ones plane of B, the missing count from the list lengths
+                    if (!(P.dbg & 16)) nhom += __popc(~(lo | hi) & 0x55555555u);
                     // flags of two consecutive words share one 32-bit word
                     if (j & 1) mflag[j >> 1] |= mb << 1; else mflag[j >> 1] = mb;
                     // code -> dosage byte: 00 -> 2, 01 -> 0, 10 -> 1, 11 -> 0
@@ -254,22 +253,16 @@ contract_tc_kernel(TcParams P) {
             asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
             mbar_arrive(&a_full[(n_stages - 1) % kTcStages]);
         }
-        // the second half hands its class counts to the first
-        if (half == 1) { cnt_s[row * 3 + 0] = nhet; cnt_s[row * 3 + 1] = nhom; cnt_s[row * 3 + 2] = nmis; }
+        // both halves of a row publish their counts; whoever reads the ones
+        // column in the epilogue writes the totals
+        cnt_s[(half * 128 + row) * 2 + 0] = nhom;
+        cnt_s[(half * 128 + row) * 2 + 1] = mcur;
         asm volatile("bar.sync 1, 256;\n" ::: "memory");
         const int out_snp = blockIdx.x * 128 + row;
         if (out_snp < P.n_snps) {
             P.mcount[(long long)out_snp * 2 + half] = (mcur <= hcap) ? mcur : -1;
-            if (half == 0) {
-                nhet += cnt_s[row * 3 + 0]; nhom += cnt_s[row * 3 + 1]; nmis += cnt_s[row * 3 + 2];
-                P.counts[(long long)out_snp * 4 + 0] = nhet;
-                P.counts[(long long)out_snp * 4 + 1] = nhom;
-                P.counts[(long long)out_snp * 4 + 2] = nmis;
-                P.counts[(long long)out_snp * 4 + 3] = 0;
-                P.gsum[(long long)out_snp * 2 + 0] = (double)(nhet + 2 * nhom);
-                P.gsum[(long long)out_snp * 2 + 1] = (double)(nhet + 4 * nhom);
+            if (half == 0)
                 for (int col = P.ncol; col < P.NCP; ++col) P.S[(long long)out_snp * P.NCP + col] = 0.0;
-            }
         }
         // ===== epilogue: D (int32, TMEM) -> FP64 sums; the halves interleave 32-column groups =====
         if (!mbar_wait(d_full, 0, fail)) *fail = 1;
@@ -295,6 +288,18 @@ contract_tc_kernel(TcParams P) {
                 for (int sl = 6; sl >= 0; --sl) acc = fma(acc, 128.0, (double)(int)d[cc * 8 + sl]);
                 if (col < P.ncol && out_snp < P.n_snps)
                     P.S[(long long)out_snp * P.NCP + col] = acc * P.scale[col];
+                if (c0 + cc * 8 == P.ones_col && out_snp < P.n_snps) {
+                    // exact integer: sum of the dosages over the design rows
+                    const int sum_g = (int)d[cc * 8];
+                    const int n_hom = cnt_s[row * 2] + cnt_s[(128 + row) * 2];
+                    const int n_mis = cnt_s[row * 2 + 1] + cnt_s[(128 + row) * 2 + 1];
+                    P.counts[(long long)out_snp * 4 + 0] = sum_g - 2 * n_hom;
+                    P.counts[(long long)out_snp * 4 + 1] = n_hom;
+                    P.counts[(long long)out_snp * 4 + 2] = n_mis;
+                    P.counts[(long long)out_snp * 4 + 3] = 0;
+                    P.gsum[(long long)out_snp * 2 + 0] = (double)sum_g;
+                    P.gsum[(long long)out_snp * 2 + 1] = (double)(sum_g + 2 * n_hom);
+                }
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
