@@ -175,7 +175,7 @@ def run_reference(args, rank, world):
     w = WORKLOADS[args.model]
     rng = np.random.default_rng(SEED)
     y, C, names = make_design(args.model, w["n"], w["k_cov"], rng)
-    cores = os.cpu_count() or 1
+    cores = len(os.sched_getaffinity(0)) or 1
     per_step = args.ref_snps or (cores * {"linear": 48, "logistic": 12,
                                             "coxph": 1}[args.model])
     import multiprocessing as mp
@@ -222,6 +222,9 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # host buffers next to the GPU (NUMA): matters for the end-to-end leg
+        from genetest_b200 import sharding
+        sharding.bind_to_device_cpus(local_rank)
     w = WORKLOADS[args.model]
     n = args.samples or w["n"]
     snps = args.snps or w["snps"]
@@ -370,7 +373,7 @@ def run_ours(args, rank, world, local_rank):
                    "mean_iterations": mean_iter}
 
     # ---- CPU baseline: restated reference path on the host cores ----
-    cores = os.cpu_count() or 1
+    cores = len(os.sched_getaffinity(0)) or 1
     cpu_snps = args.cpu_snps or (cores * {"linear": 200, "logistic": 50,
                                           "coxph": 2}[args.model])
     cpu_value, cpu_done, cpu_dt = cpu_throughput(args.model, y, C, names,
