@@ -421,3 +421,49 @@ def test_block_sink_writes_the_same_bytes_as_the_row_sink(test, tmp_path):
     assert a == b and len(a.splitlines()) == 1 + int((iout[0] == 0).sum())
     with pytest.raises(KeyError):
         block.column(["SNPs", "no_such_field"])
+
+
+def test_native_formatter_thread_slices_keep_row_order():
+    """More than 4,096 rows are formatted by several host threads, each into
+    its own slice of the output buffer: the text must not depend on that."""
+    from genetest_b200.engine import format_rows
+    rng = np.random.default_rng(3)
+    for n in (4095, 4096, 40001):
+        x = rng.normal(size=n) * 10.0 ** rng.integers(-30, 30, n)
+        k = rng.integers(-5, 1000, n)
+        names = ["rs{}".format(i) * (1 + i % 3) for i in range(n)]
+        tail = ["A" * (i % 5) for i in range(n)]          # empty strings too
+        keep = rng.random(n) < 0.6
+        got = format_rows([names, "c", x, k, tail], keep=keep) \
+            .decode().split("\n")[:-1]
+        want = ["{}\tc\t{!r}\t{}\t{}".format(names[i], float(x[i]), k[i],
+                                            tail[i])
+                for i in range(n) if keep[i]]
+        assert got == want
+        assert format_rows([x, names]).decode().split("\n")[:-1] == \
+            ["{!r}\t{}".format(float(x[i]), names[i]) for i in range(n)]
+
+
+def test_plink_reader_bim_variants(tmp_path):
+    """.bim files separated by tabs or runs of spaces, non-numeric
+    chromosomes, duplicated marker names."""
+    prefix = str(tmp_path / "v")
+    G = np.array([[0, 1, 2, -1, 0], [2, 2, 1, 0, -1], [1, 0, 0, 2, 2]])
+    with PlinkWriter(prefix) as w:
+        for row in G:
+            w.write_genotypes(row)
+        w.write_fam(["a", "b", "c", "d", "e"])
+    with open(prefix + ".bim", "w") as f:
+        f.write("X\trs1\t0\t1000\tA\tG\n")
+        f.write("MT   rs2  0.5   2000 AT  G\n")
+        f.write("23\trs1\t0\t3000\tC\tT\n")
+    with PlinkReader(prefix) as r:
+        assert r.variant_table() == [("rs1", "X", 1000, "A", "G"),
+                                     ("rs2", "MT", 2000, "AT", "G"),
+                                     ("rs1", "23", 3000, "C", "T")]
+        both = r.get_variant_by_name("rs1")
+        assert [v.variant.pos for v in both] == [1000, 3000]
+        assert r.get_variant_by_name("nope") == []
+        np.testing.assert_array_equal(
+            np.nan_to_num(both[1].genotypes, nan=-1), G[2])
+        assert r.packed().shape == (3, 2)
