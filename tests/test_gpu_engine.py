@@ -573,3 +573,53 @@ def test_dosage_rows_need_an_identity_alignment(engine):
                       n_file=50)
     with pytest.raises(EngineError, match="aligned to the design rows"):
         engine.run_dosage_host(np.zeros((2, 50)))
+
+
+def test_linear_config2_full_size_properties(engine):
+    """BASELINE config 2 at its full size: 500,000 markers x 100,000 samples
+    (12.5 GB of 2-bit genotypes in HBM, seven batches of the contraction
+    kernel, the last one partial).  Size-independent properties on every
+    marker, bit-identical results when a sub-range is run on its own (batch
+    offsets), and oracle parity on markers drawn from the batch edges."""
+    import torch
+    rng = np.random.default_rng(20261019)
+    n, n_snps = 100000, 500000
+    C, names = synth_design(rng, n, k_extra=8)
+    y = 0.1 * C[:, 0] + rng.normal(size=n)
+    pos = rng.permutation(n).astype(np.int32)
+    engine.set_design("linear", y, C, sample_pos=pos, n_file=n)
+    dev = engine.synth_packed(n, n_snps, seed=3, missing_rate=0.01)
+    out, iout = engine.run_packed_dev(dev, n_snps)
+    res = engine.fetch(out, iout)
+    assert (res.status == 0).all()
+    assert ((res.maf > 0) & (res.maf <= 0.5)).all()
+    assert (res.nobs <= n).all() and (res.nobs > 0.985 * n).all()
+    k = len(names)
+    coef, se, lo, hi, t, p = res.param(k)
+    assert np.isfinite(np.delete(res.out, 1, axis=0)).all()      # row 1 = aux, NaN when ok
+    assert (se > 0).all() and (lo < coef).all() and (coef < hi).all()
+    np.testing.assert_allclose(t, coef / se, rtol=1e-12)
+    assert ((p > 0) & (p <= 1)).all()
+    # null markers: p-values are uniform (Kolmogorov distance, 500k draws)
+    ps = np.sort(p)
+    assert np.abs(ps - (np.arange(n_snps) + 0.5) / n_snps).max() < 0.01
+    # a sub-range that straddles batch edges, run on its own: same bits
+    batch = 148 * 2 * 128 * 2
+    a, b = 3 * batch - 700, 3 * batch + 900
+    out2, iout2 = engine.run_packed_dev(dev[a:b], b - a)
+    sub = engine.fetch(out2, iout2)
+    np.testing.assert_array_equal(sub.iout, res.iout[:, a:b])
+    np.testing.assert_array_equal(sub.out.view(np.int64),
+                                  np.ascontiguousarray(res.out[:, a:b]).view(np.int64))
+    # oracle parity at the batch edges and at both ends
+    pick = np.array([0, batch - 1, batch, 3 * batch + 1, 6 * batch - 1,
+                     6 * batch, n_snps - 1])
+    packed = dev[torch.from_numpy(pick).cuda()].cpu().numpy()[:, :(n + 3) // 4]
+    G = unpack_rows(packed, n)
+    picked = type(res)(res.out[:, pick], res.iout[:, pick], res.n_params)
+    oracle = run_oracle("linear", y[:, None], C, names, G[:, pos])
+    problems, worst, n_ok = compare("linear", picked, oracle, names, rtol=LIN_TOL)
+    assert not problems, problems[:10]
+    assert n_ok == len(pick)
+    del dev, out, iout
+    torch.cuda.empty_cache()
