@@ -623,3 +623,63 @@ def test_linear_config2_full_size_properties(engine):
     assert n_ok == len(pick)
     del dev, out, iout
     torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("config", ["3-logistic", "4-linear-gxe", "5-coxph"])
+def test_baseline_configs_full_size_properties(engine, config):
+    """BASELINE configs 3-5 at their full marker counts: every marker gets a
+    finite result, a sub-range run on its own reproduces the same bits, and
+    markers from both ends agree with the oracle."""
+    import torch
+    rng = np.random.default_rng(20261020)
+    inter, W, event = None, None, None
+    if config == "3-logistic":
+        model, n, n_snps, miss, tol = "logistic", 50000, 500000, 0.0, LOGIT_TOL
+        C, names = synth_design(rng, n, k_extra=8)
+        y = (rng.random(n) < 1 / (1 + np.exp(0.5 - 0.2 * C[:, 0]))).astype(float)
+        Y = y[:, None]
+    elif config == "4-linear-gxe":
+        model, n, n_snps, miss, tol = "linear", 100000, 200000, 0.01, LIN_TOL
+        C, names = synth_design(rng, n, k_extra=8)
+        y = 0.1 * C[:, 0] + rng.normal(size=n)
+        Y = y[:, None]
+        inter, W = {"I:age": ["age"]}, C[:, [0]]
+    else:
+        model, n, n_snps, miss, tol = "coxph", 20000, 100000, 0.0, LOGIT_TOL
+        C, names = synth_design(rng, n, k_extra=8)
+        C, names = C[:, :-1], names[:-1]
+        y, event = _cox_data(rng, n, C)
+        Y = np.column_stack((y, event))
+    pos = rng.permutation(n).astype(np.int32)
+    engine.set_design(model, y, C, W=W, event=event, sample_pos=pos, n_file=n)
+    dev = engine.synth_packed(n, n_snps, seed=5, missing_rate=miss)
+    out, iout = engine.run_packed_dev(dev, n_snps)
+    res = engine.fetch(out, iout)
+    assert (res.status == 0).all()
+    assert np.isfinite(np.delete(res.out, 1, axis=0)).all()
+    assert ((res.maf > 0) & (res.maf <= 0.5)).all()
+    n_cols = len(names) + 1 + (1 if inter else 0)
+    for j in range(n_cols):
+        coef, se, lo, hi, t, p = res.param(j)
+        assert (se > 0).all() and (lo < coef).all() and (coef < hi).all()
+        assert ((p >= 0) & (p <= 1)).all()
+    p_snp = np.sort(res.param(len(names))[5])
+    assert np.abs(p_snp - (np.arange(n_snps) + 0.5) / n_snps).max() < 0.02
+    a, b = n_snps // 2 - 777, n_snps // 2 + 1234
+    out2, iout2 = engine.run_packed_dev(dev[a:b], b - a)
+    sub = engine.fetch(out2, iout2)
+    np.testing.assert_array_equal(sub.iout, res.iout[:, a:b])
+    np.testing.assert_array_equal(
+        sub.out.view(np.int64),
+        np.ascontiguousarray(res.out[:, a:b]).view(np.int64))
+    pick = np.array([0, n_snps // 2, n_snps - 1])
+    packed = dev[torch.from_numpy(pick).cuda()].cpu().numpy()[:, :(n + 3) // 4]
+    G = unpack_rows(packed, n)
+    picked = type(res)(res.out[:, pick], res.iout[:, pick], res.n_params)
+    oracle = run_oracle(model, Y, C, names, G[:, pos], interaction=inter)
+    problems, worst, n_ok = compare(model, picked, oracle, names,
+                                    inter_keys=list(inter or ()), rtol=tol)
+    assert not problems, problems[:10]
+    assert n_ok == len(pick)
+    del dev, out, iout
+    torch.cuda.empty_cache()
