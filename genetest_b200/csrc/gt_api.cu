@@ -16,6 +16,7 @@
 #include "gt_contract.cuh"
 #include "gt_contract_tc.cuh"
 #include "gt_linear.cuh"
+#include "gt_solve.cuh"
 #include "gt_logistic.cuh"
 #include "gt_cox.cuh"
 #include "gt_format.cuh"
@@ -32,7 +33,6 @@ struct gt_engine {
     DevBuf dBimg, dScale, dErr;                      // tcgen05 contraction (lean designs)
     bool use_tc = true;        // lean linear designs run on the tcgen05 int8 contraction
     int tc_dbg = 0;
-    bool split_corr = false;   // run the missing-sample corrections as their own kernel
     int tc_N = 0, tc_stages = 0, tc_ncol = 0, tc_mask_zero_lines = 0;
     DevBuf dS, dCounts, dGsum, dMlist, dMcount, dCorr; // per-batch workspace
     int mcap = 0;
@@ -393,7 +393,6 @@ int gt_engine_set_option(gt_engine *e, const char *name, int value) {
     if (!e || !name) return fail(GT_E_ARG, "gt_engine_set_option: NULL argument");
     if (std::strcmp(name, "contract_tc") == 0) { e->use_tc = value != 0; return 0; }
     if (std::strcmp(name, "tc_debug") == 0) { e->tc_dbg = value; return 0; }
-    if (std::strcmp(name, "split_corrections") == 0) { e->split_corr = value != 0; return 0; }
     if (std::strcmp(name, "host_chunk") == 0) { e->host_chunk = (int)std::max<int64_t>(0, value); return 0; }
     return fail(GT_E_ARG, "gt_engine_set_option: unknown option '%s'", name);
 }
@@ -717,10 +716,11 @@ static int launch_contract_tc(gt_engine *e, const uint8_t *g, int64_t pitch, int
     return 0;
 }
 
+// K3a (missing-sample corrections, one warp per SNP) then K3b (solve, 16 or
+// 32 lanes per SNP) for one batch.
 template <bool PACKED>
-static int launch_finish(gt_engine *e, int NT2, int grid, int threads, size_t smem,
-                         const void *g, int64_t pitch, int nb, double *out, int32_t *iout,
-                         long long stride, int wpc, bool use_list, int64_t s0) {
+static int launch_finish(gt_engine *e, const void *g, int64_t pitch, int nb, double *out,
+                         int32_t *iout, long long stride, bool use_list, int64_t s0) {
     GtDesignDev D = e->D;
     if (e->sex_maf && !D.raw_mode) {
         D.maf_o = (const double *)e->dMafO.p + s0;
@@ -731,15 +731,19 @@ static int launch_finish(gt_engine *e, int NT2, int grid, int threads, size_t sm
     const double *gs = (const double *)e->dGsum.p;
     const int *ml = use_list ? (const int *)e->dMlist.p : nullptr;
     const int *mc = (const int *)e->dMcount.p;
-    const double *corr = (use_list && e->split_corr) ? (const double *)e->dCorr.p : nullptr;
-    if (use_list && e->split_corr) {
+    double *corr = (double *)e->dCorr.p;
+    const int NT2 = (D.L + 7) / 8;
+    {
+        const gtk::CorrLayout cl = gtk::corr_layout(D.L);
         const int cw = 8;
-        size_t csm = (size_t)cw * 32 * gtk::finish_stage_stride(NT2) * 8;
-        int cgrid = (nb + cw - 1) / cw;
+        const size_t csm = (size_t)cw * cl.perWarp * 8;
+        const int cgrid = (nb + cw - 1) / cw;
 #define GT_COR(N)                                                                          \
     case N:                                                                                \
-        gtk::missing_corr_kernel<N><<<cgrid, cw * 32, csm, e->stream>>>(                   \
-            D, nb, ml, e->mcap, mc, (double *)e->dCorr.p);                                 \
+        CK(cudaFuncSetAttribute((const void *)gtk::missing_corr_kernel<PACKED, N>,         \
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));   \
+        gtk::missing_corr_kernel<PACKED, N><<<cgrid, cw * 32, csm, e->stream>>>(           \
+            D, g, pitch, nb, cnt, ml, e->mcap, mc, corr);                                  \
         break;
         int cslot = time_begin(e, 1);
         switch (NT2) {
@@ -749,23 +753,29 @@ static int launch_finish(gt_engine *e, int NT2, int grid, int threads, size_t sm
         time_end(e, cslot);
 #undef GT_COR
         CK(cudaGetLastError());
-        e->all_launches += 1;
     }
-#define GT_FIN(N)                                                                            \
-    case N:                                                                                  \
-        CK(cudaFuncSetAttribute((const void *)gtk::linear_finish_kernel<PACKED, N>,          \
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
-        gtk::linear_finish_kernel<PACKED, N><<<grid, threads, smem, e->stream>>>(            \
-            D, g, pitch, nb, S, cnt, gs, ml, e->mcap, mc, corr, out, iout, stride, wpc);                            \
-        break;
-    int fslot = time_begin(e, 2);
-    switch (NT2) {
-        GT_FIN(1) GT_FIN(2) GT_FIN(3) GT_FIN(4) GT_FIN(5)
-        default: return fail(GT_E_UNSUPPORTED, "finish kernel: design too wide");
+    {
+        const gtk::SolveLayout sl = gtk::solve_layout(D.L, D.p, D.I);
+        const bool half = D.L <= 16;                     // two SNPs per warp
+        int gpc = half ? 16 : 8;                         // SNPs per 256-thread CTA
+        while (gpc > 1 && (size_t)gpc * sl.perGroup * 8 > 110 * 1024) gpc >>= 1;
+        const int threads = gpc * (half ? 16 : 32);
+        const size_t smem = (size_t)gpc * sl.perGroup * 8;
+        if (smem > 220 * 1024) return fail(GT_E_UNSUPPORTED, "design too wide for the solve kernel (%zu B shared)", smem);
+        const int grid = (nb + gpc - 1) / gpc;
+        int fslot = time_begin(e, 2);
+        if (half) {
+            CK(cudaFuncSetAttribute((const void *)gtk::linear_solve_kernel<16>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            gtk::linear_solve_kernel<16><<<grid, threads, smem, e->stream>>>(D, nb, S, cnt, gs, corr, out, iout, stride);
+        } else {
+            CK(cudaFuncSetAttribute((const void *)gtk::linear_solve_kernel<32>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            gtk::linear_solve_kernel<32><<<grid, threads, smem, e->stream>>>(D, nb, S, cnt, gs, corr, out, iout, stride);
+        }
+        time_end(e, fslot);
+        CK(cudaGetLastError());
     }
-    time_end(e, fslot);
-#undef GT_FIN
-    CK(cudaGetLastError());
     return 0;
 }
 
@@ -788,22 +798,15 @@ static int run_linear(gt_engine *e, const void *geno, int64_t pitch, bool packed
         e->mcap = std::max(64, (D.n_file + 24) / 25) & ~1;
         if ((rc = e->dMlist.reserve((size_t)bmax * e->mcap * 4))) return rc;
         if ((rc = e->dMcount.reserve((size_t)bmax * 2 * 4))) return rc;
-        if ((rc = e->dCorr.reserve((size_t)bmax * D.L * D.L * 8))) return rc;
     }
+    if ((rc = e->dCorr.reserve((size_t)bmax * D.L * D.L * 8))) return rc;
     CK(cudaFuncSetAttribute((const void *)ce.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ce.smem));
-    gtk::FinishLayout lay = gtk::finish_layout(D.L, D.p, D.I);
-    const int NT2 = (D.L + 7) / 8;
-    int wpc = 8;
-    while (wpc > 1 && (size_t)wpc * lay.perWarp * 8 > 100 * 1024) wpc >>= 1;
-    size_t fsmem = (size_t)wpc * lay.perWarp * 8;
-    if (fsmem > 220 * 1024) return fail(GT_E_UNSUPPORTED, "design too wide for the finish kernel (%zu B shared)", fsmem);
 
     for (int s0 = 0; s0 < n_snps; s0 += kBatch) {
         int nb = std::min<int>(kBatch, n_snps - s0);
         double *S = (double *)e->dS.p;
         int *cnt = (int *)e->dCounts.p;
         double *gs = (double *)e->dGsum.p;
-        int grid = (nb + wpc - 1) / wpc;
         if (packed) {
             const uint8_t *g = (const uint8_t *)geno + (int64_t)s0 * pitch;
             int slot = time_begin(e);
@@ -815,17 +818,15 @@ static int run_linear(gt_engine *e, const void *geno, int64_t pitch, bool packed
             }
             time_end(e, slot);
             CK(cudaGetLastError());
-            if ((rc = launch_finish<true>(e, NT2, grid, wpc * 32, fsmem, g, pitch, nb, out + s0,
-                                          iout + s0, ldo, wpc, tc, s0))) return rc;
+            if ((rc = launch_finish<true>(e, g, pitch, nb, out + s0, iout + s0, ldo, tc, s0))) return rc;
         } else {
             const double *g = (const double *)geno + (int64_t)s0 * pitch;
             gtk::contract_dosage_kernel<<<(nb + 7) / 8, 256, 0, e->stream>>>(
                 g, pitch, nb, D.n, D.E, D.NCA, D.NCB, D.NC1, D.NC2, S, cnt, gs);
             CK(cudaGetLastError());
-            if ((rc = launch_finish<false>(e, NT2, grid, wpc * 32, fsmem, g, pitch, nb, out + s0,
-                                           iout + s0, ldo, wpc, false, s0))) return rc;
+            if ((rc = launch_finish<false>(e, g, pitch, nb, out + s0, iout + s0, ldo, false, s0))) return rc;
         }
-        e->all_launches += 2;
+        e->all_launches += 3;
     }
     return 0;
 }
