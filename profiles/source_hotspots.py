@@ -51,3 +51,38 @@ print()
 for (f, l), v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
     print("{:5.1f}% {:5.1f}%  {}:{}  {}".format(
         100 * v[0] / tot_s, 100 * v[1] / tot_i, f, l, v[2]))
+
+
+def sass_hotspots(path, top=30):
+    """Top SASS instructions of `ncu --page source --csv` (SASS view) with
+    their three largest stall reasons."""
+    rows = list(csv.reader(open(path, errors="replace")))
+    out = []
+    hdr = None
+    for r in rows:
+        if "Address" in r and "Source" in r and "# Samples" in r:
+            hdr = r
+            isrc = len(hdr) - 1 - hdr[::-1].index("Source")      # the SASS text
+            isamp = hdr.index("# Samples")
+            iline = hdr.index("Line No") if "Line No" in hdr else None
+            stall = [(i, h) for i, h in enumerate(hdr)
+                     if h.startswith("stall_") and "Not Issued" not in h]
+            continue
+        if hdr is None or len(r) < len(hdr):
+            continue
+        if iline is not None and r[iline].strip():
+            continue                        # a CUDA source line, not an instruction
+        try:
+            s = float(r[isamp] or 0)
+        except ValueError:
+            continue
+        st = sorted(((float(r[i] or 0), h) for i, h in stall), reverse=True)[:3]
+        out.append((s, r[isrc][:64], " ".join("%s=%d" % (h[6:], v) for v, h in st if v > 0)))
+    tot = sum(s for s, _a, _b in out) or 1.0
+    for s, a, b in sorted(out, reverse=True)[:top]:
+        print("%5.2f%%  %-64s %s" % (100 * s / tot, a, b))
+
+
+if __name__ == "__main__" and len(sys.argv) > 3 and sys.argv[3] == "sass":
+    print()
+    sass_hotspots(sys.argv[1], top)
