@@ -683,3 +683,27 @@ def test_baseline_configs_full_size_properties(engine, config):
     assert n_ok == len(pick)
     del dev, out, iout
     torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("k_extra", [14, 19, 27])
+def test_linear_wide_designs(engine, k_extra):
+    """Designs wider than 16 columns: the solve kernel runs one SNP per warp
+    (32 lanes), the corrections use 3-4 MMA tiles per side; with and without
+    the tcgen05 contraction (N = 8 (k + 1) + 1 <= 192 only)."""
+    rng = np.random.default_rng(300 + k_extra)
+    n, n_snps = 3000, 150
+    C, names = synth_design(rng, n, k_extra=k_extra)
+    G = synth_genotypes(rng, n_snps, n, missing=0.02, maf_lo=0.05, maf_hi=0.95)
+    y = _linear_y(rng, C, G)
+    oracle = run_oracle("linear", y[:, None], C, names, G)
+    engine.set_design("linear", y, C)
+    for tc in (1, 0):
+        engine.set_option("contract_tc", tc)
+        res = engine.run_packed_host(pack_rows(G))
+        problems, worst, n_ok = compare("linear", res, oracle, names, rtol=LIN_TOL)
+        assert not problems, (tc, problems[:10])
+        assert n_ok == n_snps
+    engine.set_option("contract_tc", 1)
+    res = engine.run_dosage_host(G)
+    problems, worst, n_ok = compare("linear", res, oracle, names, rtol=LIN_TOL)
+    assert not problems, problems[:10]
