@@ -169,7 +169,7 @@ logistic_irls_kernel(IterDesignDev T, const void *__restrict__ geno, long long p
         auto prefetch = [&](int b) {
             const int i = b * 32 + lane;
             ny = T.y[i];
-            if (PACKED) nbyte = ((const uint8_t *)rowp)[i >> 2];
+            if (PACKED) nbyte = (i < T.n_file) ? ((const uint8_t *)rowp)[i >> 2] : 0u;   // caller's pitch may be tight
             else ngd = (i < T.n_file) ? ((const double *)rowp)[i] : nan("");
             const double *xi = T.X + (long long)i * T.XS;
 #pragma unroll
