@@ -75,8 +75,11 @@ contract_packed_kernel(const uint8_t *__restrict__ geno, long long pitch, int n_
         for (int t = tid; t < Cfg::kTile * 4; t += kThreads) {
             int row = t >> 2, part = t & 3;
             int snp = min(tile0 + row, n_snps - 1);
-            cp_async16(gs + row * kRowPitch + part * 16,
-                       geno + (long long)snp * pitch + (long long)chunk * kRowBytes + part * 16);
+            const long long off = (long long)chunk * kRowBytes + part * 16;
+            if (off + 16 <= pitch)
+                cp_async16(gs + row * kRowPitch + part * 16, geno + (long long)snp * pitch + off);
+            else        // past the row (a pitch that is not a multiple of 64 B): masked samples anyway
+                *(uint4 *)(gs + row * kRowPitch + part * 16) = make_uint4(~0u, ~0u, ~0u, ~0u);
         }
         const double *src = E + (long long)chunk * kChunk * NC;
         double *es = stage_E(s);

@@ -37,7 +37,9 @@ sex_maf_packed_kernel(const uint8_t *__restrict__ geno, long long pitch, int n_s
     if (snp >= n_snps) return;
     const uint4 *row = (const uint4 *)(geno + (long long)snp * pitch);
     const uint4 *om = (const uint4 *)ormask, *mm = (const uint4 *)male, *fm = (const uint4 *)female;
-    const int nvec = (int)(pitch / 16);
+    // the masks are gt_packed_pitch(n_file) bytes long; a caller's pitch may be larger
+    const long long mask_pitch = (((long long)n_file + 3) / 4 + 127) / 128 * 128;
+    const int nvec = (int)((pitch < mask_pitch ? pitch : mask_pitch) / 16);
     int het_m = 0, hom_m = 0, n_m = 0, het_f = 0, hom_f = 0, n_f = 0;
     auto word = [&](unsigned w, unsigned o, unsigned m, unsigned f) {
         const unsigned wm = w | o;
@@ -59,7 +61,6 @@ sex_maf_packed_kernel(const uint8_t *__restrict__ geno, long long pitch, int n_s
         const double sum = dot + (double)het_f + 2.0 * (double)hom_f;
         sex_maf_finish(dot, sum, (double)n_m, (double)n_f, maf_o, flip_o, snp);
     }
-    (void)n_file;
 }
 
 // dosage rows aligned to the design rows; sex[i] = 0 / 1 / NaN per design row

@@ -707,3 +707,43 @@ def test_linear_wide_designs(engine, k_extra):
     res = engine.run_dosage_host(G)
     problems, worst, n_ok = compare("linear", res, oracle, names, rtol=LIN_TOL)
     assert not problems, problems[:10]
+
+
+@pytest.mark.parametrize("model", ["linear", "logistic", "coxph"])
+def test_device_rows_with_a_tight_pitch(engine, model):
+    """gt_run_packed_dev only asks for a pitch that is a multiple of 16 B and
+    covers the row: kernels must not depend on the 128 B padding of
+    gt_packed_pitch (nor read past such rows)."""
+    import torch
+    rng = np.random.default_rng(55)
+    n, n_snps = 1030, 300                       # 258 B per row -> pitch 272
+    C, names = synth_design(rng, n, k_extra=2)
+    G = synth_genotypes(rng, n_snps, n, missing=0.02)
+    event = None
+    if model == "linear":
+        y = _linear_y(rng, C)
+    elif model == "logistic":
+        y = (rng.random(n) < 0.4).astype(float)
+    else:
+        C = C[:, :-1]
+        y, event = _cox_data(rng, n, C)
+    sex = rng.integers(0, 2, n).astype(float)
+    packed = pack_rows(G)
+    tight = np.zeros((n_snps, 272), dtype=np.uint8)
+    tight[:, :packed.shape[1]] = packed
+    dev = torch.from_numpy(tight).cuda()
+    for inter in (False, True):
+        engine.set_design(model, y, C, event=event,
+                          W=C[:, [0]] if inter else None)
+        engine.set_sample_sex(sex)
+        ref = engine.run_packed_host(packed)
+        for tc in (1, 0):
+            engine.set_option("contract_tc", tc)
+            out, iout = engine.run_packed_dev(dev, n_snps, pitch=272)
+            got = engine.fetch(out, iout)
+            np.testing.assert_array_equal(got.iout, ref.iout)
+            np.testing.assert_allclose(np.nan_to_num(got.out),
+                                       np.nan_to_num(ref.out), rtol=1e-9,
+                                       atol=1e-12)
+        engine.set_option("contract_tc", 1)
+    engine.set_sample_sex(None)
