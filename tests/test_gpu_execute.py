@@ -335,3 +335,72 @@ def test_sexual_chromosome_maf_through_execute(tmp_path, reader):
         assert abs(r["coef"] - o["SNPs"]["coef"]) <= 1e-8 * abs(r["coef"])
         flips += o["_flip"]
     assert 3 < flips < n_snps - 3
+
+
+@pytest.mark.parametrize("test", ["linear", "logistic"])
+def test_impute2_dosages_through_execute(tmp_path, test):
+    """Imputed (real-valued) dosages from an IMPUTE2 file: the decoded-block
+    path aligns the samples on the host and runs the FP64 dosage kernels;
+    checked against the oracle's loop body."""
+    import oracle.gwas as og
+    from genetest_b200.genotypes import Impute2Reader
+    from genetest_b200.phenotypes import DataFramePhenotypes
+    rng = np.random.default_rng(23)
+    n_file, n, n_snps = 340, 300, 12
+    ids = ["s{:03d}".format(i) for i in range(n_file)]
+    (tmp_path / "d.sample").write_text(
+        "ID_1 ID_2 missing\n0 0 0\n" +
+        "".join("f{0} {0} 0\n".format(s) for s in ids))
+    lines, D = [], np.zeros((n_snps, n_file))
+    for j in range(n_snps):
+        maf = rng.uniform(0.1, 0.9)
+        g = rng.binomial(2, maf, n_file)
+        probs = np.full((n_file, 3), 0.01)
+        probs[np.arange(n_file), g] = 0.98
+        blur = rng.random(n_file) < 0.15                 # uncertain calls
+        probs[blur] = rng.dirichlet([2, 2, 2], blur.sum())
+        probs = np.round(probs, 4)
+        d = probs[:, 1] + 2 * probs[:, 2]
+        d[probs.max(axis=1) < 0.9] = np.nan
+        D[j] = d
+        lines.append("1 rs{} {} A G ".format(j, 100 + j) +
+                     " ".join("{:.4f}".format(v) for v in probs.ravel()))
+    (tmp_path / "d.impute2").write_text("\n".join(lines) + "\n")
+    keep = rng.permutation(n_file)[:n]
+    age = rng.normal(50, 10, n)
+    if test == "linear":
+        y = 0.02 * age + rng.normal(size=n)
+    else:
+        y = (rng.random(n) < 0.45).astype(float)
+    pheno = pd.DataFrame({"y": y, "age": age}, index=[ids[i] for i in keep])
+    spec._reset()
+    sub = subscribers.ResultsMemory()
+    analysis.execute_formula(
+        DataFramePhenotypes(pheno),
+        Impute2Reader(str(tmp_path / "d.impute2"), str(tmp_path / "d.sample")),
+        "y ~ SNPs + age", test, subscribers=[sub],
+        output_prefix=str(tmp_path / "out"))
+    got = sub._get_gwas_results()
+    order = np.sort(keep)                                # design rows in file order
+    rows = pheno.loc[[ids[i] for i in order]]
+    C = np.column_stack((rows["age"].values, np.ones(n)))
+    tol = 1e-8 if test == "linear" else 1e-6
+    n_ok = 0
+    for j in range(n_snps):
+        st, o = og.gwas_one(test, rows[["y"]].values, C, ["age", "intercept"],
+                            D[j, order], coded="G", reference="A")
+        name = "rs{}".format(j)
+        if st != "ok":
+            assert name not in got
+            continue
+        n_ok += 1
+        r = got[name]
+        assert abs(r["SNPs"]["maf"] - o["SNPs"]["maf"]) < 1e-14
+        assert (r["SNPs"]["minor"], r["SNPs"]["major"]) == \
+            (o["SNPs"]["minor"], o["SNPs"]["major"])
+        for key in ("SNPs", "age", "intercept"):
+            for f in ("coef", "std_err", "p_value"):
+                assert abs(r[key][f] - o[key][f]) <= tol * abs(o[key][f]), \
+                    (name, key, f)
+        assert r["MODEL"]["nobs"] == o["MODEL"]["nobs"]
+    assert n_ok >= n_snps - 2

@@ -467,3 +467,34 @@ def test_plink_reader_bim_variants(tmp_path):
         np.testing.assert_array_equal(
             np.nan_to_num(both[1].genotypes, nan=-1), G[2])
         assert r.packed().shape == (3, 2)
+
+
+def test_impute2_reader(tmp_path):
+    """Dosage of a2, probability threshold, gz files, lookups by name."""
+    import gzip
+    from genetest_b200.genotypes import Impute2Reader, parsers
+    assert parsers["impute2"] is Impute2Reader
+    sample = tmp_path / "x.sample"
+    sample.write_text("ID_1 ID_2 missing\n0 0 0\nf1 s1 0\nf2 s2 0\nf3 s3 0\n")
+    lines = ["1 rs1 100 A G 1 0 0 0 1 0 0 0 1",
+             "1 rs2 200 C T 0.95 0.05 0 0.5 0.4 0.1 0 0 0",
+             "X rs3 300 G GA 0.02 0.08 0.9 0 0.1 0.9 0.05 0.9 0.05"]
+    gen = tmp_path / "x.impute2.gz"
+    with gzip.open(gen, "wt") as f:
+        f.write("\n".join(lines) + "\n")
+    with Impute2Reader(str(gen), str(sample)) as r:
+        assert r.get_samples() == ["s1", "s2", "s3"]
+        assert r.get_number_variants() == 3
+        got = list(r.iter_genotypes())
+        np.testing.assert_array_equal(got[0].genotypes, [0.0, 1.0, 2.0])
+        assert (got[0].coded, got[0].reference) == ("G", "A")
+        np.testing.assert_allclose(got[1].genotypes, [0.05, np.nan, np.nan])
+        np.testing.assert_allclose(got[2].genotypes, [1.88, 1.9, 1.0])
+        assert got[2].variant.chrom == "X" and got[2].variant.pos == 300
+        assert [v.name for v in r.iter_variants()] == ["rs1", "rs2", "rs3"]
+        one = r.get_variant_by_name("rs2")
+        assert len(one) == 1 and one[0].variant.name == "rs2"
+        assert r.get_variant_by_name("nope") == []
+    loose = Impute2Reader(str(gen), str(sample), probability_threshold=0.0)
+    np.testing.assert_allclose(list(loose.iter_genotypes())[1].genotypes,
+                               [0.05, 0.6, np.nan])
