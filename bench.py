@@ -35,13 +35,27 @@ WORKLOADS = {
     "logistic": dict(n=50000, k_cov=10, snps=20000, missing=0.0,
                      name="config3: logistic GWAS 50k samples, 10 covariates "
                           "+ intercept (batched IRLS), SNP shard per step"),
+    "linear_gxe": dict(n=100000, k_cov=10, snps=200000, missing=0.01,
+                       name="config4: linear GWAS with a SNP x age interaction, "
+                            "200k SNPs x 100k samples, 1% missing genotypes"),
     "coxph": dict(n=20000, k_cov=10, snps=20000, missing=0.0,
                   name="config5: Cox PH (Efron) 20k samples, 10 covariates, "
                        "time/event phenotypes, SNP shard per step"),
 }
 
 
+def base_model(model):
+    """Engine / oracle model of a workload (config 4 is the linear model with
+    one SNP x covariate interaction column)."""
+    return "linear" if model == "linear_gxe" else model
+
+
+def interaction_of(model):
+    return {"I:age": ["age"]} if model == "linear_gxe" else None
+
+
 def make_design(model, n, k_cov, rng):
+    model = base_model(model)
     """SURVEY.md 8(d): age ~ N(50,10) standardised, sex ~ Bernoulli(.5),
     remaining covariates iid N(0,1), intercept last."""
     age = rng.normal(50, 10, n)
@@ -132,7 +146,8 @@ def _cpu_init(model, y, C, names):
     except Exception:
         pass
     from oracle import gwas as og
-    _CPU.update(model=model, y=y, C=C, names=names, og=og)
+    _CPU.update(model=base_model(model), y=y, C=C, names=names, og=og,
+                interaction=interaction_of(model))
 
 
 def _cpu_work(args):
@@ -147,7 +162,8 @@ def _cpu_work(args):
         g[rng.random(n) < 0.01] = np.nan
         y = _CPU["y"]
         og.gwas_one(_CPU["model"], y if y.ndim == 2 else y[:, None],
-                    _CPU["C"], _CPU["names"], g)
+                    _CPU["C"], _CPU["names"], g,
+                    interaction=_CPU["interaction"])
         done += 1
     return done
 
@@ -177,7 +193,7 @@ def run_reference(args, rank, world):
     y, C, names = make_design(args.model, w["n"], w["k_cov"], rng)
     cores = len(os.sched_getaffinity(0)) or 1
     per_step = args.ref_snps or (cores * {"linear": 48, "logistic": 12,
-                                            "coxph": 1}[args.model])
+                                            "coxph": 1}[base_model(args.model)])
     import multiprocessing as mp
     pool = mp.get_context("spawn").Pool(cores, _cpu_init,
                                        (args.model, y, C, names))
@@ -235,11 +251,14 @@ def run_ours(args, rank, world, local_rank):
     eng.use_torch_stream()
     # sample ids in a random permutation relative to the phenotype table
     pos = np.random.default_rng(SEED + 1).permutation(n).astype(np.int32)
+    workload = args.model
+    args.model = base_model(workload)
     if args.model == "coxph":
         eng.set_design(args.model, y[:, 0], C, event=y[:, 1], sample_pos=pos,
                        n_file=n)
     else:
-        eng.set_design(args.model, y, C, sample_pos=pos, n_file=n)
+        eng.set_design(args.model, y, C, sample_pos=pos, n_file=n,
+                       W=C[:, [0]] if workload == "linear_gxe" else None)
     if args.model == "linear":
         eng.set_option("contract_tc", int(args.contract == "tc"))
     packed = eng.synth_packed(n, snps, seed=SEED + 1000 * rank,
@@ -338,13 +357,16 @@ def run_ours(args, rank, world, local_rank):
     traffic = None
     try:        # dram bytes per launch of the dominant kernel, from the ncu capture
         prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic = prof.get(args.model, {}).get("dram_bytes_per_launch")
+        traffic = prof.get(workload, {}).get("dram_bytes_per_launch")
     except Exception:
         pass
     fp64_peak = eng.fp64_peak_tflops()
     dmma_peak = eng.dmma_peak_tflops()
     mean_iter = float(iout[3].double().mean().item())
-    if args.model == "linear":
+    if workload == "linear_gxe":
+        # (g, g w) against [q, y, 1, w] and (g^2) against [1, w, w^2]
+        flop_per_snp = 2.0 * n * (2 * (p + 1) + 3)
+    elif args.model == "linear":
         flop_per_snp = 2.0 * n * (p + 2)          # contraction columns (k+2) + g^2
     elif args.model == "logistic":
         # n (p(p+1) + 4p + 40) per IRLS pass, start pass included
@@ -354,7 +376,7 @@ def run_ours(args, rank, world, local_rank):
         # Newton step (risk-set totals, then score + Hessian) + the final one
         flop_per_snp = n * (p * (p + 1) + 4 * p + 30.0) * (2.0 * mean_iter + 2.0)
     fp64_achieved = per_launch_snps * flop_per_snp / (kernel_ms * 1e-3) / 1e12
-    if args.model == "linear" and args.contract == "tc":
+    if workload == "linear" and args.contract == "tc":
         # exact fixed point on the int8 tensor cores: 8 digit planes per column
         ops_per_snp = 2.0 * n * 8 * (p)
         compute = {"pipe": "tcgen05 kind::i8",
@@ -376,7 +398,7 @@ def run_ours(args, rank, world, local_rank):
     cores = len(os.sched_getaffinity(0)) or 1
     cpu_snps = args.cpu_snps or (cores * {"linear": 200, "logistic": 50,
                                           "coxph": 2}[args.model])
-    cpu_value, cpu_done, cpu_dt = cpu_throughput(args.model, y, C, names,
+    cpu_value, cpu_done, cpu_dt = cpu_throughput(workload, y, C, names,
                                                  cpu_snps, cores)
     value = world * snps * args.steps / (ms * 1e-3)
     line = {
@@ -385,7 +407,7 @@ def run_ours(args, rank, world, local_rank):
         "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": w["name"], "model": args.model, "samples": n,
+        "config": {"workload": w["name"], "model": workload, "samples": n,
                    "covariates": w["k_cov"] + 1, "params": p,
                    "snps_per_gpu_per_step": snps,
                    "l2": "inputs ({:.1f} GB packed per GPU) larger than L2"
@@ -397,7 +419,7 @@ def run_ours(args, rank, world, local_rank):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak,
                      "unit": "GB/s", "frac": achieved / hbm_peak,
                      "traffic": traffic, "peak_source": peak_src,
-                     "kernel": ("contract_tc_kernel" if (args.model == "linear" and
+                     "kernel": ("contract_tc_kernel" if (workload == "linear" and
                                                         args.contract == "tc")
                                 else eng.dominant_kernel()),
                      "kernel_ms_per_launch": kernel_ms,
@@ -419,8 +441,9 @@ def run_ours(args, rank, world, local_rank):
         "gpu_launches": int(all_launches),
         "clocks": clocks,
     }
-    if args.model != "linear":
-        # the iterative models are bound by the FP64 (tensor) pipe, not by HBM:
+    if workload != "linear":
+        # the iterative models (and the FP64 contraction of interaction
+        # designs) are bound by the FP64 (tensor) pipe, not by HBM:
         # report that roofline, keep the HBM figures beside it
         r = line["roofline"]
         r.update({"bound": "tensor", "unit": "TFLOP/s",
