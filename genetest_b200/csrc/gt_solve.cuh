@@ -71,10 +71,10 @@ __device__ __forceinline__ bool gt_group_cholesky(double *A, int ld, int p, int 
         for (int i = j + 1 + gl; i < p; i += GW) A[i * ld + j] *= inv;
         if (gl == 0) A[j * ld + j] = s;
         __syncwarp(mask);
-        int m = p - j - 1;
-        for (int t = gl; t < m * m; t += GW) {
-            int i = j + 1 + t / m, c = j + 1 + t % m;
-            if (c <= i) A[i * ld + c] -= A[i * ld + j] * A[c * ld + j];
+        // trailing update, one row per lane (no index division)
+        for (int i = j + 1 + gl; i < p; i += GW) {
+            const double aij = A[i * ld + j];
+            for (int c = j + 1; c <= i; ++c) A[i * ld + c] = fma(-aij, A[c * ld + j], A[i * ld + c]);
         }
         __syncwarp(mask);
     }
@@ -241,15 +241,15 @@ linear_solve_kernel(GtDesignDev D, int n_snps, const double *__restrict__ S,
     }
 
     // normal equations in the [Q | g | g w] basis
-    for (int t = gl; t < p * p; t += GW) {
-        int i = t / p, j = t % p;
-        double v;
-        if (i < k && j < k) v = S0[i * L + j];
-        else if (i < k) v = S1[(j - k) * L + i];
-        else if (j < k) v = S1[(i - k) * L + j];
-        else v = S2[(i - k) * (I + 1) + (j - k)];
-        Mo[t] = v; Mc[t] = v;
-    }
+    for (int j = gl; j < p; j += GW)                     // one column per lane
+        for (int i = 0; i < p; ++i) {
+            double v;
+            if (i < k && j < k) v = S0[i * L + j];
+            else if (i < k) v = S1[(j - k) * L + i];
+            else if (j < k) v = S1[(i - k) * L + j];
+            else v = S2[(i - k) * (I + 1) + (j - k)];
+            Mo[i * p + j] = v; Mc[i * p + j] = v;
+        }
     for (int i = gl; i < p; i += GW) rhs[i] = (i < k) ? S0[i * L + iy] : S1[(i - k) * L + iy];
     const double yy = S0[iy * L + iy], sy = S0[iy * L + i1];
     __syncwarp(gmask);
@@ -262,7 +262,7 @@ linear_solve_kernel(GtDesignDev D, int n_snps, const double *__restrict__ S,
         // column): with u = Z rhs, bq = Z' u and ssr = yy - u'u; back in the
         // reference's parameterisation beta = T bq and var_i = |column i of
         // Z T'|^2 with T = blockdiag(R^-1, I).
-        double *Z = Mi, *invd = tmpv, *u = gdiag, *W2 = Mc;
+        double *Z = Mi, *invd = tmpv, *u = gdiag;
         for (int i = gl; i < p; i += GW) invd[i] = 1.0 / Mc[i * p + i];
         for (int t = gl; t < p * p; t += GW) Z[t] = 0.0;
         __syncwarp(gmask);
@@ -287,24 +287,22 @@ linear_solve_kernel(GtDesignDev D, int n_snps, const double *__restrict__ S,
             for (int r = i; r < p; ++r) s = fma(Z[r * p + i], u[r], s);
             bq[i] = s;
         }
-        // squares of W = Z T' (the Cholesky factor is not needed any more)
-        for (int t = gl; t < p * p; t += GW) {
-            const int r = t / p, i = t - r * p;
-            double w;
-            if (i < k) {
-                w = 0.0;
-                const int hi = r < k - 1 ? r : k - 1;
-                for (int a = i; a <= hi; ++a) w = fma(Z[r * p + a], D.Rinv[i * k + a], w);
-            } else {
-                w = Z[r * p + i];
-            }
-            W2[t] = w * w;
-        }
         __syncwarp(gmask);
+        // var_i = sum over r of W[r][i]^2, W = Z T': one column per lane
         double tv = 0.0, tg = 0.0;
         for (int i = gl; i < p; i += GW) {
             double v = 0.0, b;
-            for (int r = 0; r < p; ++r) v += W2[r * p + i];
+            for (int r = i; r < p; ++r) {
+                double w;
+                if (i < k) {
+                    w = 0.0;
+                    const int hi = r < k - 1 ? r : k - 1;
+                    for (int a = i; a <= hi; ++a) w = fma(Z[r * p + a], D.Rinv[i * k + a], w);
+                } else {
+                    w = Z[r * p + i];
+                }
+                v = fma(w, w, v);
+            }
             if (i < k) {
                 b = 0.0;
                 for (int a = i; a < k; ++a) b = fma(D.Rinv[i * k + a], bq[a], b);
