@@ -265,21 +265,42 @@ def run_ours(args, rank, world, local_rank):
                               missing_rate=w["missing"])
     pitch = packed.stride(0)
     out, iout = eng.alloc_results(snps)
-    gathered = None
-    if world > 1 and rank == 0:
-        gathered = [torch.empty_like(out) for _ in range(world)]
-        gathered_i = [torch.empty_like(iout) for _ in range(world)]
+    # Result blocks are double-buffered: the gather of step i (the only
+    # collective: fixed-size blocks -> rank 0, on NCCL's stream) overlaps the
+    # kernels of step i + 1, as it does when an analysis streams its batches.
+    gather_on = world > 1 and not os.environ.get("GT_BENCH_NO_GATHER")
+    bufs = [(out, iout)]
+    if gather_on:
+        bufs.append(eng.alloc_results(snps))
+    gathered = [None, None]
+    if gather_on and rank == 0:
+        gathered = [([torch.empty_like(o) for _ in range(world)],
+                     [torch.empty_like(io) for _ in range(world)])
+                    for o, io in bufs]
+    pending = [None, None]
     torch.cuda.synchronize()
+    step_no = [0]
+
+    def drain(slot):
+        if pending[slot] is not None:
+            for work in pending[slot]:
+                work.wait()                 # the compute stream waits, not the host
+            pending[slot] = None
 
     def step():
-        eng.run_packed_dev(packed, snps, pitch, out, iout)
-        if world > 1 and not os.environ.get("GT_BENCH_NO_GATHER"):
-            # the only collective: fixed-size result blocks -> rank 0
-            dist.gather(out, gathered if rank == 0 else None, dst=0)
-            dist.gather(iout, gathered_i if rank == 0 else None, dst=0)
+        slot = step_no[0] % len(bufs)
+        step_no[0] += 1
+        o, io = bufs[slot]
+        drain(slot)                         # this block's previous gather is done
+        eng.run_packed_dev(packed, snps, pitch, o, io)
+        if gather_on:
+            g = gathered[slot] if rank == 0 else (None, None)
+            pending[slot] = (dist.gather(o, g[0], dst=0, async_op=True),
+                             dist.gather(io, g[1], dst=0, async_op=True))
 
     for _ in range(args.warmup):
         step()
+    drain(0), drain(1)
     torch.cuda.synchronize()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
@@ -294,6 +315,7 @@ def run_ours(args, rank, world, local_rank):
     ev0.record()
     for _ in range(args.steps):
         step()
+    drain(0), drain(1)                      # every gather inside the timed region
     ev1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -312,6 +334,7 @@ def run_ours(args, rank, world, local_rank):
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    out, iout = bufs[(step_no[0] - 1) % len(bufs)]
     status = iout[0]
     n_tested = int(status.numel())
     n_ok = int((status == 0).sum().item())
