@@ -212,55 +212,4 @@ __device__ __forceinline__ void gt_warp_chol_inverse(const double *Lc, int ld, i
     __syncwarp();
 }
 
-// Cyclic Jacobi eigenvalues of the symmetric p x p matrix G (shared memory,
-// destroyed).  Returns (max, min) of the diagonal after convergence.  A zero
-// row/column stays exactly zero (monomorphic marker -> eigenvalue 0 -> inf).
-__device__ __forceinline__ void gt_warp_jacobi_extremes(double *G, int ld, int p, int lane,
-                                                        double *emax, double *emin) {
-    for (int sweep = 0; sweep < 40; ++sweep) {
-        double off = 0.0, dg = 0.0;
-        for (int t = lane; t < p * p; t += 32) {
-            int i = t / p, j = t % p;
-            double v = G[i * ld + j];
-            if (i == j) dg += v * v; else off += v * v;
-        }
-        off = gt_warp_sum(off);
-        dg = gt_warp_sum(dg);
-        if (off <= 1e-32 * dg || off == 0.0) break;
-        for (int r = 0; r < p - 1; ++r) {
-            for (int c = r + 1; c < p; ++c) {
-                double apq = G[r * ld + c];
-                if (apq == 0.0) continue;
-                double app = G[r * ld + r], aqq = G[c * ld + c];
-                double tau = (aqq - app) / (2.0 * apq);
-                double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-                double cs = 1.0 / sqrt(1.0 + t * t), sn = t * cs;
-                __syncwarp();
-                for (int i = lane; i < p; i += 32) {
-                    if (i != r && i != c) {
-                        double gir = G[i * ld + r], gic = G[i * ld + c];
-                        double nr = cs * gir - sn * gic, nc = sn * gir + cs * gic;
-                        G[i * ld + r] = nr; G[r * ld + i] = nr;
-                        G[i * ld + c] = nc; G[c * ld + i] = nc;
-                    }
-                }
-                if (lane == 0) {
-                    G[r * ld + r] = app - t * apq;
-                    G[c * ld + c] = aqq + t * apq;
-                    G[r * ld + c] = 0.0;
-                    G[c * ld + r] = 0.0;
-                }
-                __syncwarp();
-            }
-        }
-    }
-    double mx = -INFINITY, mn = INFINITY;
-    for (int i = lane; i < p; i += 32) {
-        double v = G[i * ld + i];
-        mx = fmax(mx, v); mn = fmin(mn, v);
-    }
-    mx = gt_warp_max(mx);
-    mn = -gt_warp_max(-mn);
-    *emax = mx; *emin = mn;
-}
 #endif  // __CUDACC__

@@ -108,9 +108,11 @@ int gt_engine_destroy(gt_engine *e);
  * use cudaStreamLegacy / cudaStreamPerThread for a default stream. */
 int gt_engine_set_stream(gt_engine *e, void *cuda_stream);
 int gt_engine_synchronize(gt_engine *e);
-/* Engine options.  "contract_tc" = 1: run the linear contraction of designs
- * without interaction on the tcgen05 int8 tensor-core kernel (exact fixed
- * point) instead of the FP64 kernel. */
+/* Engine options.  "contract_tc" = 1 (default): run the linear contraction of
+ * designs without interaction on the tcgen05 int8 tensor-core kernel (exact
+ * fixed point) instead of the FP64 kernel.  "host_chunk" = n: markers per
+ * stage of the copy-in / compute / copy-back pipeline of the *_host entry
+ * points (0 = automatic).  "tc_debug": tuning probes of the tcgen05 kernel. */
 int gt_engine_set_option(gt_engine *e, const char *name, int value);
 
 /* Replaces the per-worker setup of _gwas_worker (analysis.py:68-106) and the
