@@ -312,6 +312,11 @@ int64_t gt_format_rows(int32_t n_rows, int32_t n_cols, const int32_t *col_type,
     }
     return (int64_t)(p - out);
 }
+// host evaluations of the formulas the kernels use for p-values and
+// confidence intervals (GT_HD functions of gt_common.cuh): no GPU needed
+double gt_host_t_sf2(double t, double df) { return gt_t_sf2(t, df); }
+double gt_host_t_ppf975(double df) { return gt_t_ppf975(df); }
+double gt_host_norm_sf2(double z) { return gt_norm_sf2(z); }
 const char *gt_last_error(void) { return g_err.c_str(); }
 
 int64_t gt_packed_pitch(int32_t n_file) {

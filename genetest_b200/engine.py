@@ -36,6 +36,7 @@ ABI_SYMBOLS = [
     "gt_engine_enable_timing", "gt_engine_kernel_time",
     "gt_engine_dominant_kernel", "gt_engine_kernel_breakdown", "gt_measure_fp64_peak",
     "gt_measure_dmma_peak", "gt_debug_read_pattern", "gt_format_rows",
+    "gt_host_t_sf2", "gt_host_t_ppf975", "gt_host_norm_sf2",
 ]
 
 
@@ -87,6 +88,11 @@ def load_library():
     lib.gt_engine_set_option.argtypes = [vp, c.c_char_p, c.c_int]
     lib.gt_engine_set_design.argtypes = [vp, c.POINTER(_DesignDesc)]
     lib.gt_engine_set_sample_sex.argtypes = [vp, vp]
+    for name in ("gt_host_t_sf2", "gt_host_t_ppf975", "gt_host_norm_sf2"):
+        getattr(lib, name).restype = c.c_double
+    lib.gt_host_t_sf2.argtypes = [c.c_double, c.c_double]
+    lib.gt_host_t_ppf975.argtypes = [c.c_double]
+    lib.gt_host_norm_sf2.argtypes = [c.c_double]
     lib.gt_engine_num_params.argtypes = [vp]
     lib.gt_engine_num_fields.argtypes = [vp]
     lib.gt_packed_pitch.argtypes = [i32]

@@ -175,6 +175,14 @@ int gt_debug_read_pattern(gt_engine *e, const uint8_t *packed_dev, int64_t pitch
                           int32_t n_rows, int tpr, int vec, int ctas_per_sm,
                           double *gbs);
 
+/* The p-value / quantile formulas of the kernels, evaluated on the host (the
+ * same source compiled for the CPU): 2 P(T_df > |t|), t.ppf(0.975, df),
+ * 2 Phi(-|z|) -- scipy.stats.t.sf / t.ppf / norm.sf of linear.py:64-89,
+ * logistic.py:49-72, survival.py:100-120.  For tests; no device needed. */
+double gt_host_t_sf2(double t, double df);
+double gt_host_t_ppf975(double df);
+double gt_host_norm_sf2(double z);
+
 /* Streaming result sink (host only): format `n_rows` result rows as delimited
  * text, the way GWASWriter / RowWriter.handle() does one dict at a time
  * (genetest/subscribers.py:192-205).  Column types: 0 = NUL-separated strings

@@ -498,3 +498,40 @@ def test_impute2_reader(tmp_path):
     loose = Impute2Reader(str(gen), str(sample), probability_threshold=0.0)
     np.testing.assert_allclose(list(loose.iter_genotypes())[1].genotypes,
                                [0.05, 0.6, np.nan])
+
+
+def test_p_value_formulas_match_scipy():
+    """The Student-t / normal tails and the t quantile the kernels use
+    (gt_common.cuh, compiled for the host behind gt_host_*): relative error
+    against scipy over the ranges a GWAS meets, tiny p-values included."""
+    import scipy.stats as st
+    from genetest_b200.engine import load_library
+    lib = load_library()
+    rng = np.random.default_rng(0)
+    dfs = [1, 2, 3, 5, 8, 10, 11, 20, 31, 57, 58, 100, 500, 1000, 5000, 19988,
+           49988, 99988, 500000, 1e6]
+    ts = np.concatenate([
+        [0, 1e-12, 1e-6, 1e-3, 0.01, 0.1, 0.5, 1, 1.5, 2, 2.5, 2.9, 3, 3.1, 4,
+         5, 7, 10, 15, 20, 30, 38, 50, 100, 300, 1000],
+        rng.uniform(0, 6, 200), 10 ** rng.uniform(-3, 2.5, 200)])
+    worst = 0.0
+    for df in dfs:
+        want = 2 * st.t.sf(ts, df)
+        for t, w in zip(ts, want):
+            got = lib.gt_host_t_sf2(float(t), float(df))
+            assert lib.gt_host_t_sf2(float(-t), float(df)) == got
+            if w < 1e-300:
+                assert got < 1e-299
+                continue
+            worst = max(worst, abs(got - w) / w)
+    assert worst < 1e-9, worst
+    assert np.isnan(lib.gt_host_t_sf2(float("nan"), 10.0))
+    assert lib.gt_host_t_sf2(float("inf"), 10.0) == 0.0
+    for df in dfs + [4, 6, 7, 9, 15, 40]:
+        w = st.t.ppf(0.975, df)
+        assert abs(lib.gt_host_t_ppf975(float(df)) - w) <= 1e-12 * w
+    for z in np.concatenate([[0, 1e-9, 0.5, 1, 2, 5, 10, 20, 37],
+                             rng.uniform(0, 37, 200)]):
+        w = 2 * st.norm.sf(z)
+        assert abs(lib.gt_host_norm_sf2(float(z)) - w) <= 1e-12 * w
+        assert lib.gt_host_norm_sf2(float(-z)) == lib.gt_host_norm_sf2(float(z))
