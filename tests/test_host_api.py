@@ -535,3 +535,31 @@ def test_p_value_formulas_match_scipy():
         w = 2 * st.norm.sf(z)
         assert abs(lib.gt_host_norm_sf2(float(z)) - w) <= 1e-12 * w
         assert lib.gt_host_norm_sf2(float(-z)) == lib.gt_host_norm_sf2(float(z))
+
+
+def test_properties_pack_roundtrip_and_float_repr():
+    """Property tests (hypothesis): 2-bit packing round-trips for any shape,
+    and the native formatter reproduces ``repr(float)`` for any double."""
+    from hypothesis import given, settings, strategies as hs
+    from genetest_b200.engine import format_rows
+
+    @settings(max_examples=60, deadline=None)
+    @given(hs.integers(1, 9), hs.integers(1, 70), hs.integers(0, 2 ** 32 - 1))
+    def roundtrip(m, n, seed):
+        rng = np.random.default_rng(seed)
+        G = rng.integers(-1, 3, (m, n)).astype(float)
+        G[G < 0] = np.nan
+        packed = pack_rows(G)
+        assert packed.shape == (m, (n + 3) // 4) and packed.dtype == np.uint8
+        np.testing.assert_array_equal(unpack_rows(packed, n), G)
+
+    @settings(max_examples=40, deadline=None)
+    @given(hs.lists(hs.floats(allow_nan=True, allow_infinity=True, width=64),
+                    min_size=1, max_size=200))
+    def float_repr(values):
+        x = np.array(values, dtype=np.float64)
+        got = format_rows([x]).decode().split("\n")[:-1]
+        assert got == [repr(float(v)) for v in x]
+
+    roundtrip()
+    float_repr()
