@@ -563,3 +563,112 @@ def test_properties_pack_roundtrip_and_float_repr():
 
     roundtrip()
     float_repr()
+
+
+def _write_bgen(path, samples, variants, bits=8, compress=True, layout=2,
+                embed_samples=True):
+    """Minimal BGEN writer for the tests (unphased diploid bi-allelic).
+    ``variants``: [(rsid, chrom, pos, a1, a2, probs[n, 3], missing[n])]."""
+    import struct
+    import zlib
+
+    def lstr(s, fmt):
+        b = s.encode()
+        return struct.pack(fmt, len(b)) + b
+
+    n = len(samples)
+    flags = (1 if compress else 0) | (layout << 2) | ((1 << 31) if embed_samples else 0)
+    header = struct.pack("<III", 20, len(variants), n) + b"bgen" + struct.pack("<I", flags)
+    sample_block = b""
+    if embed_samples:
+        ids = b"".join(lstr(s, "<H") for s in samples)
+        sample_block = struct.pack("<II", 8 + len(ids), n) + ids
+    body = b""
+    for rsid, chrom, pos, a1, a2, probs, missing in variants:
+        v = b""
+        if layout == 1:
+            v += struct.pack("<I", n)
+        v += lstr("id_" + rsid, "<H") + lstr(rsid, "<H") + lstr(chrom, "<H")
+        v += struct.pack("<I", pos)
+        if layout == 2:
+            v += struct.pack("<H", 2)
+        v += lstr(a1, "<I") + lstr(a2, "<I")
+        if layout == 1:
+            q = np.where(missing[:, None], 0.0, probs)
+            data = np.round(q * 32768).astype("<u2").tobytes()
+            v += (struct.pack("<I", len(zlib.compress(data))) + zlib.compress(data)
+                  if compress else data)
+        else:
+            scale = 2 ** bits - 1
+            ints = np.round(probs[:, :2] * scale).astype(np.uint64)
+            if bits in (8, 16, 32):
+                payload = ints.astype({8: "<u1", 16: "<u2", 32: "<u4"}[bits]).tobytes()
+            else:
+                flat = ((ints.reshape(-1, 1) >> np.arange(bits, dtype=np.uint64)) & 1) \
+                    .astype(np.uint8).ravel()
+                payload = np.packbits(flat, bitorder="little").tobytes()
+            ploidy = (np.full(n, 2, dtype=np.uint8) | (missing.astype(np.uint8) << 7))
+            data = struct.pack("<IHBB", n, 2, 2, 2) + ploidy.tobytes() + \
+                struct.pack("<BB", 0, bits) + payload
+            if compress:
+                z = zlib.compress(data)
+                v += struct.pack("<II", len(z) + 4, len(data)) + z
+            else:
+                v += struct.pack("<I", len(data)) + data
+        body += v
+    with open(path, "wb") as f:
+        f.write(struct.pack("<I", len(header) + len(sample_block)))
+        f.write(header + sample_block + body)
+
+
+@pytest.mark.parametrize("layout, bits, compress", [
+    (2, 8, True), (2, 16, True), (2, 8, False), (2, 11, True), (1, 16, True),
+    (1, 16, False)])
+def test_bgen_reader(tmp_path, layout, bits, compress):
+    from genetest_b200.genotypes import BgenReader, parsers
+    assert parsers["bgen"] is BgenReader
+    rng = np.random.default_rng(layout * 100 + bits)
+    n, m = 37, 5
+    samples = ["s{}".format(i) for i in range(n)]
+    variants = []
+    for j in range(m):
+        g = rng.integers(0, 3, n)
+        probs = np.full((n, 3), 0.02)
+        probs[np.arange(n), g] = 0.96
+        blur = rng.random(n) < 0.2
+        probs[blur] = rng.dirichlet([1, 1, 1], int(blur.sum()))
+        missing = rng.random(n) < 0.1
+        variants.append(("rs{}".format(j), str(1 + j % 2), 1000 + j, "A", "GT",
+                         probs, missing))
+    path = str(tmp_path / "t.bgen")
+    _write_bgen(path, samples, variants, bits=bits, compress=compress,
+                layout=layout, embed_samples=(layout == 2))
+    sample_file = None
+    if layout == 1:
+        sample_file = str(tmp_path / "t.sample")
+        with open(sample_file, "w") as f:
+            f.write("ID_1 ID_2 missing\n0 0 0\n")
+            f.writelines("f {} 0\n".format(s) for s in samples)
+    scale = 32768.0 if layout == 1 else float(2 ** bits - 1)
+    with BgenReader(path, sample_file) as r:
+        assert r.get_samples() == samples and r.get_number_variants() == m
+        got = list(r.iter_genotypes())
+        assert [g.variant.name for g in got] == [v[0] for v in variants]
+        assert [v.name for v in r.iter_variants()] == [v[0] for v in variants]
+        for g, (rsid, chrom, pos, a1, a2, probs, missing) in zip(got, variants):
+            assert (g.variant.chrom, g.variant.pos) == (chrom, pos)
+            assert (g.reference, g.coded) == ("A", "GT")
+            if layout == 1:
+                q = np.round(probs * scale) / scale
+            else:
+                q2 = np.round(probs[:, :2] * scale) / scale
+                q = np.column_stack((q2, 1 - q2.sum(axis=1)))
+            want = q[:, 1] + 2 * q[:, 2]
+            want[missing | (q.max(axis=1) < 0.9)] = np.nan
+            np.testing.assert_allclose(g.genotypes, want, rtol=0, atol=1e-12)
+        one = r.get_variant_by_name("rs3")
+        assert len(one) == 1 and one[0].variant.pos == 1003
+        np.testing.assert_array_equal(np.isnan(one[0].genotypes),
+                                      np.isnan(got[3].genotypes))
+        # iteration restarts cleanly after a lookup
+        assert len(list(r.iter_genotypes())) == m
