@@ -916,7 +916,9 @@ static int run_host(gt_engine *e, const void *src, int64_t src_pitch_bytes, int6
     // SM busy) and at most 512 MiB of genotypes per slot
     int64_t chunk = e->host_chunk > 0 ? e->host_chunk : (((int64_t)n_snps + 7) / 8 + 1023) / 1024 * 1024;
     if (e->host_chunk <= 0) {
-        chunk = std::max<int64_t>(chunk, 8192);
+        // the iterative models are compute-bound by orders of magnitude and
+        // pay a partial last wave per chunk: keep their chunks large
+        chunk = std::max<int64_t>(chunk, e->model == GT_MODEL_LINEAR ? 8192 : 65536);
         chunk = std::min<int64_t>(chunk, std::max<int64_t>(1024, ((int64_t)512 << 20) / dev_pitch_bytes / 1024 * 1024));
     }
     chunk = std::min<int64_t>(chunk, n_snps);
