@@ -45,6 +45,7 @@ struct gt_engine {
     std::vector<int> pos;
     bool identity_pos = true, sex_maf = false;
     DevBuf dSexM, dSexF, dSexRow, dMafO, dFlipO;
+    DevBuf dCounter;           // work counter of the persistent iterative kernels
     // timing
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
@@ -350,7 +351,7 @@ int gt_engine_destroy(gt_engine *e) {
     for (auto &ev : e->events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     DevBuf *bufs[] = {&e->dE, &e->dMask, &e->dFF0, &e->dR, &e->dRinv, &e->dTq, &e->dIter, &e->dBimg, &e->dScale, &e->dErr,
                       &e->dS, &e->dCounts, &e->dGsum, &e->dMlist, &e->dMcount, &e->dCorr, &e->dGeno, &e->dOut, &e->dIout,
-                      &e->dSexM, &e->dSexF, &e->dSexRow, &e->dMafO, &e->dFlipO};
+                      &e->dSexM, &e->dSexF, &e->dSexRow, &e->dMafO, &e->dFlipO, &e->dCounter};
     for (DevBuf *b : bufs) b->release();
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     if (e->s_in) cudaStreamDestroy(e->s_in);
@@ -871,7 +872,12 @@ static int run_any(gt_engine *e, const void *geno, int64_t pitch, bool packed, i
         T.flip_o = (const int *)e->dFlipO.p;
     }
     if (e->model == GT_MODEL_LINEAR) return run_linear(e, geno, pitch, packed, n_snps, out, iout, ldo);
-    return gtk::iter_run(T, e->model, geno, pitch, packed, n_snps, out, iout, ldo, e->stream, e->timing,
+    {
+        int rc = e->dCounter.reserve(16);
+        if (rc) return rc;
+    }
+    return gtk::iter_run(T, e->model, geno, pitch, packed, n_snps, out, iout, ldo, e->stream,
+                         (int *)e->dCounter.p, e->timing,
                          [&]() { return time_begin(e); }, [&](int s) { time_end(e, s); },
                          e->all_launches, g_err);
 }

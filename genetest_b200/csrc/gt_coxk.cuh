@@ -58,16 +58,15 @@ struct CoxCfg {
     __host__ __device__ static constexpr int perWarp(int p) { return 2 * p * XT + fixed; }
 };
 
+// one marker, by one warp (sm: the CTA's dynamic shared memory)
 template <bool PACKED, int NT>
-__global__ void __launch_bounds__(256)
-cox_newton_kernel(IterDesignDev T, const void *__restrict__ geno, long long pitch, int n_snps,
-                  double *__restrict__ out, int *__restrict__ iout, long long ostride) {
+__device__ __forceinline__ void
+cox_newton_one(const IterDesignDev &T, const void *__restrict__ geno, long long pitch, int n_snps,
+               double *__restrict__ out, int *__restrict__ iout, long long ostride,
+               const int snp, double *sm) {
     using Cfg = CoxCfg<NT>;
     constexpr int XT = Cfg::XT, PH = Cfg::PH;
-    extern __shared__ __align__(16) double sm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int snp = blockIdx.x * (blockDim.x >> 5) + warp;
-    if (snp >= n_snps) return;
     const int k = T.k, I = T.I, p = T.p;
     const int nf = GT_F_PARAM0 + 6 * p;
 
@@ -523,6 +522,26 @@ cox_newton_kernel(IterDesignDev T, const void *__restrict__ geno, long long pitc
         iout[(long long)GT_I_NOBS * ostride + snp] = nj;
         iout[(long long)GT_I_FLIP * ostride + snp] = flip;
         iout[(long long)GT_I_NITER * ostride + snp] = niter;
+    }
+}
+
+// Warps take markers from a shared counter until none is left: the iteration
+// count varies from marker to marker, and a static assignment would leave
+// the last wave of CTAs partly empty.
+template <bool PACKED, int NT>
+__global__ void __launch_bounds__(256)
+cox_newton_kernel(IterDesignDev T, const void *__restrict__ geno, long long pitch, int n_snps,
+                  double *__restrict__ out, int *__restrict__ iout, long long ostride,
+                  int *__restrict__ next_marker) {
+    extern __shared__ __align__(16) double sm[];
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        int snp = 0;
+        if (lane == 0) snp = atomicAdd(next_marker, 1);
+        snp = __shfl_sync(GT_FULL, snp, 0);
+        if (snp >= n_snps) return;
+        cox_newton_one<PACKED, NT>(T, geno, pitch, n_snps, out, iout, ostride, snp, sm);
+        __syncwarp();
     }
 }
 
