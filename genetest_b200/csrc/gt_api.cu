@@ -15,6 +15,7 @@
 #include "gt_host.cuh"
 #include "gt_contract.cuh"
 #include "gt_contract_tc.cuh"
+#include "gt_contract_tc2.cuh"
 #include "gt_linear.cuh"
 #include "gt_solve.cuh"
 #include "gt_logistic.cuh"
@@ -33,9 +34,9 @@ struct gt_engine {
     DevBuf dBimg, dScale, dErr;                      // tcgen05 contraction (lean designs)
     bool use_tc = true;        // lean linear designs run on the tcgen05 int8 contraction
     int tc_dbg = 0;
-    int tc_N = 0, tc_stages = 0, tc_ncol = 0, tc_mask_zero_lines = 0;
+    int tc_N = 0;              // 0: the design does not run on the tcgen05 kernel
+    gtk::Tc2Params tc{};       // constant part of the kernel parameters
     DevBuf dS, dCounts, dGsum, dMlist, dMcount, dCorr; // per-batch workspace
-    int mcap = 0;
     DevBuf dGeno, dOut, dIout;                 // staging of the *_host entry points
     cudaStream_t s_in = nullptr, s_out = nullptr;     // copy streams of the *_host pipeline
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_start = nullptr;
@@ -578,61 +579,94 @@ int gt_engine_set_design(gt_engine *e, const gt_design_desc *d) {
         if ((rc = upload(e->dE, E.data(), E.size() * 8, st))) return rc;
         // ---- digit planes for the tcgen05 int8 contraction (lean designs) ----
         e->tc_N = 0;
-        std::vector<uint8_t> Bimg;
-        std::vector<double> scale;
-        if (lean && 8 * NC1 + 1 <= 192) {
+        if (lean) {
             const int ncol = NC1;
-            // 8 digit planes per column + one plane of ones over the design
-            // rows (its D column is the exact sum of the dosages)
-            const int N = (8 * ncol + 1 + 15) / 16 * 16;
             std::vector<char> is_design(n_pad, 0);
             for (int i = 0; i < n; ++i) is_design[pos[i]] = 1;
-            const int n_st = (n_file + gtk::kTcStageK - 1) / gtk::kTcStageK;
-            static const int perm16[16] = {0, 2, 4, 6, 8, 10, 12, 14, 1, 3, 5, 7, 9, 11, 13, 15};
-            scale.assign(ncol, 1.0);
+            gtk::Tc2Params &T = e->tc;
+            T = gtk::Tc2Params{};
+            // If the constant vector is a combination of the E columns (a design with
+            // an intercept: 1 = Q a), the column with the largest |a_j| needs no digit
+            // planes: the kernel derives its sum from sum(g) and the other columns.
+            T.ncolL = 0; T.drv_col = -1; T.drv_inv = 0.0;
+            std::vector<long double> acoef(ncol, 0.0L);
+            if (H.has_const && !H.degenerate && k > 0) {
+                for (int c = 0; c < k; ++c) {
+                    long double sacc = 0;
+                    for (int i = 0; i < n; ++i) sacc += H.Q[(size_t)c * n + i];
+                    acoef[c] = sacc;
+                }
+                long double worst = 0;
+                for (int i = 0; i < n; ++i) {
+                    long double r = 1.0L;
+                    for (int c = 0; c < k; ++c) r -= acoef[c] * H.Q[(size_t)c * n + i];
+                    worst = std::max(worst, fabsl(r));
+                }
+                int j = 0;
+                for (int c = 1; c < k; ++c) if (fabsl(acoef[c]) > fabsl(acoef[j])) j = c;
+                if (worst <= 1e-12L && fabsl(acoef[j]) > 0.5L) { T.drv_col = j; T.drv_inv = (double)(1.0L / acoef[j]); }
+            }
+            std::vector<int> dig_src;                    // E column of digit column cl
             for (int c = 0; c < ncol; ++c) {
+                if (c == T.drv_col) continue;
+                if (T.ncolL >= gtk::kT2MaxCols) { T.ncolL = gtk::kT2MaxCols + 1; break; }   // too wide
                 double mx = 0.0;
                 for (int i = 0; i < n; ++i) mx = std::max(mx, std::fabs(E[(size_t)pos[i] * NCP + c]));
-                scale[c] = mx > 0.0 ? mx : 1.0;
+                T.out_col[T.ncolL] = c;
+                T.scale[T.ncolL] = mx > 0.0 ? mx : 1.0;
+                T.drv_a[T.ncolL] = (double)acoef[c];
+                dig_src.push_back(c);
+                ++T.ncolL;
             }
-            Bimg.assign((size_t)n_st * N * 128, 0);
-            for (int st_i = 0; st_i < n_st; ++st_i) {
-                uint8_t *img = &Bimg[(size_t)st_i * N * 128];
-                for (int kk = 0; kk < 128; ++kk) {
-                    long long smp = (long long)st_i * 128 + (kk / 16) * 16 + perm16[kk % 16];
-                    if (smp >= (long long)n_pad) continue;
-                    const double *er = &E[(size_t)smp * NCP];
-                    if (is_design[smp]) {
-                        int nrow = 8 * ncol, grp = nrow >> 3, r = nrow & 7, chunk = kk >> 4, b = kk & 15;
-                        img[(size_t)grp * 1024 + r * 128 + ((chunk ^ r) << 4) + b] = 1;
-                    }
-                    for (int c = 0; c < ncol; ++c) {
-                        double x = er[c] / scale[c];
-                        long long Z = llround(std::ldexp(x, 54));
-                        for (int sl = 0; sl < 8; ++sl) {
-                            long long d8 = ((Z + 64) & 127) - 64;      // balanced base-128 digit
-                            Z = (Z - d8) / 128;
-                            int nrow = c * 8 + sl;
-                            int grp = nrow >> 3, r = nrow & 7, chunk = kk >> 4, b = kk & 15;
-                            img[(size_t)grp * 1024 + r * 128 + ((chunk ^ r) << 4) + b] = (uint8_t)(int8_t)d8;
+            // seven digit planes per column + one plane of ones over the design
+            // rows (its D column is the exact sum of the dosages)
+            const int N = (gtk::kT2Digits * T.ncolL + 1 + 15) / 16 * 16;
+            if (T.ncolL <= gtk::kT2MaxCols && N <= 256 && (long long)n_file <= (1ll << 22)) {
+                const int n_gst = (int)(pitch / 128);
+                const int n_slots = 4 * n_gst;
+                static const int perm16[16] = {0, 2, 4, 6, 8, 10, 12, 14, 1, 3, 5, 7, 9, 11, 13, 15};
+                std::vector<uint8_t> Bimg((size_t)n_slots * N * 128, 0);
+                auto put = [&](uint8_t *img, int nrow, int kk, uint8_t v) {
+                    // K-major, 128B swizzle: 8-row groups 1024 B apart, 16-byte chunk ^ row
+                    int grp = nrow >> 3, r = nrow & 7, chunk = kk >> 4, b = kk & 15;
+                    img[(size_t)grp * 1024 + r * 128 + ((chunk ^ r) << 4) + b] = v;
+                };
+                for (int sl_i = 0; sl_i < n_slots; ++sl_i) {
+                    uint8_t *img = &Bimg[(size_t)sl_i * N * 128];
+                    for (int kk = 0; kk < 128; ++kk) {
+                        // the expansion threads deliver the 16 samples of a word even ones first
+                        long long smp = (long long)sl_i * 128 + (kk / 16) * 16 + perm16[kk % 16];
+                        if (smp >= (long long)n_file || !is_design[smp]) continue;
+                        const double *er = &E[(size_t)smp * NCP];
+                        put(img, gtk::kT2Digits * T.ncolL, kk, 1);
+                        for (int cl = 0; cl < T.ncolL; ++cl) {
+                            long long Z = llround(std::ldexp(er[dig_src[cl]] / T.scale[cl], 54));
+                            for (int dg = 0; dg < gtk::kT2Digits; ++dg) {
+                                long long d8 = ((Z + 128) & 255) - 128;    // balanced base-256 digit
+                                Z = (Z - d8) / 256;
+                                put(img, cl * gtk::kT2Digits + dg, kk, (uint8_t)(int8_t)d8);
+                            }
                         }
                     }
                 }
+                for (int cl = 0; cl < T.ncolL; ++cl) T.scale[cl] = std::ldexp(T.scale[cl], -54);
+                if ((rc = upload(e->dBimg, Bimg.data(), Bimg.size(), st))) return rc;
+                if ((rc = e->dErr.reserve(16))) return rc;
+                CK(cudaMemsetAsync(e->dErr.p, 0, 16, st));
+                int zl = 0;
+                while ((size_t)(zl + 1) * 128 <= mask.size()) {
+                    bool zero = true;
+                    for (int b = 0; b < 128 && zero; ++b) zero = mask[(size_t)zl * 128 + b] == 0;
+                    if (!zero) break;
+                    ++zl;
+                }
+                T.n_gstages = n_gst; T.mask_zero_stages = zl;
+                T.ormask = (const uint8_t *)e->dMask.p; T.Bimg = (const uint8_t *)e->dBimg.p;
+                T.ncol = ncol; T.NCP = NCP; T.rcap = 16 * n_gst;
+                T.error_flag = (int *)e->dErr.p;
+                e->tc_N = N;
+                CK(cudaStreamSynchronize(st));           // Bimg goes out of scope
             }
-            for (int c = 0; c < ncol; ++c) scale[c] = std::ldexp(scale[c], -54);
-            if ((rc = upload(e->dBimg, Bimg.data(), Bimg.size(), st))) return rc;
-            if ((rc = upload(e->dScale, scale.data(), scale.size() * 8, st))) return rc;
-            if ((rc = e->dErr.reserve(16))) return rc;
-            CK(cudaMemsetAsync(e->dErr.p, 0, 16, st));
-            e->tc_N = N; e->tc_stages = n_st; e->tc_ncol = ncol;
-            int zl = 0;
-            while ((size_t)(zl + 1) * 128 <= mask.size()) {
-                bool zero = true;
-                for (int b = 0; b < 128 && zero; ++b) zero = mask[(size_t)zl * 128 + b] == 0;
-                if (!zero) break;
-                ++zl;
-            }
-            e->tc_mask_zero_lines = zl;
         }
         if ((rc = upload(e->dFF0, FF0.data(), FF0.size() * 8, st))) return rc;
         if ((rc = upload(e->dR, H.R.data(), H.R.size() * 8, st))) return rc;
@@ -694,27 +728,71 @@ static void time_end(gt_engine *e, int slot) {
 }
 
 
+// cuTensorMapEncodeTiled through the runtime (no link-time dependency on libcuda)
+typedef CUresult (*tmap_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                   CUtensorMapFloatOOBfill);
+static tmap_encode_fn tmap_encoder() {
+    static tmap_encode_fn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess &&
+            qr == cudaDriverEntryPointSuccess)
+            fn = (tmap_encode_fn)p;
+    }
+    return fn;
+}
+
+// SNP rows per CTA of the tcgen05 contraction for this design
+static int tc_tiles(const gt_engine *e) { return e->tc_N <= 96 ? 4 : (e->tc_N <= 128 ? 2 : 1); }
+static int tc_rows(const gt_engine *e) { return 128 * tc_tiles(e); }
+
 static int launch_contract_tc(gt_engine *e, const uint8_t *g, int64_t pitch, int nb) {
-    gtk::TcParams P;
-    P.geno = g; P.pitch = pitch; P.n_snps = nb; P.ormask = e->D.ormask;
-    P.Bimg = (const uint8_t *)e->dBimg.p; P.scale = (const double *)e->dScale.p;
-    P.n_stages = e->tc_stages; P.ncol = e->tc_ncol; P.ones_col = 8 * e->tc_ncol; P.N = e->tc_N; P.NCP = e->D.NCP;
+    gtk::Tc2Params P = e->tc;
+    P.pitch = pitch; P.n_snps = nb;
     P.S = (double *)e->dS.p; P.counts = (int *)e->dCounts.p; P.gsum = (double *)e->dGsum.p;
-    P.error_flag = (int *)e->dErr.p;
-    P.mlist = (int *)e->dMlist.p; P.mcap = e->mcap; P.mcount = (int *)e->dMcount.p;
-    P.mask_zero_lines = e->tc_mask_zero_lines; P.dbg = e->tc_dbg;
-    const int grid = (nb + 127) / 128;
+    P.mrec = (uint2 *)e->dMlist.p; P.mcount = (int *)e->dMcount.p;
+    const int rows = tc_rows(e);
+    tmap_encode_fn enc = tmap_encoder();
+    if (!enc) return fail(GT_E_CUDA, "tcgen05 contraction: cuTensorMapEncodeTiled is not available");
+    // the packed rows as a 2-D byte tensor [n_snps][pitch]; tiles of `rows` x 128 B, 128B swizzle;
+    // bytes past a row's pitch / rows past the batch read as zero
+    CUtensorMap gmap;
+    cuuint64_t gdim[2] = {(cuuint64_t)pitch, (cuuint64_t)nb};
+    cuuint64_t gstr[1] = {(cuuint64_t)pitch};
+    const cuuint32_t box[2] = {128u, (cuuint32_t)std::min(rows, 256)};
+    const cuuint32_t estr[2] = {1u, 1u};
+    CUresult cr = enc(&gmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)g, gdim, gstr, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return fail(GT_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
+    const int grid = (nb + rows - 1) / rows;
     const int NT = e->tc_N / 16;
-    size_t smem = (size_t)gtk::kTcStages * e->tc_N * 128 + 1024 + 256 + 128 * 4 * 4;
-#define GT_TC(T)                                                                               \
-    case T:                                                                                    \
-        CK(cudaFuncSetAttribute((const void *)gtk::contract_tc_kernel<T>,                      \
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
-        gtk::contract_tc_kernel<T><<<grid, gtk::kTcThreads, smem, e->stream>>>(P);             \
-        break;
+#define GT_TC(T, TL)                                                                              \
+    case T: {                                                                                     \
+        const int smem = gtk::Tc2Cfg<TL>::smem_bytes(16 * T);                                     \
+        CK(cudaFuncSetAttribute((const void *)gtk::contract_tc2_kernel<T, TL>,                    \
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, smem));              \
+        gtk::contract_tc2_kernel<T, TL><<<grid, gtk::Tc2Cfg<TL>::kThreads, smem, e->stream>>>(gmap, P); \
+    } break;
+#define GT_TCD(T, TL, DB)                                                                         \
+    if (NT == T && e->tc_dbg == DB) {                                                             \
+        const int smem = gtk::Tc2Cfg<TL>::smem_bytes(16 * T);                                     \
+        CK(cudaFuncSetAttribute((const void *)gtk::contract_tc2_kernel<T, TL, DB>,                \
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, smem));              \
+        gtk::contract_tc2_kernel<T, TL, DB><<<grid, gtk::Tc2Cfg<TL>::kThreads, smem, e->stream>>>(gmap, P); \
+        CK(cudaGetLastError());                                                                   \
+        return 0;                                                                                 \
+    }
+    // tuning probes (option "tc_debug") of the 5 x 16 column instantiation only
+    GT_TCD(5, 4, 1) GT_TCD(5, 4, 2) GT_TCD(5, 4, 6) GT_TCD(5, 4, 14) GT_TCD(5, 4, 32) GT_TCD(5, 4, 63)
+    GT_TCD(5, 4, 61) GT_TCD(5, 4, 189) GT_TCD(5, 4, 132) GT_TCD(5, 4, 128) GT_TCD(5, 4, 130) GT_TCD(5, 4, 134) GT_TCD(5, 4, 142) GT_TCD(5, 4, 191)
+#undef GT_TCD
     switch (NT) {
-        GT_TC(1) GT_TC(2) GT_TC(3) GT_TC(4) GT_TC(5) GT_TC(6) GT_TC(7) GT_TC(8) GT_TC(9)
-        GT_TC(10) GT_TC(11) GT_TC(12)
+        GT_TC(1, 4) GT_TC(2, 4) GT_TC(3, 4) GT_TC(4, 4) GT_TC(5, 4) GT_TC(6, 4) GT_TC(7, 2) GT_TC(8, 2)
+        GT_TC(9, 1) GT_TC(10, 1) GT_TC(11, 1) GT_TC(12, 1) GT_TC(13, 1) GT_TC(14, 1) GT_TC(15, 1) GT_TC(16, 1)
         default: return fail(GT_E_UNSUPPORTED, "tcgen05 contraction: N=%d not instantiated", e->tc_N);
     }
 #undef GT_TC
@@ -733,9 +811,9 @@ static int launch_finish(gt_engine *e, const void *g, int64_t pitch, int nb, dou
         D.flip_o = (const int *)e->dFlipO.p + s0;
     }
     const double *S = (const double *)e->dS.p;
-    const int *cnt = (const int *)e->dCounts.p;
+    int *cnt = (int *)e->dCounts.p;
     const double *gs = (const double *)e->dGsum.p;
-    const int *ml = use_list ? (const int *)e->dMlist.p : nullptr;
+    const uint2 *ml = use_list ? (const uint2 *)e->dMlist.p : nullptr;
     const int *mc = (const int *)e->dMcount.p;
     double *corr = (double *)e->dCorr.p;
     const int NT2 = (D.L + 7) / 8;
@@ -749,7 +827,7 @@ static int launch_finish(gt_engine *e, const void *g, int64_t pitch, int nb, dou
         CK(cudaFuncSetAttribute((const void *)gtk::missing_corr_kernel<PACKED, N>,         \
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));   \
         gtk::missing_corr_kernel<PACKED, N><<<cgrid, cw * 32, csm, e->stream>>>(           \
-            D, g, pitch, nb, cnt, ml, e->mcap, mc, corr);                                  \
+            D, g, pitch, nb, cnt, ml, e->tc.rcap, mc, corr);                                \
         break;
         int cslot = time_begin(e, 1);
         switch (NT2) {
@@ -790,20 +868,24 @@ static int run_linear(gt_engine *e, const void *geno, int64_t pitch, bool packed
     const GtDesignDev &D = e->D;
     const ContractEntry &ce = kContract[e->contract_idx];
     const int tile = 32 * ce.rows;
-    // a multiple of the tcgen05 kernel's wave (148 SMs x 2 CTAs x 128 SNPs)
-    const int kBatch = 148 * 2 * 128 * 2;
+    const bool tc = packed && e->use_tc && e->tc_N > 0;
+    // whole waves of the tcgen05 kernel (148 SMs x one CTA of 128 / 256 SNP rows); the
+    // records of the missing genotypes take up to a packed row per SNP
+    int kBatch = 148 * 2 * 128 * 2;
+    if (tc) {
+        const int wave = 148 * tc_rows(e);
+        const long long fit = ((long long)4 << 30) / ((long long)e->tc.rcap * 8);
+        kBatch = (int)std::max<long long>(wave, std::min<long long>(8, fit / wave) * wave);
+    }
     int rc;
     const int bmax = std::min<int>(n_snps, kBatch);
     if ((rc = e->dS.reserve((size_t)bmax * D.NCP * 8))) return rc;
     if ((rc = e->dCounts.reserve((size_t)bmax * 4 * 4))) return rc;
     if ((rc = e->dGsum.reserve((size_t)bmax * 2 * 8))) return rc;
-    const bool tc = packed && e->use_tc && e->tc_N > 0;
     if (tc) {
-        // per-SNP list of missing samples written by the tcgen05 kernel:
-        // room for 4 % missing (overflow falls back to re-scanning the row)
-        e->mcap = std::max(64, (D.n_file + 24) / 25) & ~1;
-        if ((rc = e->dMlist.reserve((size_t)bmax * e->mcap * 4))) return rc;
-        if ((rc = e->dMcount.reserve((size_t)bmax * 2 * 4))) return rc;
+        const size_t brows = ((size_t)bmax + tc_rows(e) - 1) / tc_rows(e) * tc_rows(e);   // whole CTAs
+        if ((rc = e->dMlist.reserve(brows * e->tc.rcap * 8))) return rc;
+        if ((rc = e->dMcount.reserve((size_t)bmax * 4))) return rc;
     }
     if ((rc = e->dCorr.reserve((size_t)bmax * D.L * D.L * 8))) return rc;
     CK(cudaFuncSetAttribute((const void *)ce.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ce.smem));

@@ -26,10 +26,9 @@ __device__ __forceinline__ void dmma884_lin(double &c0, double &c1, double a, do
 // vectors gathered into a shared staging tile, and the outer products
 // accumulated with FP64 tensor-core MMAs (m8n8k4, upper tiles only).
 template <bool PACKED, int NT2>
-__device__ __forceinline__ void subtract_missing(const GtDesignDev &D, const void *rowp,
-                                                 double *S0, double *stage, int *queue,
-                                                 int lane, const int *mlist, int mcountA,
-                                                 int mcountB, int hcap) {
+__device__ __forceinline__ int subtract_missing(const GtDesignDev &D, const void *rowp,
+                                                double *S0, double *stage, int *queue,
+                                                int lane, const uint2 *mrec, int nrec) {
     constexpr int LS = finish_stage_stride(NT2);
     const int L = D.L;
     const int nlive = D.lean ? D.k + 1 : L;      // columns present in E
@@ -86,22 +85,23 @@ __device__ __forceinline__ void subtract_missing(const GtDesignDev &D, const voi
         return has;
     };
 
-    if (mlist != nullptr && mcountA >= 0 && mcountB >= 0) {
-        // The contraction kernel already listed the missing samples.  Each
-        // lane loads its own MMA fragment elements straight from E (no
+    int n_listed = 0;
+    if (mrec != nullptr) {
+        // The contraction kernel recorded every 32-sample pair that has missing
+        // genotypes as (pair index, flags); flag bit b is sample
+        // 32 * pair + 16 * (b & 1) + (b >> 1).  The records are turned into
+        // sample indices in the warp's queue (the staging tile is not needed on
+        // this path, the queue takes its place), one round of up to kQCap
+        // indices at a time, and every round runs the gather / MMA pipeline:
+        // each lane loads its own MMA fragment elements straight from E (no
         // shared staging): lane (c = lane / 4, e = lane % 4) of k-step ks
         // needs elements t * 8 + c of sample 4 ks + e, so the eight lanes of
         // one sample read 64 contiguous bytes -- whole 32 B sectors.  Group
-        // g + 1 is in flight while the tensor cores work on group g; the
-        // indices run two groups ahead.
-        const int mcount = mcountA + mcountB;
-        const int ngroups = (mcount + 31) / 32;
+        // g + 1 is in flight while the tensor cores work on group g.
+        constexpr int kQCap = 32 * finish_stage_stride(NT2) * 2 + 64;   // ints in stage + queue
+        int *rq = (int *)stage;                  // the queue follows the staging tile (corr_layout)
         const int c = lane >> 2, e4 = lane & 3;
         const int one_col = D.lean ? D.k + 1 : -1;
-        auto index_of = [&](int g) {
-            int t = g * 32 + lane;
-            return (t < mcount) ? (t < mcountA ? mlist[t] : mlist[hcap + t - mcountA]) : -1;
-        };
         // every load is unconditional: lanes without an element (padding
         // columns, samples past the end of the list) read the constant 0.0,
         // the lane of the ones column reads the constant 1.0 -- a predicated
@@ -136,29 +136,65 @@ __device__ __forceinline__ void subtract_missing(const GtDesignDev &D, const voi
                     for (int nt = mt; nt < NT2; ++nt)
                         dmma884_lin(acc[mt][nt][0], acc[mt][nt][1], f[ks * NT2 + mt], f[ks * NT2 + nt]);
         };
-        if (NT2 <= 2) {
-            // branch-free software pipeline: groups past the end gather zeros
-            // (index -1), so no conditional copy sits between a load and the
-            // MMAs two stages later
-            double fa[8 * NT2], fb[8 * NT2];
-            int i1 = index_of(1), i2 = index_of(2);
-            gather(index_of(0), fa);
-            for (int g = 0; g < ngroups; g += 2) {
-                gather(i1, fb);
-                i1 = index_of(g + 3);
-                mma(fa);
-                gather(i2, fa);
-                i2 = index_of(g + 4);
-                mma(fb);
+        int r = 0;
+        while (r < nrec) {
+            // ---- records -> indices, until the queue cannot take another 32 records ----
+            int qn2 = 0;
+            while (r < nrec) {
+                const int t = r + lane;
+                uint2 rec = make_uint2(0u, 0u);
+                if (t < nrec) rec = mrec[t];
+                uint32_t f = rec.y;
+                int incl = __popc(f);
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    int v = __shfl_up_sync(GT_FULL, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                const int total = __shfl_sync(GT_FULL, incl, 31);
+                if (qn2 + total > kQCap) break;               // run what is queued first
+                int w = qn2 + incl - __popc(f);
+                const int base = (int)rec.x * 32;
+                while (f) {
+                    const int b = __ffs((int)f) - 1;
+                    rq[w++] = base + 16 * (b & 1) + (b >> 1);
+                    f &= f - 1;
+                }
+                qn2 += total;
+                r += 32;
             }
-        } else {
-            double fa[8 * NT2];
-            int inext = index_of(0);
-            for (int g = 0; g < ngroups; ++g) {
-                gather(inext, fa);
-                inext = index_of(g + 1);
-                mma(fa);
+            __syncwarp();
+            n_listed += qn2;
+            const int ngroups = (qn2 + 31) / 32;
+            auto index_of = [&](int g) {
+                int t = g * 32 + lane;
+                return (t < qn2) ? rq[t] : -1;
+            };
+            if (NT2 <= 2) {
+                // branch-free software pipeline: groups past the end gather zeros
+                // (index -1), so no conditional copy sits between a load and the
+                // MMAs two stages later
+                double fa[8 * NT2], fb[8 * NT2];
+                int i1 = index_of(1), i2 = index_of(2);
+                gather(index_of(0), fa);
+                for (int g = 0; g < ngroups; g += 2) {
+                    gather(i1, fb);
+                    i1 = index_of(g + 3);
+                    mma(fa);
+                    gather(i2, fa);
+                    i2 = index_of(g + 4);
+                    mma(fb);
+                }
+            } else {
+                double fa[8 * NT2];
+                int inext = index_of(0);
+                for (int g = 0; g < ngroups; ++g) {
+                    gather(inext, fa);
+                    inext = index_of(g + 1);
+                    mma(fa);
+                }
             }
+            __syncwarp();
         }
     } else if (PACKED) {
         const int nwords = (D.n_file + 15) / 16;         // 32-bit words of 16 samples
@@ -215,6 +251,7 @@ __device__ __forceinline__ void subtract_missing(const GtDesignDev &D, const voi
                 }
             }
     __syncwarp();
+    return n_listed;
 }
 
 // K3a: the missing-sample corrections of a batch.  One warp per SNP; writes
@@ -236,28 +273,28 @@ __host__ __device__ inline CorrLayout corr_layout(int L) {
 template <bool PACKED, int NT2>
 __global__ void __launch_bounds__(256, 2)
 missing_corr_kernel(GtDesignDev D, const void *__restrict__ geno, long long pitch, int n_snps,
-                    const int *__restrict__ counts, const int *__restrict__ mlist, int mcap,
+                    int *__restrict__ counts, const uint2 *__restrict__ mrec, int rcap,
                     const int *__restrict__ mcount, double *__restrict__ corr) {
     extern __shared__ __align__(16) double sm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int snp = blockIdx.x * (blockDim.x >> 5) + warp;
     if (snp >= n_snps) return;
-    if (counts[(long long)snp * 4 + 2] <= 0) return;       // nothing missing
+    const int mA = mrec ? mcount[snp] : 0;
+    if (mrec ? (mA == 0) : (counts[(long long)snp * 4 + 2] <= 0)) return;   // nothing missing
     const int L = D.L;
     const CorrLayout lay = corr_layout(L);
     double *W = sm + (size_t)warp * lay.perWarp;
     double *S0 = W + lay.oS0, *stage = W + lay.oStage;
     int *queue = (int *)(W + lay.oQueue);
     for (int t = lane; t < L * L; t += 32) S0[t] = 0.0;
-    for (int t = lane; t < 32 * finish_stage_stride(NT2); t += 32) stage[t] = 0.0;
+    if (!mrec) for (int t = lane; t < 32 * finish_stage_stride(NT2); t += 32) stage[t] = 0.0;
     __syncwarp();
     const void *rowp = PACKED ? (const void *)((const uint8_t *)geno + (long long)snp * pitch)
                               : (const void *)((const double *)geno + (long long)snp * pitch);
-    const int mA = mlist ? mcount[(long long)snp * 2] : -1;
-    const int mB = mlist ? mcount[(long long)snp * 2 + 1] : -1;
-    subtract_missing<PACKED, NT2>(D, rowp, S0, stage, queue, lane,
-                                  mlist ? mlist + (long long)snp * mcap : nullptr, mA, mB,
-                                  mcap >> 1);
+    const int n_listed = subtract_missing<PACKED, NT2>(
+        D, rowp, S0, stage, queue, lane, mrec ? mrec + (long long)snp * rcap : nullptr, mA);
+    // the tcgen05 contraction leaves the missing count to this kernel
+    if (mrec && lane == 0) counts[(long long)snp * 4 + 2] = n_listed;
     double *out = corr + (long long)snp * L * L;
     for (int t = lane; t < L * L; t += 32) out[t] = -S0[t];
 }

@@ -1,4 +1,5 @@
-"""Time the tcgen05 contraction with parts disabled (tuning probe)."""
+"""Time the tcgen05 contraction with parts compiled out (tuning probe):
+option "tc_debug" bits 1 no records, 2 no MMA, 4 no TMEM store, 16 no counts."""
 import sys
 sys.path.insert(0, ".")
 import numpy as np, torch
@@ -6,21 +7,25 @@ from genetest_b200.engine import Engine
 import bench
 eng = Engine(0)
 rng = np.random.default_rng(0)
-n, snps = 100000, 75776
+n = 100000
+snps = int(sys.argv[1]) if len(sys.argv) > 1 else 151552
 y, C, names = bench.make_design("linear", n, 10, rng)
 eng.set_design("linear", y, C)
 eng.set_option("contract_tc", 1)
 packed = eng.synth_packed(n, snps, seed=1, missing_rate=0.01)
 out, iout = eng.alloc_results(snps)
-for dbg in (0, 1, 16, 17, 2, 4, 8, 1 | 2 | 4 | 16, 1 | 2 | 4 | 8 | 16):
+for dbg in [int(a) for a in sys.argv[2:]] or (0, 128, 191):
     eng.set_option("tc_debug", dbg)
-    for _ in range(2):
+    for _ in range(1):
         eng.run_packed_dev(packed, snps, packed.stride(0), out, iout)
     eng.synchronize()
     eng.enable_timing(True)
-    for _ in range(3):
+    for _ in range(1 if dbg & 128 else 3):
         eng.run_packed_dev(packed, snps, packed.stride(0), out, iout)
     eng.synchronize()
     ms, k, _ = eng.kernel_time()
+    br = eng.kernel_breakdown()
     eng.enable_timing(False)
-    print("dbg %2d: %.3f ms per launch" % (dbg, ms / k), flush=True)
+    gbs = snps * 25000.0 / (ms / k * 1e-3) / 1e9
+    print("dbg %2d: contraction %.3f ms per launch of %d SNPs = %.0f GB/s packed; per 3 runs: %s"
+          % (dbg, ms / k, snps, gbs, {a: round(b, 3) for a, b in br.items()}), flush=True)
