@@ -97,12 +97,50 @@ GT_HD double gt_lbeta_half(double a) {
     return 0.5 * log(3.14159265358979323846) - gt_lgamma_half_diff(a);
 }
 
+// I_x(a, 1/2) for large a by the asymptotic expansion of DiDonato & Morris
+// (ACM TOMS 18, 1992, "BGRAT": sum of p_n J_n(b, u) with u = -(a + (b-1)/2) ln x),
+// specialised to b = 1/2 where Q(b, u) = erfc(sqrt(u)) and the p_n are constants.
+// t2 = t^2, a = df / 2 >= 250: at most 12 terms reach 1e-13 relative for every
+// |t| (checked against 40-digit references in tests/test_host_api.py); for
+// df ~ 1e5 three terms do.  Returns -1 when exp(-u) would underflow.
+GT_HD double gt_t_sf2_large_df(double t2, double df) {
+    const double pn[12] = {1.0, -0.08333333333333333, 0.00625, -0.0005042989417989418,
+                           4.343722442680776e-05, -3.896385732323232e-06, 3.5833354634507906e-07,
+                           -3.349747072060578e-08, 3.1675854343161146e-09, -3.0210368517370963e-10,
+                           2.900415787669253e-11, -2.799396748375269e-12};
+    const double a = 0.5 * df, T = a - 0.25;
+    const double lx = -log1p(t2 / df);            // ln x, x = df / (df + t^2)
+    const double u = -T * lx;
+    if (!(u < 700.0)) return -1.0;
+    const double su = sqrt(u);
+    const double h = su * exp(-u) * 0.56418958354775628695;          // u^b e^-u / Gamma(b)
+    const double prefix = h * exp(gt_lgamma_half_diff(a)) / sqrt(T);
+    double j = erfc(su) / h;
+    double sum = j;                                                  // p_0 = 1
+    const double lx2 = 0.25 * lx * lx, t4inv = 1.0 / (4.0 * T * T);
+    double lxp = 1.0, b2n = 0.5;
+    for (int n = 1; n < 12; ++n) {
+        j = (b2n * (b2n + 1.0) * j + (u + b2n + 1.0) * lxp) * t4inv;
+        lxp *= lx2;
+        b2n += 2.0;
+        const double r = pn[n] * j;
+        sum += r;
+        if (fabs(r) < 1e-17 * fabs(sum)) break;
+    }
+    return prefix * sum;
+}
+
 // Two-sided tail 2 * P(T_df > |t|) = I_x(df/2, 1/2), x = df / (df + t^2).
 GT_HD double gt_t_sf2(double t, double df) {
     if (!(df > 0.0) || t != t) return nan("");
     double t2 = t * t;
     if (t2 == 0.0) return 1.0;
     if (isinf(t2)) return 0.0;
+    if (df >= 500.0) {
+        // the continued fraction below needs O(sqrt(df)) partial quotients here
+        const double v = gt_t_sf2_large_df(t2, df);
+        if (v >= 0.0) return v;
+    }
     double a = 0.5 * df;
     double lnpre = -gt_lbeta_half(a) - a * log1p(t2 / df) +
                    0.5 * (log(t2) - log(df + t2));

@@ -132,11 +132,13 @@ template <int TILES> struct Tc2Cfg {
     }
     __host__ __device__ static constexpr int b_stages(int N) {
         // what is left of ~210 KB after the genotype ring, at most 6 stages of 128 samples
-        return ((210 * 1024 - kGStages * kGStage) / (N * 128)) < 6
-                   ? ((210 * 1024 - kGStages * kGStage) / (N * 128)) : 6;
+        return ((210 * 1024 - kGStages * kGStage - kRecRing) / (N * 128)) < 6
+                   ? ((210 * 1024 - kGStages * kGStage - kRecRing) / (N * 128)) : 6;
     }
+    // staging ring of the missing-pair records: 8 records of 8 B per expansion thread
+    static constexpr int kRecRing = kRows * 64;
     __host__ __device__ static constexpr int smem_bytes(int N) {
-        return 1024 + kGStages * kGStage + b_stages(N) * N * 128 + 512;
+        return 1024 + kGStages * kGStage + b_stages(N) * N * 128 + 512 + kRecRing;
     }
 };
 
@@ -167,6 +169,7 @@ contract_tc2_kernel(const __grid_constant__ CUtensorMap gmap, const Tc2Params P)
     uint32_t *tmem_slot = (uint32_t *)(d_full + 1);
     int *fail = (int *)(tmem_slot + 1);
     uint32_t *lut_s = tmem_slot + 2;
+    unsigned char *sRec = (unsigned char *)(bars + 64);         // [8][kRows] records (uint2)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // probe (DBG & 128): cycles the roles of CTA 0 spend in their waits
@@ -209,8 +212,12 @@ contract_tc2_kernel(const __grid_constant__ CUtensorMap gmap, const Tc2Params P)
         const uint32_t sw = (uint32_t)(row & 7);
         // rows past the batch read as zeros (TMA fill): they never produce a record,
         // and the record buffer is sized for whole CTAs anyway
-        const char *const mbase = (const char *)(P.mrec + (long long)snp * P.rcap);
-        uint32_t moff = 0;                               // bytes of records written
+        // Records are staged in shared memory (slot k of this thread at [k][row]: every
+        // access is conflict free) and leave in whole 32-byte sectors, four at a time:
+        // 8-byte stores scattered over 512 rows cost the L2 a read-modify-write each.
+        char *const mbase = (char *)(P.mrec + (long long)snp * P.rcap);
+        const uint32_t rec_s = smem_u32(sRec) + row * 8;
+        uint32_t wcnt = 0, flushed = 0;                  // records staged / written to global
         int nhom = 0;
         // code -> dosage byte: 00 -> 2, 01 -> 0, 10 -> 1, 11 -> 0.  Opaque to the
         // compiler (read back from shared memory) so that it stays in one vector
@@ -257,9 +264,10 @@ contract_tc2_kernel(const __grid_constant__ CUtensorMap gmap, const Tc2Params P)
                     asm volatile(
                         "{\n\t.reg .pred p;\n\t"
                         "setp.ne.u32 p, %3, 0;\n\t"
-                        "@p st.global.v2.u32 [%1], {%2, %3};\n\t"
-                        "@p add.u32 %0, %0, 8;\n\t}\n"
-                        : "+r"(moff) : "l"(mbase + moff), "r"((uint32_t)(it * 2 + pr)), "r"(mis2)
+                        "@p st.shared.v2.u32 [%1], {%2, %3};\n\t"
+                        "@p add.u32 %0, %0, 1;\n\t}\n"
+                        : "+r"(wcnt) : "r"(rec_s + ((wcnt & 7u) * (uint32_t)(Cfg::kRows * 8))),
+                          "r"((uint32_t)(it * 2 + pr)), "r"(mis2)
                         : "memory");
                 }
             }
@@ -279,6 +287,21 @@ contract_tc2_kernel(const __grid_constant__ CUtensorMap gmap, const Tc2Params P)
                 : "memory");
         };
 
+        // every two slots (at most four new records): one whole sector leaves when four are staged
+        auto flush4 = [&]() {
+            if ((DBG & 1) || wcnt - flushed < 4u) return;
+            const uint32_t src = rec_s + ((flushed & 4u) * (uint32_t)(Cfg::kRows * 8));
+            uint2 r0, r1, r2, r3;
+            asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];\n" : "=r"(r0.x), "=r"(r0.y) : "r"(src));
+            asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];\n" : "=r"(r1.x), "=r"(r1.y) : "r"(src + Cfg::kRows * 8));
+            asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];\n" : "=r"(r2.x), "=r"(r2.y) : "r"(src + Cfg::kRows * 16));
+            asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];\n" : "=r"(r3.x), "=r"(r3.y) : "r"(src + Cfg::kRows * 24));
+            uint4 *dst = (uint4 *)(mbase + (size_t)flushed * 8);
+            dst[0] = make_uint4(r0.x, r0.y, r1.x, r1.y);
+            dst[1] = make_uint4(r2.x, r2.y, r3.x, r3.y);
+            flushed += 4;
+        };
+
         for (int gs = 0; gs < n_gst; ++gs) {
             const int st = gs % G;
             GT_PROF(0, if (!mbar_wait2(&g_full[st], (gs / G) & 1, fail)) *fail = 1);
@@ -295,11 +318,17 @@ contract_tc2_kernel(const __grid_constant__ CUtensorMap gmap, const Tc2Params P)
                 }
                 if (gs < P.mask_zero_stages) {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) do_slot(pw[q], make_uint4(0u, 0u, 0u, 0u), gs * 8 + hf * 4 + q);
+                    for (int q = 0; q < 4; ++q) {
+                        do_slot(pw[q], make_uint4(0u, 0u, 0u, 0u), gs * 8 + hf * 4 + q);
+                        if (q & 1) flush4();
+                    }
                 } else {
                     const uint4 *mrow = (const uint4 *)(P.ormask + (long long)gs * 128);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) do_slot(pw[q], __ldg(mrow + 4 * hf + q), gs * 8 + hf * 4 + q);
+                    for (int q = 0; q < 4; ++q) {
+                        do_slot(pw[q], __ldg(mrow + 4 * hf + q), gs * 8 + hf * 4 + q);
+                        if (q & 1) flush4();
+                    }
                 }
             }
         }
@@ -307,7 +336,16 @@ contract_tc2_kernel(const __grid_constant__ CUtensorMap gmap, const Tc2Params P)
         if ((DBG & 128) && blockIdx.x == 0 && (tid == 0 || tid == 32 * (EW - 1)))
             printf("expansion warp %d: total %lld  g_full %lld  a_empty %lld  wait_st %lld\n", warp,
                    clock64() - prof_t0, prof[0], prof[1], prof[2]);
-        const int nrec = (int)(moff >> 3);
+        const int nrec = (int)wcnt;
+        if (!(DBG & 1)) {
+            // at most three staged records are left
+            for (; flushed < wcnt; ++flushed) {
+                uint2 r;
+                asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];\n" : "=r"(r.x), "=r"(r.y)
+                             : "r"(rec_s + ((flushed & 7u) * (uint32_t)(Cfg::kRows * 8))));
+                *(uint2 *)(mbase + (size_t)flushed * 8) = r;
+            }
+        }
         if (owner) {
             P.mcount[snp] = nrec;
             for (int col = P.ncol; col < P.NCP; ++col) P.S[(long long)snp * P.NCP + col] = 0.0;

@@ -525,6 +525,20 @@ def test_p_value_formulas_match_scipy():
                 continue
             worst = max(worst, abs(got - w) / w)
     assert worst < 1e-9, worst
+    # Large degrees of freedom (biobank sizes): the asymptotic expansion the
+    # kernels switch to at df >= 500 against 40-digit references (scipy's own
+    # tail loses digits to cancellation there), df up to 1e7.
+    import mpmath
+    mpmath.mp.dps = 40
+    worst_big = 0.0
+    for df in (499, 500, 501, 750, 1000, 3000, 19988, 99988, 499988, 1e6, 1e7):
+        for t in (1e-9, 1e-4, 0.01, 0.3, 1, 1.9, 2.5, 3, 3.5, 4.5, 6, 9, 14, 22, 30, 36):
+            x = mpmath.mpf(df) / (mpmath.mpf(df) + mpmath.mpf(t) ** 2)
+            w = float(mpmath.betainc(mpmath.mpf(df) / 2, mpmath.mpf(1) / 2, 0, x,
+                                     regularized=True))
+            got = lib.gt_host_t_sf2(float(t), float(df))
+            worst_big = max(worst_big, abs(got - w) / w)
+    assert worst_big < 5e-13, worst_big
     assert np.isnan(lib.gt_host_t_sf2(float("nan"), 10.0))
     assert lib.gt_host_t_sf2(float("inf"), 10.0) == 0.0
     for df in dfs + [4, 6, 7, 9, 15, 40]:
