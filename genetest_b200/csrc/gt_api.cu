@@ -16,6 +16,7 @@
 #include "gt_contract.cuh"
 #include "gt_contract_tc.cuh"
 #include "gt_contract_tc2.cuh"
+#include "gt_corr_stream.cuh"
 #include "gt_linear.cuh"
 #include "gt_solve.cuh"
 #include "gt_logistic.cuh"
@@ -32,7 +33,11 @@ struct gt_engine {
     gtk::IterDesignDev T{};           // logistic / coxph design
     DevBuf dE, dMask, dFF0, dR, dRinv, dTq, dIter;   // design
     DevBuf dBimg, dScale, dErr;                      // tcgen05 contraction (lean designs)
+    DevBuf dEi;                                      // compact design rows of the streaming corrections
+    gtk::CorrStreamParams cs{};
+    int cs_nv = 0;             // columns the streaming correction kernel gathers (0: not available)
     bool use_tc = true;        // lean linear designs run on the tcgen05 int8 contraction
+    bool use_stream_corr = true;   // ... and their corrections on the streaming kernel
     int tc_dbg = 0;
     int tc_N = 0;              // 0: the design does not run on the tcgen05 kernel
     gtk::Tc2Params tc{};       // constant part of the kernel parameters
@@ -350,7 +355,7 @@ int gt_engine_destroy(gt_engine *e) {
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
     for (auto &ev : e->events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
-    DevBuf *bufs[] = {&e->dE, &e->dMask, &e->dFF0, &e->dR, &e->dRinv, &e->dTq, &e->dIter, &e->dBimg, &e->dScale, &e->dErr,
+    DevBuf *bufs[] = {&e->dE, &e->dMask, &e->dFF0, &e->dR, &e->dRinv, &e->dTq, &e->dIter, &e->dBimg, &e->dScale, &e->dErr, &e->dEi,
                       &e->dS, &e->dCounts, &e->dGsum, &e->dMlist, &e->dMcount, &e->dCorr, &e->dGeno, &e->dOut, &e->dIout,
                       &e->dSexM, &e->dSexF, &e->dSexRow, &e->dMafO, &e->dFlipO, &e->dCounter};
     for (DevBuf *b : bufs) b->release();
@@ -400,6 +405,7 @@ int gt_engine_set_option(gt_engine *e, const char *name, int value) {
     if (!e || !name) return fail(GT_E_ARG, "gt_engine_set_option: NULL argument");
     if (std::strcmp(name, "contract_tc") == 0) { e->use_tc = value != 0; return 0; }
     if (std::strcmp(name, "tc_debug") == 0) { e->tc_dbg = value; return 0; }
+    if (std::strcmp(name, "stream_corrections") == 0) { e->use_stream_corr = value != 0; return 0; }
     if (std::strcmp(name, "host_chunk") == 0) { e->host_chunk = (int)std::max<int64_t>(0, value); return 0; }
     return fail(GT_E_ARG, "gt_engine_set_option: unknown option '%s'", name);
 }
@@ -665,7 +671,31 @@ int gt_engine_set_design(gt_engine *e, const gt_design_desc *d) {
                 T.ncol = ncol; T.NCP = NCP; T.rcap = 16 * n_gst;
                 T.error_flag = (int *)e->dErr.p;
                 e->tc_N = N;
-                CK(cudaStreamSynchronize(st));           // Bimg goes out of scope
+                // ---- compact rows (the digit columns only) for the streaming corrections ----
+                e->cs_nv = 0;
+                if (T.ncolL <= gtk::kCsRow) {
+                    const int nblk = (n_file + gtk::kCsBlk - 1) / gtk::kCsBlk;
+                    std::vector<double> Ec((size_t)nblk * gtk::kCsBlk * gtk::kCsRow, 0.0);
+                    gtk::CorrStreamParams &C = e->cs;
+                    C = gtk::CorrStreamParams{};
+                    for (int cl = 0; cl < T.ncolL; ++cl) {
+                        C.vcol[cl] = dig_src[cl];
+                        C.drv_a[cl] = T.drv_a[cl];
+                        // 16-byte chunks (column pairs) of row i are stored at chunk ^ ((i >> 2) & 1)
+                        for (int i = 0; i < n; ++i) {
+                            const int ps = pos[i];
+                            const int slot = (((cl >> 1) ^ ((ps >> 2) & 1)) << 1) | (cl & 1);
+                            Ec[(size_t)ps * gtk::kCsRow + slot] = E[(size_t)ps * NCP + dig_src[cl]];
+                        }
+                    }
+                    C.drv_col = T.drv_col; C.drv_inv = T.drv_inv;
+                    C.n_blocks = nblk; C.L = L; C.rcap = T.rcap;
+                    if ((rc = upload(e->dEi, Ec.data(), Ec.size() * 8, st))) return rc;
+                    C.Ec = (const double *)e->dEi.p;
+                    C.error_flag = (int *)e->dErr.p;
+                    e->cs_nv = T.ncolL;
+                }
+                CK(cudaStreamSynchronize(st));           // Bimg / Ei go out of scope
             }
         }
         if ((rc = upload(e->dFF0, FF0.data(), FF0.size() * 8, st))) return rc;
@@ -816,8 +846,31 @@ static int launch_finish(gt_engine *e, const void *g, int64_t pitch, int nb, dou
     const uint2 *ml = use_list ? (const uint2 *)e->dMlist.p : nullptr;
     const int *mc = (const int *)e->dMcount.p;
     double *corr = (double *)e->dCorr.p;
+    const long long ldc = (nb + 31) / 32 * 32;
     const int NT2 = (D.L + 7) / 8;
-    {
+    const bool stream = use_list && e->cs_nv > 0 && e->use_stream_corr;
+    if (stream) {
+        // thread-per-SNP streaming corrections (gt_corr_stream.cuh)
+        gtk::CorrStreamParams C = e->cs;
+        C.n_snps = nb; C.mrec = ml; C.mcount = mc; C.corrT = corr; C.ldc = ldc; C.counts = cnt;
+        const int sm = gtk::kCsBuf * gtk::kCsBlk * gtk::kCsRow * 8 + (gtk::kCsRecRing / 2) * gtk::kCsSnps * 16 + 256;
+        const int cgrid = (nb + gtk::kCsSnps - 1) / gtk::kCsSnps;
+        int cslot = time_begin(e, 1);
+#define GT_CS(N)                                                                              \
+    case N:                                                                                   \
+        CK(cudaFuncSetAttribute((const void *)gtk::missing_corr_stream_kernel<N>,             \
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, sm));            \
+        gtk::missing_corr_stream_kernel<N><<<cgrid, gtk::kCsThreads, sm, e->stream>>>(C);     \
+        break;
+        switch (e->cs_nv) {
+            GT_CS(1) GT_CS(2) GT_CS(3) GT_CS(4) GT_CS(5) GT_CS(6) GT_CS(7) GT_CS(8) GT_CS(9) GT_CS(10)
+            GT_CS(11) GT_CS(12)
+            default: return fail(GT_E_UNSUPPORTED, "streaming corrections: %d columns", e->cs_nv);
+        }
+#undef GT_CS
+        time_end(e, cslot);
+        CK(cudaGetLastError());
+    } else {
         const gtk::CorrLayout cl = gtk::corr_layout(D.L);
         const int cw = 8;
         const size_t csm = (size_t)cw * cl.perWarp * 8;
@@ -827,7 +880,7 @@ static int launch_finish(gt_engine *e, const void *g, int64_t pitch, int nb, dou
         CK(cudaFuncSetAttribute((const void *)gtk::missing_corr_kernel<PACKED, N>,         \
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));   \
         gtk::missing_corr_kernel<PACKED, N><<<cgrid, cw * 32, csm, e->stream>>>(           \
-            D, g, pitch, nb, cnt, ml, e->tc.rcap, mc, corr);                                \
+            D, g, pitch, nb, cnt, ml, e->tc.rcap, mc, corr, ldc);                              \
         break;
         int cslot = time_begin(e, 1);
         switch (NT2) {
@@ -851,11 +904,11 @@ static int launch_finish(gt_engine *e, const void *g, int64_t pitch, int nb, dou
         if (half) {
             CK(cudaFuncSetAttribute((const void *)gtk::linear_solve_kernel<16>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            gtk::linear_solve_kernel<16><<<grid, threads, smem, e->stream>>>(D, nb, S, cnt, gs, corr, out, iout, stride);
+            gtk::linear_solve_kernel<16><<<grid, threads, smem, e->stream>>>(D, nb, S, cnt, gs, corr, ldc, out, iout, stride);
         } else {
             CK(cudaFuncSetAttribute((const void *)gtk::linear_solve_kernel<32>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            gtk::linear_solve_kernel<32><<<grid, threads, smem, e->stream>>>(D, nb, S, cnt, gs, corr, out, iout, stride);
+            gtk::linear_solve_kernel<32><<<grid, threads, smem, e->stream>>>(D, nb, S, cnt, gs, corr, ldc, out, iout, stride);
         }
         time_end(e, fslot);
         CK(cudaGetLastError());
@@ -884,10 +937,10 @@ static int run_linear(gt_engine *e, const void *geno, int64_t pitch, bool packed
     if ((rc = e->dGsum.reserve((size_t)bmax * 2 * 8))) return rc;
     if (tc) {
         const size_t brows = ((size_t)bmax + tc_rows(e) - 1) / tc_rows(e) * tc_rows(e);   // whole CTAs
-        if ((rc = e->dMlist.reserve(brows * e->tc.rcap * 8))) return rc;
+        if ((rc = e->dMlist.reserve(brows * e->tc.rcap * 8 + 256))) return rc;     // + read-ahead slack
         if ((rc = e->dMcount.reserve((size_t)bmax * 4))) return rc;
     }
-    if ((rc = e->dCorr.reserve((size_t)bmax * D.L * D.L * 8))) return rc;
+    if ((rc = e->dCorr.reserve(((size_t)bmax + 32) * (D.L * (D.L + 1) / 2) * 8))) return rc;
     CK(cudaFuncSetAttribute((const void *)ce.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ce.smem));
 
     for (int s0 = 0; s0 < n_snps; s0 += kBatch) {

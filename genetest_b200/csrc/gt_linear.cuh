@@ -256,7 +256,8 @@ __device__ __forceinline__ int subtract_missing(const GtDesignDev &D, const void
 
 // K3a: the missing-sample corrections of a batch.  One warp per SNP; writes
 // Corr[snp][L*L] = sum over the missing samples of v v' for every marker that
-// has missing genotypes (the solve kernel reads it only for those).  The
+// has missing genotypes (the solve kernel reads it only for those), as the upper
+// triangle in SoA layout corrT[entry][marker].  The
 // samples come from the lists the tcgen05 contraction emitted, or from a
 // re-scan of the row (FP64 contraction, dosages, an overflowed list).
 struct CorrLayout { int perWarp, oS0, oStage, oQueue; };
@@ -274,7 +275,7 @@ template <bool PACKED, int NT2>
 __global__ void __launch_bounds__(256, 2)
 missing_corr_kernel(GtDesignDev D, const void *__restrict__ geno, long long pitch, int n_snps,
                     int *__restrict__ counts, const uint2 *__restrict__ mrec, int rcap,
-                    const int *__restrict__ mcount, double *__restrict__ corr) {
+                    const int *__restrict__ mcount, double *__restrict__ corrT, long long ldc) {
     extern __shared__ __align__(16) double sm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int snp = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -295,8 +296,11 @@ missing_corr_kernel(GtDesignDev D, const void *__restrict__ geno, long long pitc
         D, rowp, S0, stage, queue, lane, mrec ? mrec + (long long)snp * rcap : nullptr, mA);
     // the tcgen05 contraction leaves the missing count to this kernel
     if (mrec && lane == 0) counts[(long long)snp * 4 + 2] = n_listed;
-    double *out = corr + (long long)snp * L * L;
-    for (int t = lane; t < L * L; t += 32) out[t] = -S0[t];
+    // upper triangle, SoA over the markers: entry (a <= b) at [a L - a (a - 1) / 2 + (b - a)][snp]
+    for (int t = lane; t < L * L; t += 32) {
+        const int a = t / L, b = t % L;
+        if (a <= b) corrT[(long long)(a * L - a * (a - 1) / 2 + (b - a)) * ldc + snp] = -S0[t];
+    }
 }
 
 }  // namespace gtk

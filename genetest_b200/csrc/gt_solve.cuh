@@ -151,13 +151,13 @@ __device__ __forceinline__ void solve_write_fail(double *out, int *iout, long lo
     }
 }
 
-// corr[snp][L*L] = sum over the missing samples of v v' (K3a), read only for
-// markers with missing genotypes.
+// corrT[entry][snp] = upper triangle of the sum over the missing samples of v v'
+// (K3a), read only for markers with missing genotypes.
 template <int GW>
 __global__ void __launch_bounds__(256)
 linear_solve_kernel(GtDesignDev D, int n_snps, const double *__restrict__ S,
                     const int *__restrict__ counts, const double *__restrict__ gsum,
-                    const double *__restrict__ corr, double *__restrict__ out,
+                    const double *__restrict__ corrT, long long ldc, double *__restrict__ out,
                     int *__restrict__ iout, long long ostride) {
     extern __shared__ __align__(16) double sm[];
     const int lane = threadIdx.x & 31;
@@ -181,8 +181,13 @@ linear_solve_kernel(GtDesignDev D, int n_snps, const double *__restrict__ S,
 
     const int n_miss = counts[(long long)snp * 4 + 2];
     if (n_miss > 0) {
-        const double *cs = corr + (long long)snp * L * L;
-        for (int t = gl; t < L * L; t += GW) S0[t] = D.FF0[t] - cs[t];
+        // upper triangle, SoA over the markers (the 16 markers of a CTA share the sectors)
+        const double *cs = corrT + snp;
+        for (int t = gl; t < L * L; t += GW) {
+            const int a = t / L, b = t % L;
+            const int lo = a < b ? a : b, hi = a < b ? b : a;
+            S0[t] = D.FF0[t] - __ldg(cs + (long long)(lo * L - lo * (lo - 1) / 2 + (hi - lo)) * ldc);
+        }
     } else {
         for (int t = gl; t < L * L; t += GW) S0[t] = D.FF0[t];
     }
