@@ -147,25 +147,35 @@ def _cpu_init(model, y, C, names):
         pass
     from oracle import gwas as og
     _CPU.update(model=base_model(model), y=y, C=C, names=names, og=og,
-                interaction=interaction_of(model))
+                interaction=interaction_of(model),
+                missing=WORKLOADS[model]["missing"])
 
 
 def _cpu_work(args):
+    """Returns (markers done, seconds spent in the fits): the synthetic
+    genotype rows are drawn outside the timed part."""
     seed, count = args
     og = _CPU["og"]
     rng = np.random.default_rng(seed)
     n = _CPU["C"].shape[0]
-    done = 0
-    for _ in range(count):
-        maf = rng.uniform(0.05, 0.5)
-        g = rng.binomial(2, maf, n).astype(float)
-        g[rng.random(n) < 0.01] = np.nan
-        y = _CPU["y"]
-        og.gwas_one(_CPU["model"], y if y.ndim == 2 else y[:, None],
-                    _CPU["C"], _CPU["names"], g,
-                    interaction=_CPU["interaction"])
-        done += 1
-    return done
+    y = _CPU["y"]
+    y = y if y.ndim == 2 else y[:, None]
+    done, spent = 0, 0.0
+    chunk = 8
+    while done < count:
+        rows = []
+        for _ in range(min(chunk, count - done)):
+            maf = rng.uniform(0.05, 0.5)
+            g = rng.binomial(2, maf, n).astype(float)
+            g[rng.random(n) < _CPU["missing"]] = np.nan
+            rows.append(g)
+        t0 = time.perf_counter()
+        for g in rows:
+            og.gwas_one(_CPU["model"], y, _CPU["C"], _CPU["names"], g,
+                        interaction=_CPU["interaction"])
+        spent += time.perf_counter() - t0
+        done += len(rows)
+    return done, spent
 
 
 def cpu_throughput(model, y, C, names, n_snps, cores, pool=None):
@@ -177,9 +187,11 @@ def cpu_throughput(model, y, C, names, n_snps, cores, pool=None):
                                            (model, y, C, names))
     per = max(1, n_snps // cores)
     jobs = [(SEED + 17 * i, per) for i in range(cores)]
-    t0 = time.perf_counter()
-    done = sum(pool.map(_cpu_work, jobs))
-    dt = time.perf_counter() - t0
+    res = pool.map(_cpu_work, jobs)
+    done = sum(r[0] for r in res)
+    # every process fits its share concurrently: the job takes as long as
+    # the slowest one spends fitting (drawing the rows is not counted)
+    dt = max(r[1] for r in res)
     if own:
         pool.close()
     return done / dt, done, dt
@@ -200,13 +212,12 @@ def run_reference(args, rank, world):
     for _ in range(args.warmup):
         cpu_throughput(args.model, y, C, names, max(cores, per_step // 4),
                        cores, pool)
-    t0 = time.perf_counter()
-    total = 0
+    total, dt = 0, 0.0
     for _ in range(args.steps):
-        _, done, _ = cpu_throughput(args.model, y, C, names, per_step, cores,
-                                    pool)
+        _, done, step_dt = cpu_throughput(args.model, y, C, names, per_step,
+                                          cores, pool)
         total += done
-    dt = time.perf_counter() - t0
+        dt += step_dt
     pool.close()
     value = total / dt
     sample = ("{} SNPs per step of the same synthetic workload, oracle port "
@@ -229,6 +240,136 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+
+def flops_per_snp(workload, n, p, mean_iter):
+    """FP64 work of one marker."""
+    model = base_model(workload)
+    if workload == "linear_gxe":
+        # (g, g w) against [q, y, 1, w] and (g^2) against [1, w, w^2]
+        return 2.0 * n * (2 * (p + 1) + 3)
+    if model == "linear":
+        return 2.0 * n * (p + 2)              # contraction columns (k+2) + g^2
+    if model == "logistic":
+        # n (p(p+1) + 4p + 40) per IRLS pass, start pass included
+        return n * (p * (p + 1) + 4 * p + 40.0) * (mean_iter + 1.0)
+    # n (p(p+1) + 4p + 30) per pass over the samples; two passes per Newton
+    # step (risk-set totals, then score + Hessian) + the final one
+    return n * (p * (p + 1) + 4 * p + 30.0) * (2.0 * mean_iter + 2.0)
+
+
+def set_workload_design(eng, workload, n, rng_seed):
+    w = WORKLOADS[workload]
+    y, C, names = make_design(workload, n, w["k_cov"], np.random.default_rng(rng_seed))
+    pos = np.random.default_rng(rng_seed + 1).permutation(n).astype(np.int32)
+    model = base_model(workload)
+    if model == "coxph":
+        eng.set_design(model, y[:, 0], C, event=y[:, 1], sample_pos=pos, n_file=n)
+    else:
+        eng.set_design(model, y, C, sample_pos=pos, n_file=n,
+                       W=C[:, [0]] if workload == "linear_gxe" else None)
+    return y, C, names
+
+
+def measure_side_workload(eng, torch, dist, rank, world, workload, steps,
+                          warmup, peaks, snps=None, cpu=True):
+    """One of the other BASELINE configs (or the strong-scaling shard of config
+    2) on this rank's GPU: device-resident throughput (CUDA events, max over
+    ranks, every rank its own shard, no gather), the FP64 / HBM roofline of its
+    dominant kernel, the end-to-end figure through gt_run_packed_host and a
+    small CPU sample."""
+    w = WORKLOADS[workload]
+    n = w["n"]
+    snps = snps or w["snps"]
+    y, C, names = set_workload_design(eng, workload, n, SEED)
+    packed = eng.synth_packed(n, snps, seed=SEED + 1000 * rank + 7,
+                              missing_rate=w["missing"])
+    pitch = packed.stride(0)
+    out, iout = eng.alloc_results(snps)
+    for _ in range(warmup):
+        eng.run_packed_dev(packed, snps, pitch, out, iout)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    eng.enable_timing(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        eng.run_packed_dev(packed, snps, pitch, out, iout)
+    ev1.record()
+    torch.cuda.synchronize()
+    eng.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    kms, klaunches, all_launches = eng.kernel_time()
+    breakdown = eng.kernel_breakdown()
+    eng.enable_timing(False)
+    # end to end with host buffers
+    e2e_snps = min(snps, 65536)
+    hp = torch.empty((e2e_snps, (n + 3) // 4), dtype=torch.uint8).pin_memory()
+    hp.copy_(packed[:e2e_snps, :(n + 3) // 4].cpu())
+    ho = torch.empty((eng.n_fields, e2e_snps), dtype=torch.float64).pin_memory()
+    hi = torch.empty((4, e2e_snps), dtype=torch.int32).pin_memory()
+    eng.run_packed_host(hp.numpy(), ho.numpy(), hi.numpy())
+    t0 = time.perf_counter()
+    for _ in range(2):
+        eng.run_packed_host(hp.numpy(), ho.numpy(), hi.numpy())
+    e2e_dt = (time.perf_counter() - t0) / 2
+    if world > 1:
+        t = torch.tensor([ms, e2e_dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_dt = float(t[0].item()), float(t[1].item())
+    p = eng.n_params
+    mean_iter = float(iout[3].double().mean().item())
+    n_ok = int((iout[0] == 0).sum().item())
+    kernel_ms = kms / max(1, klaunches)
+    per_launch = snps * steps / max(1, klaunches)
+    fl = flops_per_snp(workload, n, p, mean_iter)
+    achieved_tf = per_launch * fl / (kernel_ms * 1e-3) / 1e12
+    bytes_per_snp = (n + 3) // 4 + 8 * (6 * p + 5) + 8
+    achieved_gbs = per_launch * bytes_per_snp / (kernel_ms * 1e-3) / 1e9
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    model = base_model(workload)
+    if workload == "linear":
+        roof = {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved_gbs / hbm_peak, "kernel": "contract_tc2_kernel"}
+    else:
+        # interaction designs run the FP64 FMA contraction, the iterative models
+        # accumulate with FP64 tensor-core MMAs: each against its own measured peak
+        fma = workload == "linear_gxe"
+        peak = eng.fp64_peak_tflops() if fma else eng.dmma_peak_tflops()
+        roof = {"bound": "fp64", "achieved": achieved_tf, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved_tf / peak if peak else None,
+                "peak_source": "measured FP64 {} rate (gt_measure_{}_peak)".format(
+                    "FMA" if fma else "m8n8k4 MMA", "fp64" if fma else "dmma"),
+                "kernel": eng.dominant_kernel(), "flop_per_snp": fl,
+                "mean_iterations": mean_iter,
+                "hbm": {"achieved_gbs": achieved_gbs, "frac": achieved_gbs / hbm_peak}}
+    roof.update({"kernel_ms_per_launch": kernel_ms, "kernel_share_of_step": kms / ms,
+                 "step_breakdown_ms": {k: v / steps for k, v in breakdown.items()}})
+    res = {
+        "workload": w["name"], "model": workload, "samples": n, "params": p,
+        "snps_per_gpu_per_step": snps, "steps": steps,
+        "value": world * snps * steps / (ms * 1e-3), "unit": "SNP-tests/s",
+        "ms_per_step": ms / steps, "ok_markers_last_step": n_ok,
+        "roofline": roof,
+        "e2e": {"value": world * e2e_snps / e2e_dt, "unit": "SNP-tests/s",
+                "h2d_bytes_per_step": int(hp.numel()),
+                "d2h_bytes_per_step": int(ho.numel() * 8 + hi.numel() * 4),
+                "snps_per_step": e2e_snps,
+                "call": "gt_run_packed_host (pinned host buffers)"},
+        "gpu_launches": int(all_launches),
+    }
+    if cpu and rank == 0:
+        cores = len(os.sched_getaffinity(0)) or 1
+        cpu_snps = cores * {"linear": 32, "logistic": 12, "coxph": 1}[model]
+        v, done, dt = cpu_throughput(workload, y, C, names, cpu_snps, cores)
+        res["cpu_baseline"] = {"value": v, "unit": "SNP-tests/s", "cores": cores, "kind": "port",
+                               "sample": "{} SNPs in {:.1f} s of fitting, oracle port, {} processes x 1 "
+                                         "BLAS thread".format(done, dt, cores)}
+    del packed, out, iout
+    torch.cuda.empty_cache()
+    return res
+
+
 # --------------------------------------------------------------------------
 def run_ours(args, rank, world, local_rank):
     import torch
@@ -244,6 +385,9 @@ def run_ours(args, rank, world, local_rank):
     w = WORKLOADS[args.model]
     n = args.samples or w["n"]
     snps = args.snps or w["snps"]
+    if args.scaling == "strong":
+        # the configuration as named: the SNPs of ONE job split over the GPUs
+        snps = (snps + world - 1) // world
     rng = np.random.default_rng(SEED)
     y, C, names = make_design(args.model, n, w["k_cov"], rng)
 
@@ -360,19 +504,41 @@ def run_ours(args, rank, world, local_rank):
         e2e_dt = float(t.item())
     e2e_value = world * e2e_snps * e2e_steps / e2e_dt
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
+    # everything the main line needs from the engine, before other designs replace this one
+    p = eng.n_params
+    mean_iter = float(iout[3].double().mean().item())
+    dominant = eng.dominant_kernel()
+    fp64_peak = eng.fp64_peak_tflops()
+    dmma_peak = eng.dmma_peak_tflops()
+    del packed, bufs, out, iout, gathered
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE configs and the strong-scaling shard, same run ----
+    others, strong = [], None
+    if not args.no_side:
+        side_steps = max(2, min(args.steps, 3))
+        if workload == "linear" and args.scaling == "weak":
+            strong = measure_side_workload(
+                eng, torch, dist, rank, world, "linear", side_steps, 2, peaks,
+                snps=(w["snps"] + world - 1) // world, cpu=False)
+            strong["scaling"] = "strong"
+            strong["snps_total_per_step"] = w["snps"]
+        for wl in ("logistic", "linear_gxe", "coxph"):
+            if wl != workload:
+                others.append(measure_side_workload(
+                    eng, torch, dist, rank, world, wl, side_steps, 2, peaks))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured" if "hbm_gbs" in peaks else "fallback"
-    p = eng.n_params
     bytes_per_snp = (n + 3) // 4 + 8 * (6 * p + 5) + 8
     per_launch_snps = snps * args.steps / max(1, klaunches)
     kernel_ms = kms / max(1, klaunches)
@@ -383,25 +549,13 @@ def run_ours(args, rank, world, local_rank):
         traffic = prof.get(workload, {}).get("dram_bytes_per_launch")
     except Exception:
         pass
-    fp64_peak = eng.fp64_peak_tflops()
-    dmma_peak = eng.dmma_peak_tflops()
-    mean_iter = float(iout[3].double().mean().item())
-    if workload == "linear_gxe":
-        # (g, g w) against [q, y, 1, w] and (g^2) against [1, w, w^2]
-        flop_per_snp = 2.0 * n * (2 * (p + 1) + 3)
-    elif args.model == "linear":
-        flop_per_snp = 2.0 * n * (p + 2)          # contraction columns (k+2) + g^2
-    elif args.model == "logistic":
-        # SURVEY 8(d): n (p(p+1) + 4p + 40) per IRLS pass, start pass included
-        flop_per_snp = n * (p * (p + 1) + 4 * p + 40.0) * (mean_iter + 1.0)
-    else:
-        # n (p(p+1) + 4p + 30) per pass over the samples; two passes per
-        # Newton step (risk-set totals, then score + Hessian) + the final one
-        flop_per_snp = n * (p * (p + 1) + 4 * p + 30.0) * (2.0 * mean_iter + 2.0)
+    flop_per_snp = flops_per_snp(workload, n, p, mean_iter)
     fp64_achieved = per_launch_snps * flop_per_snp / (kernel_ms * 1e-3) / 1e12
     if workload == "linear" and args.contract == "tc":
-        # exact fixed point on the int8 tensor cores: 8 digit planes per column
-        ops_per_snp = 2.0 * n * 8 * (p)
+        # exact fixed point on the int8 tensor cores: 7 digit planes for each of the
+        # p - 1 columns that are not derived from the constant + the plane of ones,
+        # rounded up to the N = 16 * ceil(.) columns of the MMA
+        ops_per_snp = 2.0 * n * 16 * ((7 * (p - 1) + 1 + 15) // 16)
         compute = {"pipe": "tcgen05 kind::i8",
                    "achieved_tops": per_launch_snps * ops_per_snp /
                    (kernel_ms * 1e-3) / 1e12,
@@ -428,7 +582,7 @@ def run_ours(args, rank, world, local_rank):
         "metric": "SNP-tests/sec", "value": value, "unit": "SNP-tests/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": w["name"], "model": workload, "samples": n,
                    "covariates": w["k_cov"] + 1, "params": p,
@@ -442,9 +596,9 @@ def run_ours(args, rank, world, local_rank):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak,
                      "unit": "GB/s", "frac": achieved / hbm_peak,
                      "traffic": traffic, "peak_source": peak_src,
-                     "kernel": ("contract_tc_kernel" if (workload == "linear" and
+                     "kernel": ("contract_tc2_kernel" if (workload == "linear" and
                                                         args.contract == "tc")
-                                else eng.dominant_kernel()),
+                                else dominant),
                      "kernel_ms_per_launch": kernel_ms,
                      "kernel_share_of_step": kms / ms,
                      "step_breakdown_ms": {k: v / args.steps
@@ -465,27 +619,31 @@ def run_ours(args, rank, world, local_rank):
         "clocks": clocks,
     }
     if workload != "linear":
-        # the iterative models (and the FP64 contraction of interaction
-        # designs) are bound by the FP64 (tensor) pipe, not by HBM:
+        # the iterative models are bound by the FP64 tensor pipe, the FP64
+        # contraction of interaction designs by the FP64 FMA pipe, not by HBM:
         # report that roofline, keep the HBM figures beside it
         r = line["roofline"]
+        fma = workload == "linear_gxe"
+        pk = fp64_peak if fma else dmma_peak
         r.update({"bound": "tensor", "unit": "TFLOP/s",
-                  "achieved": fp64_achieved, "peak": dmma_peak,
-                  "frac": fp64_achieved / dmma_peak if dmma_peak else None,
-                  "peak_source": "measured FP64 m8n8k4 MMA rate "
-                                 "(gt_measure_dmma_peak; not in "
-                                 "MEASURED_PEAKS.json)",
+                  "achieved": fp64_achieved, "peak": pk,
+                  "frac": fp64_achieved / pk if pk else None,
+                  "peak_source": "measured FP64 {} rate (gt_measure_{}_peak; "
+                                 "not in MEASURED_PEAKS.json)".format(
+                                     "FMA" if fma else "m8n8k4 MMA",
+                                     "fp64" if fma else "dmma"),
                   "hbm": {"achieved_gbs": achieved, "peak_gbs": hbm_peak,
                           "frac": achieved / hbm_peak}})
+    if strong is not None:
+        line["strong_scaling"] = strong
+    if others:
+        line["other_workloads"] = others
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
-    # keep stdout to the one JSON line (NCCL_DEBUG=VERSION prints there)
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
-        os.environ["NCCL_DEBUG"] = "WARN"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -497,6 +655,11 @@ def main():
     ap.add_argument("--contract", default="tc", choices=["tc", "fp64"],
                     help="linear contraction kernel: tcgen05 int8 or FP64")
     ap.add_argument("--e2e-snps", type=int, default=65536)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every GPU its own full shard; strong: the SNPs "
+                         "of one job (500k for config 2) split over the GPUs")
+    ap.add_argument("--no-side", action="store_true",
+                    help="skip the other configs / the strong-scaling shard")
     ap.add_argument("--cpu-snps", type=int, default=0)
     ap.add_argument("--ref-snps", type=int, default=0)
     args = ap.parse_args()

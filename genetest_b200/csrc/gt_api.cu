@@ -38,6 +38,7 @@ struct gt_engine {
     int cs_nv = 0;             // columns the streaming correction kernel gathers (0: not available)
     bool use_tc = true;        // lean linear designs run on the tcgen05 int8 contraction
     bool use_stream_corr = true;   // ... and their corrections on the streaming kernel
+    int cox_maxiter = 100;     // Newton step limit of the Cox model (statsmodels' default)
     int tc_dbg = 0;
     int tc_N = 0;              // 0: the design does not run on the tcgen05 kernel
     gtk::Tc2Params tc{};       // constant part of the kernel parameters
@@ -406,6 +407,7 @@ int gt_engine_set_option(gt_engine *e, const char *name, int value) {
     if (std::strcmp(name, "contract_tc") == 0) { e->use_tc = value != 0; return 0; }
     if (std::strcmp(name, "tc_debug") == 0) { e->tc_dbg = value; return 0; }
     if (std::strcmp(name, "stream_corrections") == 0) { e->use_stream_corr = value != 0; return 0; }
+    if (std::strcmp(name, "cox_maxiter") == 0) { e->cox_maxiter = value > 0 ? value : 100; return 0; }
     if (std::strcmp(name, "host_chunk") == 0) { e->host_chunk = (int)std::max<int64_t>(0, value); return 0; }
     return fail(GT_E_ARG, "gt_engine_set_option: unknown option '%s'", name);
 }
@@ -988,6 +990,7 @@ static int run_any(gt_engine *e, const void *geno, int64_t pitch, bool packed, i
     if (!packed && !e->identity_pos)
         return fail(GT_E_STATE, "dosage rows are aligned to the design rows: set the design without sample_pos / n_file");
     gtk::IterDesignDev T = e->T;
+    T.newton_maxiter = e->cox_maxiter;
     if (e->sex_maf) {
         int rc;
         if ((rc = e->dMafO.reserve((size_t)n_snps * 8))) return rc;

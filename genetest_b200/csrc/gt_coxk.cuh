@@ -482,8 +482,10 @@ cox_newton_one(const IterDesignDev &T, const void *__restrict__ geno, long long 
         __syncwarp();
         niter += 1;
         if (!(worst == worst)) { status = GT_NAN_PVALUE; break; }
+        // statsmodels warns (-> StatsError, survival.py:87-88) whenever the step count
+        // reaches maxiter, also when that very step met the tolerance
+        if (niter >= T.newton_maxiter) { status = GT_NO_CONVERGENCE; break; }
         if (!(worst > 1e-8)) { final_eval = true; continue; }
-        if (niter >= 100) { status = GT_NO_CONVERGENCE; break; }
     }
     if (status != GT_OK) { write_fail(status, flip, maf, nan(""), niter); return; }
 

@@ -42,6 +42,7 @@ struct IterDesignDev {
     const double *colmax;   // [p] coxph: max |x| of every design column (q, g, g w)
     const double *maf_o;    // sex-aware MAF / flip per marker of the launch, or NULL
     const int *flip_o;
+    int newton_maxiter;     // coxph: PHReg.fit(maxiter=100); engine option "cox_maxiter" (tests)
 };
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {

@@ -355,7 +355,10 @@ linear_solve_kernel(GtDesignDev D, int n_snps, const double *__restrict__ S,
         __syncwarp(gmask);
         double emax, emin;
         gt_group_jacobi_extremes<GW>(G, p, p, gl, gmask, &emax, &emin);
-        double cond = (emin > 0.0) ? sqrt(emax / emin) : INFINITY;
+        // statsmodels: condition_number = sqrt(max / min) of eigvalsh(X'X): a zero minimum
+        // gives inf, a (rounding) negative one NaN -- and NaN passes the `> threshold` test,
+        // so that marker fails on the eigenvalue check below instead (linear.py:51-61)
+        double cond = (emin > 0.0) ? sqrt(emax / emin) : (emin == 0.0 ? INFINITY : nan(""));
         if (D.degenerate) cond = INFINITY;
         if (cond > D.cond_t) {
             solve_write_fail<GW>(out, iout, ostride, snp, nf, GT_COND_LARGE, nj, flip, maf, cond, gl);

@@ -112,7 +112,12 @@ int gt_engine_synchronize(gt_engine *e);
  * designs without interaction on the tcgen05 int8 tensor-core kernel (exact
  * fixed point) instead of the FP64 kernel.  "host_chunk" = n: markers per
  * stage of the copy-in / compute / copy-back pipeline of the *_host entry
- * points (0 = automatic).  "tc_debug": tuning probes of the tcgen05 kernel. */
+ * points (0 = automatic).  "stream_corrections" = 1 (default): missing-sample
+ * corrections of those designs on the streaming thread-per-SNP kernel instead
+ * of the gather kernel.  "cox_maxiter" = n: Newton step limit of the Cox model
+ * (PHReg.fit's maxiter, default 100; reaching it is "Maximum Likelihood
+ * optimization failed to converge", survival.py:87-88).  "tc_debug": tuning
+ * probes of the tcgen05 kernel. */
 int gt_engine_set_option(gt_engine *e, const char *name, int value);
 
 /* Replaces the per-worker setup of _gwas_worker (analysis.py:68-106) and the

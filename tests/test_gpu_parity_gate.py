@@ -1,0 +1,162 @@
+"""SURVEY 8(d) parity gate at the BASELINE shapes: 2,000-marker stratified
+samples (lowest MAF, most missing genotypes, random draw) of configs 2, 3 and 4
+-- 256 markers for Cox, whose oracle fits ~0.5 markers / s / core -- against the
+CPU oracle, with the STRICT comparison (plain relative error on coef, std_err,
+CI bounds, t / z and p: 1e-8 linear, 1e-6 logistic / Cox), plus the status
+branches no other GPU test reaches (``smallest eigenvalue is small``,
+``Maximum Likelihood optimization failed to converge``).
+
+The oracle runs one process per host core (``run_oracle_packed``); the rows
+travel as 2-bit packs."""
+
+import numpy as np
+import pytest
+
+from genetest_b200.genotypes import pack_rows
+
+from gpu_support import (compare, run_oracle, run_oracle_packed,
+                         stratified_sample, synth_design, synth_genotypes)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine():
+    from genetest_b200.engine import Engine
+    eng = Engine(0)
+    yield eng
+    eng.close()
+
+
+def _cox_data(rng, n, C):
+    t_event = rng.exponential(1.0 / np.exp(0.1 * C[:, 0]))
+    t_cens = rng.exponential(2.0, n)
+    return np.minimum(t_event, t_cens), (t_event <= t_cens).astype(float)
+
+
+@pytest.mark.parametrize("config", ["2-linear", "3-logistic", "4-linear-gxe",
+                                    "5-coxph"])
+def test_stratified_sample_strict_parity(engine, config):
+    rng = np.random.default_rng(20261020)
+    inter, W, event = None, None, None
+    if config == "2-linear":
+        model, n, n_snps, miss, tol = "linear", 100000, 32768, 0.01, 1e-8
+        picks = (500, 500, 1000)
+        C, names = synth_design(rng, n, k_extra=8)
+        y = 0.1 * C[:, 0] + rng.normal(size=n) + 10.0
+        Y = y[:, None]
+    elif config == "3-logistic":
+        model, n, n_snps, miss, tol = "logistic", 50000, 16384, 0.0, 1e-6
+        picks = (700, 0, 1300)
+        C, names = synth_design(rng, n, k_extra=8)
+        y = (rng.random(n) < 1 / (1 + np.exp(0.5 - 0.2 * C[:, 0]))).astype(float)
+        Y = y[:, None]
+    elif config == "4-linear-gxe":
+        model, n, n_snps, miss, tol = "linear", 100000, 16384, 0.01, 1e-8
+        picks = (500, 500, 1000)
+        C, names = synth_design(rng, n, k_extra=8)
+        y = 0.1 * C[:, 0] + rng.normal(size=n)
+        Y = y[:, None]
+        inter, W = {"I:age": ["age"]}, C[:, [0]]
+    else:
+        model, n, n_snps, miss, tol = "coxph", 20000, 4096, 0.0, 1e-6
+        picks = (96, 0, 160)
+        C, names = synth_design(rng, n, k_extra=8)
+        C, names = C[:, :-1], names[:-1]
+        y, event = _cox_data(rng, n, C)
+        Y = np.column_stack((y, event))
+    pos = rng.permutation(n).astype(np.int32)
+    engine.set_design(model, y, C, W=W, event=event, sample_pos=pos, n_file=n)
+    dev = engine.synth_packed(n, n_snps, seed=23, maf_lo=0.005, maf_hi=0.5,
+                              missing_rate=miss)
+    out, iout = engine.run_packed_dev(dev, n_snps)
+    res = engine.fetch(out, iout)
+    pick = stratified_sample(res, rng, *picks)
+    packed = dev[:, :(n + 3) // 4].cpu().numpy()[pick]
+    sub = type(res)(res.out[:, pick], res.iout[:, pick], res.n_params)
+    oracle = run_oracle_packed(model, Y, C, names, packed, n, pos=pos,
+                               interaction=inter)
+    problems, worst, n_ok = compare(model, sub, oracle, names,
+                                    inter_keys=list(inter or ()), rtol=tol,
+                                    strict=True)
+    assert not problems, problems[:10]
+    assert n_ok >= 0.99 * len(pick)
+    print("config {}: {} markers vs oracle (strict), worst rel err {:.2e}".format(
+        config, n_ok, worst))
+
+
+def test_linear_smallest_eigenvalue_branch(engine):
+    """StatsLinear raises ``smallest eigenvalue is small, {x}`` when the
+    condition number passes its gate but an eigenvalue of X'X is below
+    ``eigenvals_t`` (reference linear.py:58-61): a tiny-scale covariate and a
+    condition threshold that lets it through."""
+    rng = np.random.default_rng(5)
+    n, n_snps = 2000, 64
+    C, names = synth_design(rng, n, k_extra=1)
+    C[:, 2] *= 1e-8                       # eigenvalue ~ n * 1e-16 << 1e-10
+    G = synth_genotypes(rng, n_snps, n, missing=0.01)
+    y = 0.2 * C[:, 0] + rng.normal(size=n)
+    kwargs = dict(condition_value_t=1e30, eigenvals_t=1e-10)
+    engine.set_design("linear", y, C, **kwargs)
+    res = engine.run_packed_host(pack_rows(G))
+    oracle = run_oracle("linear", y[:, None], C, names, G, model_kwargs=kwargs)
+    assert all(st == "failed" and msg.startswith("smallest eigenvalue is small")
+               for st, msg in oracle)
+    assert (res.status == 4).all(), res.status
+    # the offending eigenvalue is reported; the reference prints it from an SVD
+    want = np.array([float(msg.split(", ")[1]) for _, msg in oracle])
+    np.testing.assert_allclose(res.aux, want, rtol=1e-6)
+    # ... and a looser eigenvalue threshold lets the same markers through
+    engine.set_design("linear", y, C, condition_value_t=1e30, eigenvals_t=1e-20)
+    res = engine.run_packed_host(pack_rows(G))
+    oracle = run_oracle("linear", y[:, None], C, names, G,
+                        model_kwargs=dict(condition_value_t=1e30, eigenvals_t=1e-20))
+    problems, worst, n_ok = compare("linear", res, oracle, names, rtol=1e-6)
+    assert not problems and n_ok == n_snps, problems[:5]
+
+
+def test_coxph_no_convergence_branch(engine):
+    """``Maximum Likelihood optimization failed to converge`` (survival.py:87-88):
+    PHReg's Newton loop stops at ``maxiter`` steps and statsmodels warns whenever the
+    step count reaches it -- also when that very step met the tolerance.  On real data
+    the default of 100 is out of reach (a diverging fit overflows first and ends as
+    ``Inference did not converge.``), so the limit is lowered through the engine
+    option and through the oracle's argument: one step short of what a marker needs,
+    exactly what it needs (still a failure), and one more (a fit)."""
+    from oracle import sm_port
+    rng = np.random.default_rng(9)
+    n, n_snps = 3000, 48
+    C, names = synth_design(rng, n, k_extra=2)
+    C, names = C[:, :-1], names[:-1]
+    tte, event = _cox_data(rng, n, C)
+    G = synth_genotypes(rng, n_snps, n, missing=0.01)
+    Y = np.column_stack((tte, event))
+    engine.set_design("coxph", tte, C, event=event)
+    try:
+        full = engine.run_packed_host(pack_rows(G))
+        assert (full.status == 0).all()
+        need = full.niter.copy()                # Newton steps every marker takes
+        assert need.min() >= 2
+        for delta, ok in ((-1, False), (0, False), (1, True)):
+            for it in np.unique(need):
+                engine.set_option("cox_maxiter", int(it + delta))
+                res = engine.run_packed_host(pack_rows(G))
+                sel = need == it
+                if ok:
+                    assert (res.status[sel] == 0).all()
+                    np.testing.assert_array_equal(res.out[:, sel].view(np.int64),
+                                                  full.out[:, sel].view(np.int64))
+                else:
+                    assert (res.status[sel] == 8).all(), (it, delta, res.status[sel])
+        # the oracle agrees on both sides of the limit for one marker
+        j = 0
+        ok = ~np.isnan(G[j])
+        g = G[j][ok]
+        if np.mean(g) / 2 > 0.5:
+            g = 2 - g
+        X = np.column_stack((C[ok], g))
+        with pytest.raises(sm_port.OracleConvergence):
+            sm_port.phreg_efron_newton(tte[ok], event[ok], X, maxiter=int(need[j]))
+        sm_port.phreg_efron_newton(tte[ok], event[ok], X, maxiter=int(need[j]) + 1)
+    finally:
+        engine.set_option("cox_maxiter", 100)
