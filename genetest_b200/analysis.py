@@ -35,7 +35,9 @@ PARAM_FIELDS = ("coef", "std_err", "lower_ci", "upper_ci", "t_value",
                 "p_value")
 
 #: markers per engine call (bounds host staging memory)
-BATCH_SNPS = 65536
+# markers per call of the host pipeline: two waves of the tcgen05 contraction
+# (148 CTAs x 512 SNP rows); the engine splits it into half-wave stages
+BATCH_SNPS = 151552
 
 
 def _missing(y, X):
@@ -340,6 +342,20 @@ class ResultBlock(object):
         return out
 
 
+def _takes_blocks(subscriber):
+    """Whole result blocks go to a sink only when its ``handle`` -- the
+    reference's one extension point (subscribers.py:49) -- is a stock
+    implementation of this package: a user subclass that overrides ``handle``
+    keeps receiving one dictionary per marker."""
+    cls = type(subscriber)
+    if not hasattr(cls, "handle_block"):
+        return False
+    for base in cls.__mro__:
+        if "handle" in base.__dict__:
+            return base.__module__ == subscribers_module.__name__
+    return False
+
+
 def _dispatch_block(block, subscribers, messages):
     """Failures -> ``messages``; successes -> the subscribers: whole blocks
     for sinks that define ``handle_block``, one dictionary per marker for the
@@ -352,7 +368,7 @@ def _dispatch_block(block, subscribers, messages):
             messages["failed"].append((name, reason))
     dict_sinks = []
     for subscriber in subscribers:
-        if hasattr(subscriber, "handle_block"):
+        if _takes_blocks(subscriber):
             try:
                 subscriber.handle_block(block)
             except KeyError as e:
@@ -499,9 +515,11 @@ def _execute_gwas(genotypes, modelspec, subscribers, y, X, variant_predicates,
 
     rank, world = sharding.rank_world()
     eng = get_engine(sharding.local_device())
-    names_only = all(isinstance(f, _name_filter_type())
-                     for f in variant_predicates)
-    packed_path = hasattr(genotypes, "packed") and names_only
+    # the stock NameFilter / MAFFilter are evaluated on the packed rows (the
+    # names against the .bim table, the MAF on the device); a subclass or any
+    # other callable gets the decoded markers, one at a time, like the reference
+    stock = all(type(f) in _stock_filter_types() for f in variant_predicates)
+    packed_path = hasattr(genotypes, "packed") and stock
     if packed_path:
         # raw .bed rows go to the GPU as they are: the engine aligns them
         eng.set_design(model, y_main, C, W=W, event=event,
@@ -562,17 +580,26 @@ def _execute_gwas(genotypes, modelspec, subscribers, y, X, variant_predicates,
     logger.info("Analysis completed")
 
 
-def _name_filter_type():
-    from .modelspec.predicates import NameFilter
-    return NameFilter
+def _stock_filter_types():
+    from .modelspec.predicates import MAFFilter, NameFilter
+    return (NameFilter, MAFFilter)
 
 
 def _packed_blocks(reader, eng, predicates, messages, rank, world):
-    """Fast path: the reader exposes SNP-major 2-bit rows (PLINK .bed)."""
+    """Fast path: the reader exposes SNP-major 2-bit rows (PLINK .bed).
+    ``NameFilter`` is applied to the .bim table before anything is read;
+    ``MAFFilter`` (predicates.py:33-57: MAF over ALL samples of the file)
+    is evaluated on the device next to the fit, and the markers it rejects
+    are dropped from the block and listed as skipped."""
+    from .modelspec.predicates import MAFFilter, NameFilter
     table = reader.variant_table()
     keep = np.ones(len(table), dtype=bool)
+    maf_min = None
     for f in predicates:
-        keep &= np.array([t[0] in f.extract for t in table], dtype=bool)
+        if type(f) is NameFilter:
+            keep &= np.array([t[0] in f.extract for t in table], dtype=bool)
+        elif type(f) is MAFFilter:
+            maf_min = f.maf if maf_min is None else max(maf_min, f.maf)
     if rank == 0:
         messages["skipped"].extend(
             t[0] for t, k in zip(table, keep) if not k)
@@ -580,16 +607,31 @@ def _packed_blocks(reader, eng, predicates, messages, rank, world):
     lo, hi = sharding.shard_range(len(idx), world, rank)
     idx = idx[lo:hi]
     packed = reader.packed()
+    any_block = False
     for s in range(0, len(idx), BATCH_SNPS):
         sel = idx[s:s + BATCH_SNPS]
         if len(sel) and sel[-1] - sel[0] + 1 == len(sel):
-            rows = packed[sel[0]:sel[-1] + 1]          # contiguous: no copy
+            rows = packed[sel[0]:sel[-1] + 1]          # contiguous: read in place
         else:
             rows = packed[sel]
-        res = eng.run_packed_host(np.ascontiguousarray(rows))
+        file_maf = None
+        if maf_min is not None:
+            file_maf = np.empty(len(sel), dtype=np.float64)
+        res = eng.run_packed_host(rows, file_maf=file_maf)
         meta = [table[i] for i in sel]
+        if maf_min is not None:
+            ok = file_maf >= maf_min                   # NaN (nothing genotyped) -> skipped
+            if not ok.all():
+                messages["skipped"].extend(m[0] for m, k in zip(meta, ok) if not k)
+                from .engine import Results
+                res = Results(np.ascontiguousarray(res.out[:, ok]),
+                              np.ascontiguousarray(res.iout[:, ok]), res.n_params)
+                meta = [m for m, k in zip(meta, ok) if k]
+            if not len(meta):
+                continue
+        any_block = True
         yield res, meta
-    if len(idx) == 0:
+    if not any_block:
         yield None, []
 
 

@@ -47,6 +47,11 @@ struct gt_engine {
     cudaStream_t s_in = nullptr, s_out = nullptr;     // copy streams of the *_host pipeline
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_start = nullptr;
     int host_chunk = 0;        // option "host_chunk": SNPs per pipeline stage (0 = automatic)
+    void *pin[2] = {nullptr, nullptr};   // pinned staging of pageable sources (one per pipeline slot)
+    size_t pin_bytes = 0;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr};
+    double *file_maf_host = nullptr;     // gt_engine_set_file_maf_output
+    DevBuf dFileMaf;
     int contract_idx = -1;
     // sample alignment of the current design; sex-aware MAF (sexual_chromosome=True)
     std::vector<int> pos;
@@ -193,8 +198,45 @@ read_pattern_kernel(const uint8_t *geno, long long pitch, int n_rows, int tpr, i
     if (acc == 0x12345678u) sink[0] = acc;
 }
 
+// MAF of every marker over ALL samples of its file row (what MAFFilter sees:
+// get_maf(snp.genotypes), predicates.py:49 / descriptive.py:19-48): exact class
+// counts, NaN when every genotype is missing.  One warp per marker.
+__global__ void __launch_bounds__(256)
+file_maf_packed_kernel(const uint8_t *__restrict__ geno, long long pitch, int n_snps, int n_file,
+                       double *__restrict__ maf_o) {
+    const int lane = threadIdx.x & 31;
+    const int snp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (snp >= n_snps) return;
+    const uint32_t *row = (const uint32_t *)(geno + (long long)snp * pitch);
+    const int nwords = (n_file + 15) / 16;
+    int het = 0, hom = 0, mis = 0;
+    for (int w = lane; w < nwords; w += 32) {
+        uint32_t x = row[w];
+        const int left = n_file - w * 16;              // samples in this word
+        if (left < 16) x |= 0xFFFFFFFFu << (2 * left);   // the padding reads as 11 (not counted)
+        const uint32_t lo = x & 0x55555555u, hi = (x >> 1) & 0x55555555u;
+        het += __popc(hi & ~lo); hom += __popc(~(lo | hi) & 0x55555555u); mis += __popc(lo & ~hi);
+    }
+    het = gt_warp_sum_int(het); hom = gt_warp_sum_int(hom); mis = gt_warp_sum_int(mis);
+    if (lane == 0) {
+        const int present = n_file - mis;
+        double maf = nan("");
+        if (present > 0) {
+            maf = ((double)(het + 2 * hom) / (double)present) / 2.0;
+            if (maf > 0.5) maf = 1.0 - maf;
+        }
+        maf_o[snp] = maf;
+    }
+}
+
 // ---------------------------------------------------------------------------
 extern "C" {
+
+int gt_engine_set_file_maf_output(gt_engine *e, double *maf_host) {
+    if (!e) return fail(GT_E_ARG, "engine is NULL");
+    e->file_maf_host = maf_host;
+    return 0;
+}
 
 int gt_debug_read_pattern(gt_engine *e, const uint8_t *packed_dev, int64_t pitch, int32_t n_rows,
                           int tpr, int vec, int ctas_per_sm, double *gbs) {
@@ -358,8 +400,12 @@ int gt_engine_destroy(gt_engine *e) {
     for (auto &ev : e->events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     DevBuf *bufs[] = {&e->dE, &e->dMask, &e->dFF0, &e->dR, &e->dRinv, &e->dTq, &e->dIter, &e->dBimg, &e->dScale, &e->dErr, &e->dEi,
                       &e->dS, &e->dCounts, &e->dGsum, &e->dMlist, &e->dMcount, &e->dCorr, &e->dGeno, &e->dOut, &e->dIout,
-                      &e->dSexM, &e->dSexF, &e->dSexRow, &e->dMafO, &e->dFlipO, &e->dCounter};
+                      &e->dSexM, &e->dSexF, &e->dSexRow, &e->dMafO, &e->dFlipO, &e->dCounter, &e->dFileMaf};
     for (DevBuf *b : bufs) b->release();
+    for (int i = 0; i < 2; ++i) {
+        if (e->pin[i]) cudaFreeHost(e->pin[i]);
+        if (e->ev_h2d[i]) cudaEventDestroy(e->ev_h2d[i]);
+    }
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     if (e->s_in) cudaStreamDestroy(e->s_in);
     if (e->s_out) cudaStreamDestroy(e->s_out);
@@ -1064,12 +1110,65 @@ static int run_host(gt_engine *e, const void *src, int64_t src_pitch_bytes, int6
         // pay a partial last wave per chunk: keep their chunks large
         chunk = std::max<int64_t>(chunk, e->model == GT_MODEL_LINEAR ? 8192 : 65536);
         chunk = std::min<int64_t>(chunk, std::max<int64_t>(1024, ((int64_t)512 << 20) / dev_pitch_bytes / 1024 * 1024));
+        // whole half-waves of the tcgen05 contraction (148 CTAs x 128 .. 512 SNP rows)
+        if (packed && e->model == GT_MODEL_LINEAR && e->use_tc && e->tc_N > 0) {
+            const int64_t hw = 148 * (int64_t)tc_rows(e) / 2;
+            if (chunk > hw) chunk = chunk / hw * hw;
+        }
     }
     chunk = std::min<int64_t>(chunk, n_snps);
     int rc;
     if ((rc = e->dGeno.reserve((size_t)dev_pitch_bytes * chunk * 2))) return rc;
     if ((rc = e->dOut.reserve((size_t)nf * n_snps * 8))) return rc;
     if ((rc = e->dIout.reserve((size_t)GT_NUM_IFIELDS * n_snps * 4))) return rc;
+    const bool want_maf = packed && e->file_maf_host != nullptr;
+    if (want_maf && (rc = e->dFileMaf.reserve((size_t)n_snps * 8))) return rc;
+    // A pageable source (an mmap-ed .bed, a numpy array) is staged through two pinned
+    // buffers by a few host threads: cudaMemcpyAsync from pageable memory is a
+    // synchronous, single-threaded bounce copy at a fraction of the link rate.
+    bool stage = false;
+    {
+        cudaPointerAttributes attr;
+        cudaError_t pe = cudaPointerGetAttributes(&attr, src);
+        if (pe != cudaSuccess) { cudaGetLastError(); stage = true; }
+        else stage = attr.type == cudaMemoryTypeUnregistered;
+    }
+    const size_t slot_bytes = (size_t)width_bytes * chunk;
+    if (stage) {
+        if (e->pin_bytes < slot_bytes) {
+            for (int i = 0; i < 2; ++i) { if (e->pin[i]) cudaFreeHost(e->pin[i]); e->pin[i] = nullptr; }
+            e->pin_bytes = 0;
+            for (int i = 0; i < 2; ++i)
+                if (cudaHostAlloc(&e->pin[i], slot_bytes, cudaHostAllocDefault) != cudaSuccess) {
+                    cudaGetLastError();
+                    for (int j = 0; j < 2; ++j) { if (e->pin[j]) cudaFreeHost(e->pin[j]); e->pin[j] = nullptr; }
+                    stage = false;                       // no pinned memory: fall back to the direct copy
+                    break;
+                }
+            if (stage) e->pin_bytes = slot_bytes;
+        }
+        for (int i = 0; i < 2 && stage; ++i)
+            if (!e->ev_h2d[i]) CK(cudaEventCreateWithFlags(&e->ev_h2d[i], cudaEventDisableTiming));
+    }
+    const int n_threads = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
+    auto stage_rows = [&](int64_t c0, int nb, char *dst) {
+        // rows [c0, c0 + nb) -> dst, `width_bytes` each, tightly packed
+        auto work = [&](int t) {
+            const int64_t r0 = (int64_t)nb * t / n_threads, r1 = (int64_t)nb * (t + 1) / n_threads;
+            if (src_pitch_bytes == width_bytes) {
+                std::memcpy(dst + r0 * width_bytes, (const char *)src + (c0 + r0) * src_pitch_bytes,
+                            (size_t)(r1 - r0) * width_bytes);
+            } else {
+                for (int64_t r = r0; r < r1; ++r)
+                    std::memcpy(dst + r * width_bytes, (const char *)src + (c0 + r) * src_pitch_bytes,
+                                (size_t)width_bytes);
+            }
+        };
+        std::vector<std::thread> pool;
+        for (int t = 1; t < n_threads; ++t) pool.emplace_back(work, t);
+        work(0);
+        for (auto &th : pool) th.join();
+    };
     double *dout = (double *)e->dOut.p;
     int32_t *diout = (int32_t *)e->dIout.p;
     CK(cudaEventRecord(e->ev_start, e->stream));       // earlier work on the engine's stream
@@ -1080,6 +1179,9 @@ static int run_host(gt_engine *e, const void *src, int64_t src_pitch_bytes, int6
                              (size_t)nb * 8, nf, cudaMemcpyDeviceToHost, e->s_out));
         CK(cudaMemcpy2DAsync(iout_host + c0, (size_t)n_snps * 4, diout + c0, (size_t)n_snps * 4,
                              (size_t)nb * 4, GT_NUM_IFIELDS, cudaMemcpyDeviceToHost, e->s_out));
+        if (want_maf)
+            CK(cudaMemcpyAsync(e->file_maf_host + c0, (double *)e->dFileMaf.p + c0, (size_t)nb * 8,
+                               cudaMemcpyDeviceToHost, e->s_out));
         return 0;
     };
     int64_t prev0 = -1;
@@ -1087,11 +1189,26 @@ static int run_host(gt_engine *e, const void *src, int64_t src_pitch_bytes, int6
     for (int64_t c0 = 0; c0 < n_snps; c0 += chunk, ++c) {
         const int nb = (int)std::min<int64_t>(chunk, n_snps - c0), slot = c & 1;
         char *dg = (char *)e->dGeno.p + (size_t)slot * dev_pitch_bytes * chunk;
+        const char *hsrc = (const char *)src + c0 * src_pitch_bytes;
+        size_t hpitch = (size_t)src_pitch_bytes;
+        if (stage) {
+            if (c >= 2) CK(cudaEventSynchronize(e->ev_h2d[slot]));    // the copy out of this buffer is done
+            stage_rows(c0, nb, (char *)e->pin[slot]);
+            hsrc = (const char *)e->pin[slot];
+            hpitch = (size_t)width_bytes;
+        }
         if (c >= 2) CK(cudaStreamWaitEvent(e->s_in, e->ev_done[slot], 0));   // slot read by chunk c-2
-        CK(cudaMemcpy2DAsync(dg, dev_pitch_bytes, (const char *)src + c0 * src_pitch_bytes, src_pitch_bytes,
+        CK(cudaMemcpy2DAsync(dg, dev_pitch_bytes, hsrc, hpitch,
                              width_bytes, nb, cudaMemcpyHostToDevice, e->s_in));
+        if (stage) CK(cudaEventRecord(e->ev_h2d[slot], e->s_in));
         CK(cudaEventRecord(e->ev_in[slot], e->s_in));
         CK(cudaStreamWaitEvent(e->stream, e->ev_in[slot], 0));
+        if (want_maf) {
+            file_maf_packed_kernel<<<(nb + 7) / 8, 256, 0, e->stream>>>(
+                (const uint8_t *)dg, dev_pitch_bytes, nb, e_n_file(e), (double *)e->dFileMaf.p + c0);
+            CK(cudaGetLastError());
+            e->all_launches += 1;
+        }
         if ((rc = run_any(e, dg, dev_pitch_arg, packed, nb, dout + c0, diout + c0, n_snps))) return rc;
         CK(cudaEventRecord(e->ev_done[slot], e->stream));
         if (prev0 >= 0 && (rc = copy_back(prev0, prev_nb, prev_slot))) return rc;

@@ -30,7 +30,8 @@ ABI_SYMBOLS = [
     "gt_abi_version", "gt_last_error", "gt_engine_create",
     "gt_engine_destroy", "gt_engine_set_stream", "gt_engine_synchronize",
     "gt_engine_set_option",
-    "gt_engine_set_design", "gt_engine_set_sample_sex", "gt_engine_num_params", "gt_engine_num_fields",
+    "gt_engine_set_design", "gt_engine_set_sample_sex", "gt_engine_set_file_maf_output",
+    "gt_engine_num_params", "gt_engine_num_fields",
     "gt_packed_pitch", "gt_run_packed_dev", "gt_run_packed_host",
     "gt_run_dosage_dev", "gt_run_dosage_host", "gt_synth_packed_dev",
     "gt_engine_enable_timing", "gt_engine_kernel_time",
@@ -88,6 +89,7 @@ def load_library():
     lib.gt_engine_set_option.argtypes = [vp, c.c_char_p, c.c_int]
     lib.gt_engine_set_design.argtypes = [vp, c.POINTER(_DesignDesc)]
     lib.gt_engine_set_sample_sex.argtypes = [vp, vp]
+    lib.gt_engine_set_file_maf_output.argtypes = [vp, vp]
     for name in ("gt_host_t_sf2", "gt_host_t_ppf975", "gt_host_norm_sf2"):
         getattr(lib, name).restype = c.c_double
     lib.gt_host_t_sf2.argtypes = [c.c_double, c.c_double]
@@ -319,17 +321,27 @@ class Engine(object):
             ctypes.c_void_p(iout.data_ptr())))
         return out, iout
 
-    def run_packed_host(self, packed, out=None, iout=None):
-        """``packed``: uint8 ndarray [n_snps, row_bytes] (a .bed body).
-        Copies in, runs, copies back, synchronises."""
+    def run_packed_host(self, packed, out=None, iout=None, file_maf=None):
+        """``packed``: uint8 ndarray [n_snps, row_bytes] (a .bed body; an
+        ``np.memmap`` slice is read in place).  Copies in, runs, copies back,
+        synchronises.  ``file_maf``: float64 [n_snps] that receives the MAF of
+        every marker over ALL samples of the file (what ``MAFFilter`` tests)."""
         packed = np.ascontiguousarray(packed, dtype=np.uint8)
         n_snps, row_bytes = packed.shape
         if out is None:
             out = np.empty((self.n_fields, n_snps), dtype=np.float64)
             iout = np.empty((NUM_IFIELDS, n_snps), dtype=np.int32)
-        self._check(self.lib.gt_run_packed_host(
-            self._h, packed.ctypes.data, int(row_bytes), int(n_snps),
-            out.ctypes.data, iout.ctypes.data))
+        if file_maf is not None:
+            assert file_maf.dtype == np.float64 and file_maf.shape == (n_snps,)
+            self._check(self.lib.gt_engine_set_file_maf_output(
+                self._h, file_maf.ctypes.data))
+        try:
+            self._check(self.lib.gt_run_packed_host(
+                self._h, packed.ctypes.data, int(row_bytes), int(n_snps),
+                out.ctypes.data, iout.ctypes.data))
+        finally:
+            if file_maf is not None:
+                self.lib.gt_engine_set_file_maf_output(self._h, None)
         return Results(out, iout, self.n_params)
 
     def run_dosage_host(self, dosage, out=None, iout=None):

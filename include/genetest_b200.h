@@ -146,6 +146,13 @@ int gt_run_packed_host(gt_engine *e, const uint8_t *packed_host,
                        int64_t row_bytes, int32_t n_snps, double *out_host,
                        int32_t *iout_host);
 
+/* MAFFilter support (genetest/modelspec/predicates.py:33-57): when `maf_host` is
+ * not NULL, every following gt_run_packed_host call also writes the MAF of each
+ * marker over ALL samples of its file row -- get_maf(snp.genotypes), what the
+ * predicate evaluates before a marker enters the analysis -- to
+ * maf_host[0 .. n_snps).  NULL switches it off. */
+int gt_engine_set_file_maf_output(gt_engine *e, double *maf_host);
+
 /* Same for real-valued dosages (impute2 / bgen / dataframe readers):
  * row-major [n_snps][ld] doubles already aligned to the design rows
  * (ld >= n), NaN = missing. */

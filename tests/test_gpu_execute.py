@@ -404,3 +404,77 @@ def test_impute2_dosages_through_execute(tmp_path, test):
                     (name, key, f)
         assert r["MODEL"]["nobs"] == o["MODEL"]["nobs"]
     assert n_ok >= n_snps - 2
+
+
+def test_maf_filter_runs_on_the_packed_path(tmp_path):
+    """``MAFFilter`` (predicates.py:33-57: MAF over ALL samples of the file,
+    phenotyped or not) is evaluated on the device for .bed sources; a subclass
+    -- any predicate the engine does not know -- sends the same analysis through
+    the reference's per-marker loop.  Both give the same rows, the same skipped
+    list and the same failure lines, and a subscriber that overrides ``handle``
+    (the reference's extension point) is called once per marker on either path."""
+    from genetest_b200.modelspec.predicates import MAFFilter, NameFilter
+    from genetest_b200.phenotypes import DataFramePhenotypes
+    rng = np.random.default_rng(77)
+    n_file, n, n_snps = 500, 420, 96
+    ids = np.array(["s{:03d}".format(i) for i in range(n_file)])
+    maf = np.concatenate([rng.uniform(0.001, 0.08, n_snps // 2),
+                          rng.uniform(0.08, 0.5, n_snps - n_snps // 2)])
+    G = rng.binomial(2, maf[:, None], size=(n_snps, n_file)).astype(float)
+    G[rng.random(G.shape) < 0.03] = np.nan
+    G[5] = np.nan                                        # nothing genotyped: always skipped
+    names = ["rs{}".format(j) for j in range(n_snps)]
+    with PlinkWriter(str(tmp_path / "g")) as w:
+        for j in range(n_snps):
+            w.write_genotypes(np.nan_to_num(G[j], nan=-1))
+        w.write_bim([(1, nm, 100 + j, "A", "G") for j, nm in enumerate(names)])
+        w.write_fam(list(ids))
+    keep = rng.permutation(n_file)[:n]
+    pheno = pd.DataFrame({"y": rng.normal(size=n), "age": rng.normal(50, 10, n)},
+                         index=ids[keep])
+
+    class CountingWriter(GWASWriter):
+        calls = 0
+
+        def handle(self, results):
+            type(self).calls += 1
+            return super().handle(results)
+
+    class OtherMAF(MAFFilter):
+        pass
+
+    outs = {}
+    for tag, pred in (("packed", MAFFilter(0.05)), ("decoded", OtherMAF(0.05))):
+        spec._reset()
+        CountingWriter.calls = 0
+        prefix = str(tmp_path / tag)
+        sub = CountingWriter(prefix + ".tsv", "linear")
+        analysis.execute_formula(
+            DataFramePhenotypes(pheno), PlinkReader(str(tmp_path / "g")),
+            "y ~ SNPs + age", "linear", subscribers=[sub],
+            variant_predicates=[pred, NameFilter(set(names[3:]))],
+            output_prefix=prefix, maf_t=0.06)
+        outs[tag] = (open(prefix + ".tsv").read(),
+                     sorted(open(prefix + "_not_analyzed_snps.txt").read().split()),
+                     sorted(open(prefix + "_failed_snps.txt").read().splitlines()),
+                     CountingWriter.calls)
+    assert outs["packed"][1] == outs["decoded"][1]
+    assert outs["packed"][2] == outs["decoded"][2]
+    # the same rows (the two paths sum in different orders: equal to rounding, not to the bit)
+    import io
+    ta = pd.read_csv(io.StringIO(outs["packed"][0]), sep="\t")
+    tb = pd.read_csv(io.StringIO(outs["decoded"][0]), sep="\t")
+    assert list(ta.columns) == list(tb.columns) and len(ta) == len(tb) > 10
+    for col in ta.columns:
+        if ta[col].dtype.kind == "f":
+            np.testing.assert_allclose(ta[col].values, tb[col].values, rtol=1e-9)
+        else:
+            assert (ta[col] == tb[col]).all(), col
+    assert outs["packed"][3] == outs["decoded"][3] == len(ta)
+    # the filter saw the whole file: its MAF differs from the analysed samples' MAF
+    file_maf = np.nanmean(G, axis=1) / 2
+    file_maf = np.minimum(file_maf, 1 - file_maf)
+    want_skipped = sorted(set(names[:3]) | {nm for nm, m in zip(names, file_maf)
+                                            if not m >= 0.05})
+    assert outs["packed"][1] == want_skipped
+    assert "rs5" in want_skipped and len(outs["packed"][2]) > 0
