@@ -19,6 +19,7 @@
 #include "gt_corr_stream.cuh"
 #include "gt_linear.cuh"
 #include "gt_solve.cuh"
+#include "gt_solve_thread.cuh"
 #include "gt_logistic.cuh"
 #include "gt_cox.cuh"
 #include "gt_format.cuh"
@@ -39,6 +40,7 @@ struct gt_engine {
     bool use_tc = true;        // lean linear designs run on the tcgen05 int8 contraction
     bool use_stream_corr = true;   // ... and their corrections on the streaming kernel
     int cox_maxiter = 100;     // Newton step limit of the Cox model (statsmodels' default)
+    bool use_thread_solve = true;  // thread-per-SNP solve for narrow designs without interaction
     int tc_dbg = 0;
     int tc_N = 0;              // 0: the design does not run on the tcgen05 kernel
     gtk::Tc2Params tc{};       // constant part of the kernel parameters
@@ -453,6 +455,7 @@ int gt_engine_set_option(gt_engine *e, const char *name, int value) {
     if (std::strcmp(name, "contract_tc") == 0) { e->use_tc = value != 0; return 0; }
     if (std::strcmp(name, "tc_debug") == 0) { e->tc_dbg = value; return 0; }
     if (std::strcmp(name, "stream_corrections") == 0) { e->use_stream_corr = value != 0; return 0; }
+    if (std::strcmp(name, "thread_solve") == 0) { e->use_thread_solve = value != 0; return 0; }
     if (std::strcmp(name, "cox_maxiter") == 0) { e->cox_maxiter = value > 0 ? value : 100; return 0; }
     if (std::strcmp(name, "host_chunk") == 0) { e->host_chunk = (int)std::max<int64_t>(0, value); return 0; }
     return fail(GT_E_ARG, "gt_engine_set_option: unknown option '%s'", name);
@@ -949,14 +952,33 @@ static int launch_finish(gt_engine *e, const void *g, int64_t pitch, int nb, dou
         if (smem > 220 * 1024) return fail(GT_E_UNSUPPORTED, "design too wide for the solve kernel (%zu B shared)", smem);
         const int grid = (nb + gpc - 1) / gpc;
         int fslot = time_begin(e, 2);
+        // designs without interaction and up to 13 parameters: one thread per marker first,
+        // the 16-lane kernel then only finishes what that one deferred (Jacobi gate)
+        int deferred_only = 0;
+        if (D.lean && D.I == 0 && D.p >= 2 && D.p <= 13 && e->use_thread_solve) {
+            const int tgrid = (nb + 127) / 128;
+#define GT_ST(PP)                                                                                   \
+    case PP:                                                                                        \
+        gtk::linear_solve_thread_kernel<PP><<<tgrid, 128, 0, e->stream>>>(D, nb, S, cnt, gs, corr,  \
+                                                                          ldc, out, iout, stride); \
+        break;
+            switch (D.p) {
+                GT_ST(2) GT_ST(3) GT_ST(4) GT_ST(5) GT_ST(6) GT_ST(7) GT_ST(8) GT_ST(9) GT_ST(10)
+                GT_ST(11) GT_ST(12) GT_ST(13)
+            }
+#undef GT_ST
+            CK(cudaGetLastError());
+            deferred_only = 1;
+            e->all_launches += 1;
+        }
         if (half) {
             CK(cudaFuncSetAttribute((const void *)gtk::linear_solve_kernel<16>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            gtk::linear_solve_kernel<16><<<grid, threads, smem, e->stream>>>(D, nb, S, cnt, gs, corr, ldc, out, iout, stride);
+            gtk::linear_solve_kernel<16><<<grid, threads, smem, e->stream>>>(D, nb, S, cnt, gs, corr, ldc, out, iout, stride, deferred_only);
         } else {
             CK(cudaFuncSetAttribute((const void *)gtk::linear_solve_kernel<32>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            gtk::linear_solve_kernel<32><<<grid, threads, smem, e->stream>>>(D, nb, S, cnt, gs, corr, ldc, out, iout, stride);
+            gtk::linear_solve_kernel<32><<<grid, threads, smem, e->stream>>>(D, nb, S, cnt, gs, corr, ldc, out, iout, stride, deferred_only);
         }
         time_end(e, fslot);
         CK(cudaGetLastError());

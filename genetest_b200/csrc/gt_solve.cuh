@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(256)
 linear_solve_kernel(GtDesignDev D, int n_snps, const double *__restrict__ S,
                     const int *__restrict__ counts, const double *__restrict__ gsum,
                     const double *__restrict__ corrT, long long ldc, double *__restrict__ out,
-                    int *__restrict__ iout, long long ostride) {
+                    int *__restrict__ iout, long long ostride, int only_deferred) {
     extern __shared__ __align__(16) double sm[];
     const int lane = threadIdx.x & 31;
     const int gl = lane % GW;
@@ -166,6 +166,8 @@ linear_solve_kernel(GtDesignDev D, int n_snps, const double *__restrict__ S,
     const int group = threadIdx.x / GW;
     const int snp = blockIdx.x * (blockDim.x / GW) + group;
     if (snp >= n_snps) return;
+    // second pass behind linear_solve_thread_kernel: only the markers it left to the Jacobi path
+    if (only_deferred && iout[(long long)GT_I_STATUS * ostride + snp] != -77) return;
     const int k = D.k, I = D.I, L = D.L, p = D.p;
     const int iy = k, i1 = k + 1;
     const int nf = GT_F_PARAM0 + 6 * p;
