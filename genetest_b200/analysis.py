@@ -498,10 +498,10 @@ def _execute_gwas(genotypes, modelspec, subscribers, y, X, variant_predicates,
             for cols in gwas_interaction.values()])
 
     options = dict(test.gwas_options())
+    strata = None
     if model == "coxph":
-        if "strata" in yd.columns:
-            raise NotImplementedError("stratified Cox models are not "
-                                      "supported by the B200 engine")
+        if "strata" in yd.columns:                  # survival.py:54-56
+            strata = yd["strata"].values
         if "intercept" in columns:
             columns.remove("intercept")
         C = Xd[columns].values.astype(float)
@@ -524,11 +524,11 @@ def _execute_gwas(genotypes, modelspec, subscribers, y, X, variant_predicates,
         # raw .bed rows go to the GPU as they are: the engine aligns them
         eng.set_design(model, y_main, C, W=W, event=event,
                        sample_pos=geno_index.astype(np.int32), n_file=n_file,
-                       maf_t=maf_t, **options)
+                       maf_t=maf_t, strata=strata, **options)
     else:
         # decoded genotypes are aligned to the design rows on the host
         eng.set_design(model, y_main, C, W=W, event=event, maf_t=maf_t,
-                       **options)
+                       strata=strata, **options)
     if sample_sex is not None:
         # analysis.py:141-148: get_sex_maf on the complete cases
         eng.set_sample_sex(

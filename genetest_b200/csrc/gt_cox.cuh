@@ -45,13 +45,17 @@ static int iter_set_design(const gt_design_desc *d, const std::vector<int> &pos,
     // Efron group: inside one 32-slot block when there are at most 32, else
     // over whole blocks of their own ("big group": blk_info = block count on
     // the first block).
-    std::vector<int> slot_pos, slot_info, blk_info;
+    std::vector<int> slot_pos, slot_info, blk_info, seg_start;
     std::vector<double> Xs;
     if (d->model == GT_MODEL_COXPH) {
         std::vector<int> order(n);
         for (int i = 0; i < n; ++i) order[i] = i;
-        std::stable_sort(order.begin(), order.end(),
-                         [&](int a, int b) { return d->y[a] > d->y[b]; });
+        // strata first (PHReg(strata=...): the risk sets restart with every stratum), then time
+        const double *strata = d->strata;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+            if (strata && strata[a] != strata[b]) return strata[a] < strata[b];
+            return d->y[a] > d->y[b];
+        });
         auto pad_block = [&]() {
             for (int fill = (int)(slot_pos.size() % 32); fill != 0 && fill < 32; ++fill) {
                 slot_pos.push_back(-1);
@@ -64,9 +68,15 @@ static int iter_set_design(const gt_design_desc *d, const std::vector<int> &pos,
         };
         std::vector<int> big_first, big_blocks;
         int i0 = 0;
+        seg_start.push_back(0);
         while (i0 < n) {
+            if (strata && i0 > 0 && strata[order[i0]] != strata[order[i0 - 1]]) {
+                pad_block();                             // a stratum starts on a block of its own
+                seg_start.push_back((int)(slot_pos.size() / 32));
+            }
             int i1 = i0;
-            while (i1 + 1 < n && d->y[order[i1 + 1]] == d->y[order[i0]]) ++i1;
+            while (i1 + 1 < n && d->y[order[i1 + 1]] == d->y[order[i0]] &&
+                   (!strata || strata[order[i1 + 1]] == strata[order[i0]])) ++i1;
             std::vector<int> events;
             for (int t = i0; t <= i1; ++t) {
                 int row = order[t];
@@ -90,6 +100,7 @@ static int iter_set_design(const gt_design_desc *d, const std::vector<int> &pos,
         }
         pad_block();
         const size_t ns = slot_pos.size();
+        seg_start.push_back((int)(ns / 32));
         for (size_t b = 0; b < ns; b += 32) {
             bool ties = false;
             for (int t = 0; t < 32; ++t) ties |= ((slot_info[b + t] & 31) != ((slot_info[b + t] >> 5) & 31));
@@ -111,14 +122,15 @@ static int iter_set_design(const gt_design_desc *d, const std::vector<int> &pos,
             for (int j = 0; j < k; ++j) Xs[s * XSs + j] = H.Q[(size_t)j * n + row];
             for (int j = 0; j < I; ++j) Xs[s * XSs + k + j] = d->W[(size_t)j * n + row];
         }
-        // append: Xs | slot_pos | slot_info | blk_info  (ints packed two per double)
+        // append: Xs | slot_pos | slot_info | blk_info | seg_start  (ints packed two per double)
         size_t base = host.size();
-        host.resize(base + Xs.size() + ns + ns / 64 + 2, 0.0);
+        host.resize(base + Xs.size() + ns + ns / 64 + seg_start.size() / 2 + 3, 0.0);
         std::memcpy(&host[base], Xs.data(), Xs.size() * 8);
         int *ip = (int *)&host[base + Xs.size()];
         std::memcpy(ip, slot_pos.data(), ns * 4);
         std::memcpy(ip + ns, slot_info.data(), ns * 4);
         std::memcpy(ip + 2 * ns, blk_info.data(), (ns / 32) * 4);
+        std::memcpy(ip + 2 * ns + ns / 32, seg_start.data(), seg_start.size() * 4);
         // max |x| per design column (q | g | g w): bounds the change of the
         // linear predictor after a Newton step
         size_t cm = host.size();
@@ -146,9 +158,12 @@ static int iter_set_design(const gt_design_desc *d, const std::vector<int> &pos,
         T.slot_pos = (const int *)(xs + (size_t)T.n_slots * XSs);
         T.slot_info = T.slot_pos + T.n_slots;
         T.blk_info = T.slot_info + T.n_slots;
+        T.seg_start = T.blk_info + T.n_slots / 32;
+        T.n_seg = (int)seg_start.size() - 1;
         T.colmax = (const double *)buf.p + (host.size() - p);
     } else {
         T.n_slots = 0; T.Xs = nullptr; T.slot_pos = nullptr; T.slot_info = nullptr; T.blk_info = nullptr; T.colmax = nullptr;
+        T.n_seg = 0; T.seg_start = nullptr;
     }
     CK(cudaStreamSynchronize(st));
     return 0;

@@ -183,11 +183,47 @@ cox_newton_one(const IterDesignDev &T, const void *__restrict__ geno, long long 
             emax = gt_warp_max(emax);
             slack = 0.0;
         }
-        // ---- pass 1: total of 1/den over all event terms ----
+        // ---- passes 1 and 2, stratum by stratum (PHReg(strata=...), survival.py:77-82: the
+        // risk sets restart with every stratum; one segment of blocks each, a single one
+        // without strata) ----
+        double accH[NT][NT][2], accU[NT][NT][2];
+#pragma unroll
+        for (int a = 0; a < NT; ++a)
+#pragma unroll
+            for (int b = 0; b < NT; ++b) accH[a][b][0] = accH[a][b][1] = accU[a][b][0] = accU[a][b][1] = 0.0;
+        double ll = 0.0;
+        // A = x, B = [W x | G]: the weights are applied while the fragments
+        // are loaded (column p of B carries the score); U accumulates u u'
+        auto mma_block = [&]() {
+            __syncwarp();
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+                const int e4 = ks * 4 + (lane & 3), cc = lane >> 2;
+                const double wsc = wv[e4], gsc = gv[e4];
+                double xf[NT], wf[NT], uf[NT];
+#pragma unroll
+                for (int t = 0; t < NT; ++t) {
+                    xf[t] = xT[(t * 8 + cc) * XT + e4];
+                    uf[t] = uT[(t * 8 + cc) * XT + e4];
+                    wf[t] = (t * 8 + cc == p) ? gsc : wsc * xf[t];
+                }
+#pragma unroll
+                for (int mt = 0; mt < NT; ++mt)
+#pragma unroll
+                    for (int nt = mt; nt < NT; ++nt) {
+                        dmma884(accH[mt][nt][0], accH[mt][nt][1], xf[mt], wf[nt]);
+                        dmma884(accU[mt][nt][0], accU[mt][nt][1], uf[mt], uf[nt]);
+                    }
+            }
+            __syncwarp();
+        };
+        for (int seg = 0; seg < T.n_seg; ++seg) {
+        const int seg_b0 = T.seg_start[seg], seg_b1 = T.seg_start[seg + 1];
+        // ---- pass 1: total of 1/den over the event terms of the stratum ----
         double Ttot = 0.0;
         {
             double c0 = 0.0;
-            for (int b = 0; b < nblk; ++b) {
+            for (int b = seg_b0; b < seg_b1; ++b) {
                 const int nbig = T.blk_info[b];
                 if (nbig > 1) {
                     // tied events over several blocks: den_j = S0g - (j/d) EG
@@ -230,40 +266,10 @@ cox_newton_one(const IterDesignDev &T, const void *__restrict__ geno, long long 
             Ttot = gt_warp_sum(Ttot);
         }
         // ---- pass 2: log-likelihood, score, Hessian ----
-        double accH[NT][NT][2], accU[NT][NT][2];
-#pragma unroll
-        for (int a = 0; a < NT; ++a)
-#pragma unroll
-            for (int b = 0; b < NT; ++b) accH[a][b][0] = accH[a][b][1] = accU[a][b][0] = accU[a][b][1] = 0.0;
-        double ll = 0.0, c0 = 0.0, cI = 0.0;
+        double c0 = 0.0, cI = 0.0;
         for (int t = lane; t < PH; t += 32) carry[t] = 0.0;
         __syncwarp();
-        // A = x, B = [W x | G]: the weights are applied while the fragments
-        // are loaded (column p of B carries the score); U accumulates u u'
-        auto mma_block = [&]() {
-            __syncwarp();
-#pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {
-                const int e4 = ks * 4 + (lane & 3), cc = lane >> 2;
-                const double wsc = wv[e4], gsc = gv[e4];
-                double xf[NT], wf[NT], uf[NT];
-#pragma unroll
-                for (int t = 0; t < NT; ++t) {
-                    xf[t] = xT[(t * 8 + cc) * XT + e4];
-                    uf[t] = uT[(t * 8 + cc) * XT + e4];
-                    wf[t] = (t * 8 + cc == p) ? gsc : wsc * xf[t];
-                }
-#pragma unroll
-                for (int mt = 0; mt < NT; ++mt)
-#pragma unroll
-                    for (int nt = mt; nt < NT; ++nt) {
-                        dmma884(accH[mt][nt][0], accH[mt][nt][1], xf[mt], wf[nt]);
-                        dmma884(accU[mt][nt][0], accU[mt][nt][1], uf[mt], uf[nt]);
-                    }
-            }
-            __syncwarp();
-        };
-        for (int b = 0; b < nblk; ++b) {
+        for (int b = seg_b0; b < seg_b1; ++b) {
             const int nbig = T.blk_info[b];
             if (nbig > 1) {
                 // ---- tied events over several blocks (all members are events) ----
@@ -421,6 +427,7 @@ cox_newton_one(const IterDesignDev &T, const void *__restrict__ geno, long long 
             }
             mma_block();
         }
+        }   // strata
         ll = gt_warp_sum(ll);
         // -H = accH[:p,:p] - accU ; score = accH[:, p]
 #pragma unroll

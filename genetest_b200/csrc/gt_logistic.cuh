@@ -43,6 +43,8 @@ struct IterDesignDev {
     const double *maf_o;    // sex-aware MAF / flip per marker of the launch, or NULL
     const int *flip_o;
     int newton_maxiter;     // coxph: PHReg.fit(maxiter=100); engine option "cox_maxiter" (tests)
+    int n_seg;              // coxph: strata (1 without), blocks seg_start[s] .. seg_start[s + 1) each
+    const int *seg_start;   // [n_seg + 1]
 };
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {

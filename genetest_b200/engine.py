@@ -56,6 +56,7 @@ class _DesignDesc(ctypes.Structure):
         ("condition_value_t", ctypes.c_double),
         ("eigenvals_t", ctypes.c_double), ("maf_t", ctypes.c_double),
         ("use_maf_t", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        ("strata", ctypes.c_void_p),
     ]
 
 
@@ -229,9 +230,10 @@ class Engine(object):
     # -- design -----------------------------------------------------------
     def set_design(self, model, y, C, W=None, event=None, sample_pos=None,
                    n_file=None, raw_mode=False, condition_value_t=1000.0,
-                   eigenvals_t=1e-10, maf_t=None):
+                   eigenvals_t=1e-10, maf_t=None, strata=None):
         """``y``: (n,), ``C``: (n, k) covariates, ``W``: (n, I) interaction
-        multipliers, ``sample_pos``: (n,) genotype-file positions."""
+        multipliers, ``sample_pos``: (n,) genotype-file positions, ``strata``:
+        (n,) stratum labels of a Cox model (any values; equal = same stratum)."""
         y = np.ascontiguousarray(y, dtype=np.float64).ravel()
         n = y.shape[0]
         C = np.asarray(C, dtype=np.float64).reshape(n, -1)
@@ -261,6 +263,13 @@ class Engine(object):
         d.event = ev.ctypes.data if ev is not None else None
         d.W = Wf.ctypes.data if Wf is not None else None
         d.sample_pos = pos.ctypes.data if pos is not None else None
+        st = None
+        if strata is not None:
+            # labels -> dense codes (the engine only compares them)
+            st = np.unique(np.asarray(strata), return_inverse=True)[1].astype(np.float64)
+            st = np.ascontiguousarray(st.ravel())
+            assert st.shape[0] == n
+        d.strata = st.ctypes.data if st is not None else None
         d.condition_value_t = float(condition_value_t)
         d.eigenvals_t = float(eigenvals_t)
         d.maf_t = float(maf_t) if maf_t is not None else 0.0

@@ -34,22 +34,20 @@ class StatsCoxPH(StatsModels, BatchedGWAS):
         if {"tte", "event"} - set(y.columns):
             raise ValueError(
                 "missing column in y: coxph requires 'tte' and 'event'")
-        if "strata" in y.columns:
-            raise NotImplementedError("stratified Cox models are not "
-                                      "supported by the B200 engine")
-        extra = set(y.columns) - {"tte", "event"}
+        extra = set(y.columns) - {"tte", "event", "strata"}
         if extra:
             logger.warning("{}: unknown column in y, will be ignored".format(
                 ",".join(sorted(extra))))
         if "intercept" in X.columns:
             X = X.drop("intercept", axis=1)
-        return y.tte, y.event, X
+        strata = y.strata if "strata" in y.columns else None     # survival.py:54-56
+        return y.tte, y.event, X, strata
 
     def fit(self, y, X):
-        tte, event, X = self._prepare_data(y, X)
+        tte, event, X, strata = self._prepare_data(y, X)
         res, order = fit_single(
             "coxph", [tte.values.astype(float), event.values.astype(float)],
-            X, {})
+            X, {} if strata is None else {"strata": strata.values})
         out = {"MODEL": {"log_likelihood": float(res.llf[0]),
                          "nobs": X.shape[0], "nevents": np.sum(event)}}
         for j, col in enumerate(X.columns):

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define GT_ABI_VERSION 1
+#define GT_ABI_VERSION 2
 
 /* models (genetest/statistics/__init__.py:35-40 model_map keys) */
 enum { GT_MODEL_LINEAR = 0, GT_MODEL_LOGISTIC = 1, GT_MODEL_COXPH = 2 };
@@ -97,6 +97,9 @@ typedef struct gt_design_desc {
     double maf_t;              /* execute(maf_t=...)                         */
     int32_t use_maf_t;
     int32_t reserved;
+    const double *strata;   /* host, n: coxph stratum label of every design row
+                               (y.strata -> PHReg(strata=...), survival.py:54-56,
+                               77-82), or NULL                                  */
 } gt_design_desc;
 
 int gt_abi_version(void);

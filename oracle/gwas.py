@@ -105,13 +105,13 @@ def stats_logistic(y, X, names):
 
 
 # survival.py:36-122
-def stats_coxph(tte, event, X, names):
+def stats_coxph(tte, event, X, names, strata=None):
     X = np.asarray(X, dtype=float)
     keep = [i for i, nm in enumerate(names) if nm != "intercept"]
     names = [names[i] for i in keep]
     X = X[:, keep]
     try:
-        fit = sm_port.phreg_efron_newton(tte, event, X)
+        fit = sm_port.phreg_efron_newton(tte, event, X, strata=strata)
     except sm_port.OracleLinAlgError as e:
         raise OracleStatsError(str(e))
     except sm_port.OracleConvergence as e:
@@ -134,7 +134,8 @@ def gwas_one(model, y, C, cov_names, g, maf_t=None, interaction=None,
              sexes=None, model_kwargs=None, coded="A1", reference="A2"):
     """One pass of ``_gwas_worker``'s loop body (``analysis.py:108-197``).
 
-    ``y``: (n, 1) outcome, or (n, 2) ``[tte, event]`` for coxph.
+    ``y``: (n, 1) outcome, or (n, 2) ``[tte, event]`` / (n, 3) ``[tte, event,
+    strata]`` for coxph.
     ``C``: (n, k) covariates (complete: ``execute`` already ran ``dropna``),
     ``cov_names`` its column ids (``"intercept"`` last when present).
     ``g``: (n,) dosages aligned to the rows of ``C``; NaN = missing genotype
@@ -174,7 +175,9 @@ def gwas_one(model, y, C, cov_names, g, maf_t=None, interaction=None,
         elif model == "logistic":
             res = stats_logistic(yy[:, 0], X, names)
         elif model == "coxph":
-            res = stats_coxph(yy[:, 0], yy[:, 1], X, names)
+            # a third outcome column is y.strata (survival.py:54-56)
+            res = stats_coxph(yy[:, 0], yy[:, 1], X, names,
+                              strata=yy[:, 2] if yy.shape[1] > 2 else None)
         else:
             raise ValueError(model)
     except OracleStatsError as e:

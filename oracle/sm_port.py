@@ -179,8 +179,30 @@ def glm_binomial_irls(y, X, maxiter=100, tol=1e-8, return_history=False):
 # --------------------------------------------------------------------------
 # PHReg, Efron ties, Newton
 # --------------------------------------------------------------------------
-def _efron_pieces(time, status, X, params, want):
+def _efron_pieces(time, status, X, params, want, strata=None):
     """Log partial likelihood (Efron), gradient and Hessian at ``params``.
+    With ``strata`` (PHReg(strata=...), genetest survival.py:54-56,77-82;
+    statsmodels PHSurvivalTime splits the rows by stratum label and sums the
+    per-stratum partial likelihoods, strata without events contribute nothing)
+    the pieces of every stratum are added up."""
+    if strata is not None:
+        strata = np.asarray(strata)
+        p = X.shape[1]
+        like, grad, hess = 0.0, np.zeros(p), np.zeros((p, p))
+        for lab in np.unique(strata):
+            sel = strata == lab
+            if status[sel].sum() == 0:
+                continue
+            a, b, c = _efron_pieces_one(time[sel], status[sel], X[sel], params, want)
+            like += a
+            grad += b
+            hess += c
+        return like, grad, hess
+    return _efron_pieces_one(time, status, X, params, want)
+
+
+def _efron_pieces_one(time, status, X, params, want):
+    """One stratum (or the whole, unstratified, sample).
 
     statsmodels.duration.hazard_regression.PHReg.efron_{loglike,gradient,
     hessian}: samples sorted by time, unique failure times walked backwards
@@ -236,7 +258,8 @@ def _efron_pieces(time, status, X, params, want):
     return like, grad, hess
 
 
-def phreg_efron_newton(time, status, X, maxiter=100, tol=1e-8, ridge=1e-10):
+def phreg_efron_newton(time, status, X, maxiter=100, tol=1e-8, ridge=1e-10,
+                       strata=None):
     """``sm.PHReg(..., ties="efron").fit()`` restated: LikelihoodModel.fit
     with method="newton" works on loglike/nobs with a +1e-10 ridge on the
     (un-negated) Hessian diagonal, from beta=0, until max abs(step) <= 1e-8;
@@ -250,7 +273,7 @@ def phreg_efron_newton(time, status, X, maxiter=100, tol=1e-8, ridge=1e-10):
     old = np.full(p, np.inf)
     it = 0
     while it < maxiter and np.any(np.abs(new - old) > tol):
-        _, g, H = _efron_pieces(time, status, X, new, 2)
+        _, g, H = _efron_pieces(time, status, X, new, 2, strata)
         H = H / nobs
         H[np.diag_indices(p)] += ridge
         old = new
@@ -262,7 +285,7 @@ def phreg_efron_newton(time, status, X, maxiter=100, tol=1e-8, ridge=1e-10):
     if it == maxiter:
         raise OracleConvergence("Maximum Likelihood optimization failed to "
                                 "converge.")
-    llf, _, H = _efron_pieces(time, status, X, new, 2)
+    llf, _, H = _efron_pieces(time, status, X, new, 2, strata)
     try:
         cov = np.linalg.inv(-H)
     except np.linalg.LinAlgError as exc:

@@ -160,3 +160,34 @@ def test_coxph_no_convergence_branch(engine):
         sm_port.phreg_efron_newton(tte[ok], event[ok], X, maxiter=int(need[j]) + 1)
     finally:
         engine.set_option("cox_maxiter", 100)
+
+
+@pytest.mark.parametrize("n_strata", [2, 7])
+def test_coxph_strata(engine, n_strata):
+    """Stratified Cox (y.strata -> PHReg(strata=...), survival.py:54-56, 77-82):
+    risk sets restart with every stratum.  Strata of uneven sizes, tied times
+    inside and across strata, one stratum without events, permuted subset of
+    the genotype file; against the oracle and against the unstratified fit."""
+    rng = np.random.default_rng(40 + n_strata)
+    n_file, n, n_snps = 2600, 2300, 40
+    C, names = synth_design(rng, n, k_extra=2)
+    C, names = C[:, :-1], names[:-1]
+    tte, event = _cox_data(rng, n, C)
+    tte = np.ceil(tte * 25) / 25
+    strata = rng.choice(n_strata, n, p=np.arange(1, n_strata + 1) / np.arange(1, n_strata + 1).sum())
+    event[strata == 0] = 0.0
+    pos = np.sort(rng.permutation(n_file)[:n]).astype(np.int32)
+    Gfile = synth_genotypes(rng, n_snps, n_file, missing=0.02)
+    Y = np.column_stack((tte, event, strata.astype(float)))
+    engine.set_design("coxph", tte, C, event=event, sample_pos=pos, n_file=n_file,
+                      strata=strata * 10 + 3)             # labels are arbitrary
+    res = engine.run_packed_host(pack_rows(Gfile))
+    oracle = run_oracle("coxph", Y, C, names, Gfile[:, pos])
+    problems, worst, n_ok = compare("coxph", res, oracle, names, rtol=1e-6, strict=True)
+    assert not problems, problems[:5]
+    assert n_ok == n_snps
+    engine.set_design("coxph", tte, C, event=event, sample_pos=pos, n_file=n_file)
+    plain = engine.run_packed_host(pack_rows(Gfile))
+    k = len(names)
+    assert np.max(np.abs(plain.param(k)[0] - res.param(k)[0])) > 1e-4
+    print("stratified Cox ({} strata): worst rel err {:.2e}".format(n_strata, worst))

@@ -297,7 +297,7 @@ def test_shared_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), name
     lib.gt_abi_version.restype = ctypes.c_int
-    assert lib.gt_abi_version() == 1
+    assert lib.gt_abi_version() == 2
     lib.gt_packed_pitch.restype = ctypes.c_int64
     assert lib.gt_packed_pitch(100000) == 25088
 

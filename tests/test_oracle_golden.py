@@ -210,3 +210,62 @@ def test_maf_vectors():
     assert abs(maf - 3 / 15) < 1e-15 and not flip
     maf, _, _, _ = og.get_sex_maf(np.full(4, np.nan), np.ones(4), "B", "A")
     assert np.isnan(maf)
+
+
+def test_stratified_cox_against_a_brute_force_partial_likelihood():
+    """PHReg(strata=...) (survival.py:54-56, 77-82).  The reference's tests hold no
+    stratified case, so the oracle's extension is checked against a direct
+    restatement of the stratified Efron partial likelihood (explicit loops over
+    strata, event times and tied events; numerical derivatives) and against
+    the identities it has to satisfy."""
+    from oracle import sm_port
+    rng = np.random.default_rng(3)
+    n, p = 90, 3
+    X = rng.normal(size=(n, p))
+    tte = np.ceil(rng.exponential(1.0, n) * 6) / 6         # ties
+    event = (rng.random(n) < 0.7).astype(float)
+    strata = rng.integers(0, 4, n).astype(float)
+    event[strata == 3] = 0.0                                # a stratum without events
+
+    def brute(beta):
+        ll = 0.0
+        for lab in np.unique(strata):
+            idx = np.flatnonzero(strata == lab)
+            for t in np.unique(tte[idx][event[idx] == 1]):
+                risk = idx[tte[idx] >= t]
+                tied = idx[(tte[idx] == t) & (event[idx] == 1)]
+                m = len(tied)
+                s0 = np.exp(X[risk] @ beta).sum()
+                f0 = np.exp(X[tied] @ beta).sum()
+                ll += (X[tied] @ beta).sum()
+                for j in range(m):
+                    ll -= np.log(s0 - j / m * f0)
+        return ll
+
+    beta = rng.normal(size=p) * 0.3
+    like, grad, hess = sm_port._efron_pieces(tte, event, X, beta, 2, strata)
+    assert abs(like - brute(beta)) < 1e-10 * abs(like)
+    h = 1e-5
+    for a in range(p):
+        e = np.zeros(p)
+        e[a] = h
+        num = (brute(beta + e) - brute(beta - e)) / (2 * h)
+        assert abs(grad[a] - num) < 1e-6 * max(1.0, abs(num))
+        for b in range(p):
+            e2 = np.zeros(p)
+            e2[b] = h
+            num2 = (brute(beta + e + e2) - brute(beta + e - e2) -
+                    brute(beta - e + e2) + brute(beta - e - e2)) / (4 * h * h)
+            assert abs(hess[a, b] - num2) < 2e-4 * max(1.0, abs(num2))
+    # one stratum = no strata; the fit maximises the stratified likelihood
+    one = sm_port.phreg_efron_newton(tte, event, X, strata=np.zeros(n))
+    none = sm_port.phreg_efron_newton(tte, event, X)
+    np.testing.assert_allclose(one["params"], none["params"], rtol=1e-12)
+    fit = sm_port.phreg_efron_newton(tte, event, X, strata=strata)
+    assert abs(fit["llf"] - brute(fit["params"])) < 1e-10 * abs(fit["llf"])
+    for a in range(p):
+        e = np.zeros(p)
+        e[a] = 1e-4
+        assert brute(fit["params"]) >= brute(fit["params"] + e)
+        assert brute(fit["params"]) >= brute(fit["params"] - e)
+    assert np.max(np.abs(fit["params"] - none["params"])) > 1e-3
