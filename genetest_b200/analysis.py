@@ -85,8 +85,14 @@ def execute(phenotypes, genotypes, modelspec, subscribers=None,
         cpus (int): kept for compatibility; the GPU engine ignores it.
         sexual_chromosome (bool): sex-aware MAF.
     """
+    # one process per GPU under torchrun: the ranks share the markers, the
+    # result sinks live on rank 0 only (every rank would otherwise re-open and
+    # re-write the same output files)
+    sharding.ensure_initialized()
     if subscribers is None:
         subscribers = [subscribers_module.Print()]
+    if not sharding.is_primary():
+        subscribers = []
     for subscriber in subscribers:
         subscriber.init(modelspec)
     if variant_predicates is None:
@@ -125,7 +131,8 @@ def execute(phenotypes, genotypes, modelspec, subscribers=None,
     elif SNPs in modelspec.predictors:
         _execute_gwas(genotypes, modelspec, subscribers, y, X,
                       variant_predicates, messages, maf_t, cpus, sample_sex)
-    else:
+    elif sharding.is_primary():
+        # a single fit: nothing to share out
         _execute_simple(modelspec, subscribers, y, X, variant_predicates,
                         messages)
 
@@ -534,22 +541,51 @@ def _execute_gwas(genotypes, modelspec, subscribers, y, X, variant_predicates,
         eng.set_sample_sex(
             sample_sex.reindex(Xd.index).values.astype(float))
 
-    if packed_path:
-        blocks = _packed_blocks(genotypes, eng, variant_predicates, messages,
-                                rank, world)
-    else:
-        blocks = _decoded_blocks(genotypes, eng, variant_predicates, messages,
-                                 geno_index, rank, world)
-
     def consume(res, meta):
         _dispatch_block(ResultBlock(model, fit_columns, res, meta, maf_t),
                         subscribers, messages)
 
+    from concurrent.futures import ThreadPoolExecutor
+    if packed_path:
+        # Batches of BATCH_SNPS markers are dealt to the ranks in turn: round i
+        # holds batches i * world .. i * world + world - 1, so that the blocks
+        # gathered after every round are in marker order and rank 0's sinks
+        # write while the GPUs work on the next round.  The sinks of batch i run
+        # on one helper thread (rows stay in marker order) -- both sides spend
+        # their time outside the GIL.
+        plan = _PackedPlan(genotypes, variant_predicates, messages, rank, world)
+        n_rounds = -(-len(plan.batches) // world) if plan.batches else 0
+        with ThreadPoolExecutor(max_workers=1) as pool:
+            pending = []
+            for i in range(n_rounds):
+                j = i * world + rank
+                mine = plan.run(eng, j) if j < len(plan.batches) else None
+                if world == 1:
+                    blocks = [mine]
+                else:
+                    sizes = [len(plan.batches[i * world + r])
+                             if i * world + r < len(plan.batches) else 0
+                             for r in range(world)]
+                    blocks = sharding.gather_round(mine, sizes, eng.n_fields,
+                                                   eng.n_params)
+                if rank != 0:
+                    continue
+                for r, blk in enumerate(blocks):
+                    if blk is None:
+                        continue
+                    res, meta = plan.finish(i * world + r, blk)
+                    if len(meta):
+                        pending.append(pool.submit(consume, res, meta))
+                while len(pending) > 1:
+                    pending.pop(0).result()
+            for f in pending:
+                f.result()
+        logger.info("Analysis completed")
+        return
+
+    blocks = _decoded_blocks(genotypes, eng, variant_predicates, messages,
+                             geno_index, rank, world)
     if world == 1:
-        # stream batch by batch; the sinks of batch i run on one helper
-        # thread (so rows stay in marker order) while the GPU works on batch
-        # i + 1 -- both sides spend their time outside the GIL
-        from concurrent.futures import ThreadPoolExecutor
         with ThreadPoolExecutor(max_workers=1) as pool:
             pending = []
             for res, meta in blocks:
@@ -561,8 +597,8 @@ def _execute_gwas(genotypes, modelspec, subscribers, y, X, variant_predicates,
             for f in pending:
                 f.result()
     else:
-        # every rank finishes its range, then ONE gather of the fixed-size
-        # result blocks to rank 0 (the only collective of the analysis)
+        # decoded sources: every rank finishes its range, then ONE gather of the
+        # fixed-size result blocks to rank 0
         from .engine import Results, NUM_IFIELDS
         parts = [(r, m) for r, m in blocks if r is not None]
         meta = [x for _r, m in parts for x in m]
@@ -585,54 +621,62 @@ def _stock_filter_types():
     return (NameFilter, MAFFilter)
 
 
-def _packed_blocks(reader, eng, predicates, messages, rank, world):
+class _PackedPlan(object):
     """Fast path: the reader exposes SNP-major 2-bit rows (PLINK .bed).
     ``NameFilter`` is applied to the .bim table before anything is read;
-    ``MAFFilter`` (predicates.py:33-57: MAF over ALL samples of the file)
-    is evaluated on the device next to the fit, and the markers it rejects
-    are dropped from the block and listed as skipped."""
-    from .modelspec.predicates import MAFFilter, NameFilter
-    table = reader.variant_table()
-    keep = np.ones(len(table), dtype=bool)
-    maf_min = None
-    for f in predicates:
-        if type(f) is NameFilter:
-            keep &= np.array([t[0] in f.extract for t in table], dtype=bool)
-        elif type(f) is MAFFilter:
-            maf_min = f.maf if maf_min is None else max(maf_min, f.maf)
-    if rank == 0:
-        messages["skipped"].extend(
-            t[0] for t, k in zip(table, keep) if not k)
-    idx = np.flatnonzero(keep)
-    lo, hi = sharding.shard_range(len(idx), world, rank)
-    idx = idx[lo:hi]
-    packed = reader.packed()
-    any_block = False
-    for s in range(0, len(idx), BATCH_SNPS):
-        sel = idx[s:s + BATCH_SNPS]
-        if len(sel) and sel[-1] - sel[0] + 1 == len(sel):
-            rows = packed[sel[0]:sel[-1] + 1]          # contiguous: read in place
+    ``MAFFilter`` (predicates.py:33-57: MAF over ALL samples of the file) is
+    evaluated on the device next to the fit, and the markers it rejects are
+    dropped from the block and listed as skipped.  Every rank builds the same
+    plan (the batches and their metadata follow from the .bim table alone), so
+    nothing but the fixed-size result blocks ever travels between ranks."""
+
+    def __init__(self, reader, predicates, messages, rank, world=1):
+        from .modelspec.predicates import MAFFilter, NameFilter
+        self.table = reader.variant_table()
+        self.packed = reader.packed()
+        self.messages = messages
+        keep = np.ones(len(self.table), dtype=bool)
+        self.maf_min = None
+        for f in predicates:
+            if type(f) is NameFilter:
+                keep &= np.array([t[0] in f.extract for t in self.table], dtype=bool)
+            elif type(f) is MAFFilter:
+                self.maf_min = f.maf if self.maf_min is None else max(self.maf_min, f.maf)
+        if rank == 0:
+            messages["skipped"].extend(
+                t[0] for t, k in zip(self.table, keep) if not k)
+        idx = np.flatnonzero(keep)
+        # several ranks: at least two rounds of smaller batches, so that every GPU works
+        bs = BATCH_SNPS if world == 1 else \
+            max(18944, min(BATCH_SNPS, -(-len(idx) // (2 * world))))
+        self.batches = [idx[s:s + bs] for s in range(0, len(idx), bs)]
+
+    def run(self, eng, j):
+        """Batch ``j`` on this rank's GPU -> (Results, file MAF or None)."""
+        sel = self.batches[j]
+        if sel[-1] - sel[0] + 1 == len(sel):
+            rows = self.packed[sel[0]:sel[-1] + 1]         # contiguous: read in place
         else:
-            rows = packed[sel]
+            rows = self.packed[sel]
         file_maf = None
-        if maf_min is not None:
+        if self.maf_min is not None:
             file_maf = np.empty(len(sel), dtype=np.float64)
-        res = eng.run_packed_host(rows, file_maf=file_maf)
-        meta = [table[i] for i in sel]
-        if maf_min is not None:
-            ok = file_maf >= maf_min                   # NaN (nothing genotyped) -> skipped
+        return eng.run_packed_host(rows, file_maf=file_maf), file_maf
+
+    def finish(self, j, block):
+        """(Results, file MAF) of batch ``j`` -> (Results, metadata) after the
+        MAF filter (rank 0)."""
+        res, file_maf = block
+        meta = [self.table[i] for i in self.batches[j]]
+        if self.maf_min is not None:
+            ok = file_maf >= self.maf_min                  # NaN (nothing genotyped) -> skipped
             if not ok.all():
-                messages["skipped"].extend(m[0] for m, k in zip(meta, ok) if not k)
+                self.messages["skipped"].extend(m[0] for m, k in zip(meta, ok) if not k)
                 from .engine import Results
                 res = Results(np.ascontiguousarray(res.out[:, ok]),
                               np.ascontiguousarray(res.iout[:, ok]), res.n_params)
                 meta = [m for m, k in zip(meta, ok) if k]
-            if not len(meta):
-                continue
-        any_block = True
-        yield res, meta
-    if not any_block:
-        yield None, []
+        return res, meta
 
 
 def _decoded_blocks(reader, eng, predicates, messages, geno_index, rank,

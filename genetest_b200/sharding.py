@@ -2,10 +2,11 @@
 
 The reference's only parallelism is data parallelism over markers through
 worker processes and queues (``genetest/analysis.py:601-633``).  Here it is
-one process per GPU (``torchrun``); every rank owns a contiguous range of the
-markers, nothing is exchanged while computing, and the fixed-size result
-blocks are gathered on rank 0 at the end (NCCL on GPUs; gloo in the CPU
-tests).  No statistic spans markers, so no other collective exists.
+one process per GPU (``torchrun``); the batches of markers are dealt to the
+ranks in turn, nothing is exchanged while computing, and the fixed-size result
+blocks of every round are gathered on rank 0 (NCCL on GPUs; gloo in the CPU
+tests), whose sinks write them in marker order while the next round runs.
+No statistic spans markers, so no other collective exists.
 """
 
 import os
@@ -14,7 +15,35 @@ import sys
 import numpy as np
 
 __all__ = ["rank_world", "is_primary", "local_device", "shard_range",
-           "gather_results", "gather_arrays", "bind_to_device_cpus"]
+           "gather_results", "gather_arrays", "gather_round",
+           "ensure_initialized", "bind_to_device_cpus"]
+
+
+def ensure_initialized():
+    """Under ``torchrun`` (WORLD_SIZE > 1 in the environment) join the process
+    group before anything is shared out: NCCL with this rank's own device when
+    CUDA is there (``torch.cuda.set_device(LOCAL_RANK)``, ``device_id`` so that
+    collectives and object gathers never land on device 0), gloo otherwise (CPU
+    tests).  A multi-rank launch that is not initialised would make every rank
+    run the whole analysis on cuda:0 and write the same files."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return False
+    import torch
+    import torch.distributed as dist
+    if dist.is_initialized():
+        if torch.cuda.is_available() and dist.get_backend() == "nccl":
+            torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        return True
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    if torch.cuda.is_available():
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        bind_to_device_cpus(local)
+    else:
+        dist.init_process_group("gloo")
+    return True
 
 
 def _dist():
@@ -112,6 +141,48 @@ def gather_arrays(arrays):
                 [b[..., :s].cpu().numpy() for b, s in zip(bucket, sizes)],
                 axis=-1))
     return out if rank == 0 else None
+
+
+def gather_round(block, sizes, n_fields, n_params):
+    """One round of the packed path: ``block`` = (Results, file MAF or None) of
+    this rank's batch (None when it has none this round), ``sizes[r]`` the
+    number of markers of rank r's batch (every rank knows them: the plan is
+    deterministic).  The blocks travel as ONE float64 tensor per rank --
+    [n_fields + NUM_IFIELDS + 1, max(sizes)]: result fields, the integer
+    fields, the file-level MAF -- gathered on rank 0 over NCCL (gloo on CPU).
+    Returns the list of blocks in rank order on rank 0, None elsewhere."""
+    dist = _dist()
+    from .engine import Results, NUM_IFIELDS
+    import torch
+    rank, world = dist.get_rank(), dist.get_world_size()
+    nccl = dist.get_backend() == "nccl"
+    dev = torch.device("cuda", local_device()) if nccl else torch.device("cpu")
+    n_max = max(sizes)
+    rows = n_fields + NUM_IFIELDS + 1
+    host = np.zeros((rows, n_max), dtype=np.float64)
+    if block is not None:
+        res, fmaf = block
+        m = res.out.shape[1]
+        host[:n_fields, :m] = res.out
+        host[n_fields:n_fields + NUM_IFIELDS, :m] = res.iout      # int32 values are exact in float64
+        host[-1, :m] = np.nan if fmaf is None else fmaf
+    t = torch.from_numpy(host).to(dev)
+    bucket = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
+    dist.gather(t, bucket, dst=0)
+    if rank != 0:
+        return None
+    out = []
+    for r, m in enumerate(sizes):
+        if m == 0:
+            out.append(None)
+            continue
+        a = bucket[r][:, :m].cpu().numpy()
+        res = Results(np.ascontiguousarray(a[:n_fields]),
+                      np.ascontiguousarray(a[n_fields:n_fields + NUM_IFIELDS]).astype(np.int32),
+                      n_params)
+        fm = np.ascontiguousarray(a[-1])
+        out.append((res, fm))
+    return out
 
 
 def gather_results(res, meta):

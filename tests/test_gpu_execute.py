@@ -478,3 +478,53 @@ def test_maf_filter_runs_on_the_packed_path(tmp_path):
                                             if not m >= 0.05})
     assert outs["packed"][1] == want_skipped
     assert "rs5" in want_skipped and len(outs["packed"][2]) > 0
+
+
+def test_stratified_cox_through_execute(tmp_path):
+    """``outcome=dict(tte=..., event=..., strata=...)``: the strata column of y
+    reaches PHReg(strata=...) in the reference (survival.py:54-56); here it
+    reaches the engine, for a GWAS and for a single fit."""
+    import oracle.gwas as og
+    from genetest_b200.phenotypes import DataFramePhenotypes
+    from genetest_b200.statistics.models.survival import StatsCoxPH
+    rng = np.random.default_rng(31)
+    n, n_snps = 900, 10
+    ids = np.array(["s{:03d}".format(i) for i in range(n)])
+    age = rng.normal(50, 10, n)
+    t_event = rng.exponential(1.0 / np.exp(0.02 * (age - 50)))
+    t_cens = rng.exponential(2.0, n)
+    pheno = pd.DataFrame({
+        "tte": np.ceil(np.minimum(t_event, t_cens) * 20) / 20,
+        "event": (t_event <= t_cens).astype(float), "age": age,
+        "center": rng.integers(0, 3, n).astype(float)}, index=ids)
+    G = rng.binomial(2, 0.3, size=(n_snps, n)).astype(float)
+    names = ["rs{}".format(j) for j in range(n_snps)]
+    info = pd.DataFrame({"chrom": 1, "pos": np.arange(n_snps) + 1, "a1": "A", "a2": "G"},
+                        index=names)
+    spec._reset()
+    modelspec = spec.ModelSpec(
+        outcome=dict(tte=spec.phenotypes.tte, event=spec.phenotypes.event,
+                     strata=spec.phenotypes.center),
+        predictors=[spec.SNPs, spec.phenotypes.age], test="coxph")
+    sub = subscribers.ResultsMemory()
+    analysis.execute(DataFramePhenotypes(pheno),
+                     DataFrameReader(pd.DataFrame(G.T, index=ids, columns=names), info),
+                     modelspec, subscribers=[sub], output_prefix=str(tmp_path / "o"))
+    got = sub._get_gwas_results()
+    Y = pheno[["tte", "event", "center"]].values
+    C = pheno[["age"]].values
+    for j, nm in enumerate(names):
+        st, o = og.gwas_one("coxph", Y, C, ["age"], G[j], coded="G", reference="A")
+        assert st == "ok"
+        for key in ("SNPs", "age"):
+            for f in ("coef", "std_err", "p_value"):
+                assert abs(got[nm][key][f] - o[key][f]) <= 1e-6 * abs(o[key][f]), (nm, key, f)
+    # single fit: Stats*.fit(y, X) with a strata column in y
+    y = pheno[["tte", "event"]].copy()
+    y["strata"] = pheno["center"]
+    X = pd.DataFrame({"age": age, "SNPs": G[0]}, index=ids)
+    one = StatsCoxPH().fit(y, X)
+    st, o = og.gwas_one("coxph", Y, C, ["age"], G[0])
+    # (gwas_one flips to the minor allele; G[0] has MAF 0.3: no flip)
+    assert abs(one["SNPs"]["coef"] - o["SNPs"]["coef"]) <= 1e-6 * abs(o["SNPs"]["coef"])
+    assert abs(one["MODEL"]["log_likelihood"] - o["MODEL"]["log_likelihood"]) <= 1e-8 * abs(o["MODEL"]["log_likelihood"])

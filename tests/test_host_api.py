@@ -364,6 +364,90 @@ def test_gather_results_two_ranks_gloo(tmp_path):
     assert os.path.exists(str(tmp_path / "ok"))
 
 
+def _round_worker(rank, world, port, tmp):
+    """The packed path of a multi-rank analysis without a GPU: the batch plan, the
+    dealing of batches to ranks and the per-round gather (gloo), with a fake
+    engine that derives every number from the marker's row index."""
+    import torch.distributed as dist
+    from genetest_b200 import analysis, sharding as sh
+    from genetest_b200.engine import Results
+    from genetest_b200.modelspec.predicates import MAFFilter, NameFilter
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WORLD_SIZE=str(world),
+                      RANK=str(rank), LOCAL_RANK=str(rank))
+    assert sh.ensure_initialized()
+    try:
+        assert sh.rank_world() == (rank, world)
+        n_markers = 1000
+        table = [("rs{}".format(i), "1", i, "A", "G") for i in range(n_markers)]
+
+        class Reader(object):
+            def variant_table(self):
+                return table
+
+            def packed(self):
+                return np.arange(n_markers, dtype=np.int64)[:, None].view(np.uint8)
+
+        class Eng(object):
+            n_fields, n_params = 10, 1
+
+            def run_packed_host(self, rows, file_maf=None):
+                idx = np.ascontiguousarray(rows).view(np.int64)[:, 0]
+                if file_maf is not None:
+                    file_maf[:] = (idx % 10) / 20.0
+                out = np.outer(np.arange(1, 11), idx).astype(float)
+                iout = np.vstack([idx % 3 == 0, idx, idx % 2, idx * 0]).astype(np.int32)
+                return Results(out, iout, 1)
+
+        old = analysis.BATCH_SNPS
+        analysis.BATCH_SNPS = 64
+        try:
+            messages = {"skipped": [], "failed": []}
+            plan = analysis._PackedPlan(
+                Reader(), [NameFilter({t[0] for t in table[5:]}), MAFFilter(0.1)],
+                messages, rank, world)
+            plan.batches = [b[:40] for b in plan.batches]      # small batches, several rounds
+            got = []
+            n_rounds = -(-len(plan.batches) // world)
+            for i in range(n_rounds):
+                j = i * world + rank
+                mine = plan.run(Eng(), j) if j < len(plan.batches) else None
+                sizes = [len(plan.batches[i * world + r]) if i * world + r < len(plan.batches)
+                         else 0 for r in range(world)]
+                blocks = sh.gather_round(mine, sizes, 10, 1)
+                if rank == 0:
+                    for r, blk in enumerate(blocks):
+                        if blk is not None:
+                            got.append(plan.finish(i * world + r, blk))
+                else:
+                    assert blocks is None
+        finally:
+            analysis.BATCH_SNPS = old
+        if rank == 0:
+            names = [m[0] for _res, meta in got for m in meta]
+            want = [t[0] for b in plan.batches for t in (table[i] for i in b)
+                    if (t[2] % 10) / 20.0 >= 0.1]
+            assert names == want                           # marker order, MAF filter applied
+            nobs = np.concatenate([res.nobs for res, _m in got])
+            assert nobs.tolist() == [int(nm[2:]) for nm in names]
+            out0 = np.concatenate([res.out[9] for res, _m in got])
+            np.testing.assert_array_equal(out0, 10.0 * nobs)
+            assert set(messages["skipped"]) >= {"rs0", "rs4", "rs10", "rs11"}
+            open(os.path.join(tmp, "ok2"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_multi_rank_packed_rounds_gloo(tmp_path):
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_round_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(str(tmp_path / "ok2"))
+
+
 # ---- streaming result sink ---------------------------------------------------------------
 def test_native_formatter_matches_python_repr():
     from genetest_b200.engine import format_rows
