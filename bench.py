@@ -370,6 +370,29 @@ def measure_side_workload(eng, torch, dist, rank, world, workload, steps,
     return res
 
 
+def measure_h2d_ceiling(torch, dist, world, mib=256, reps=8):
+    """What the box can move host -> device when every rank copies at once: each
+    rank streams ``reps`` x ``mib`` MiB from pinned memory to its GPU (one
+    cudaMemcpyAsync per copy); aggregate GB/s over the slowest rank.  The
+    end-to-end figure is bounded by it."""
+    src = torch.empty(mib << 20, dtype=torch.uint8).pin_memory()
+    dst = torch.empty(mib << 20, dtype=torch.uint8, device="cuda")
+    dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    return world * reps * (mib << 20) / dt / 1e9
+
+
 def measure_execute(torch, eng, n, snps, k_cov):
     """End to end through the reference's entry point: ``analysis.execute_formula``
     + ``GWASWriter`` on a real PLINK .bed / .bim / .fam (tmpfs), phenotype table
@@ -571,6 +594,8 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_dt = float(t.item())
     e2e_value = world * e2e_snps * e2e_steps / e2e_dt
+    h2d_ceiling = measure_h2d_ceiling(torch, dist, world)
+    del host_packed, host_out, host_iout
 
     peaks = {}
     try:
@@ -689,7 +714,11 @@ def run_ours(args, rank, world, local_rank):
                 "h2d_bytes_per_step": int(hp.nbytes),
                 "d2h_bytes_per_step": int(ho.nbytes + hi.nbytes),
                 "snps_per_step": e2e_snps, "steps": e2e_steps,
-                "call": "gt_run_packed_host (pinned host buffers)"},
+                "call": "gt_run_packed_host (pinned host buffers)",
+                # the copy-in alone, all ranks at once, against what it achieved
+                "h2d_ceiling_gbs": h2d_ceiling,
+                "h2d_achieved_gbs": e2e_value * ((n + 3) // 4) / 1e9,
+                "frac_of_h2d_ceiling": e2e_value * ((n + 3) // 4) / 1e9 / h2d_ceiling},
         "gpu_launches": int(all_launches),
         "clocks": clocks,
     }

@@ -123,6 +123,13 @@ __device__ __forceinline__ bool elect_one() {
         : "=r"(pred));
     return pred != 0;
 }
+// x >> 16 as the high half of x * 2^16: an IMAD.HI on the FMA pipe instead of a shift on the
+// ALU pipe, which the expansion loop saturates (LOP3 / SHF / PRMT all issue there)
+__device__ __forceinline__ uint32_t hi16(uint32_t x) {
+    uint32_t r;
+    asm("mul.hi.u32 %0, %1, 65536;\n" : "=r"(r) : "r"(x));
+    return r;
+}
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     uint4 r;
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n"
@@ -255,20 +262,27 @@ contract_tc2_kernel(const __grid_constant__ CUtensorMap gmap, const Tc2Params P)
             for (int j = 0; j < 4; ++j) {
                 const uint32_t w = words[j];
                 const uint32_t wm = w | masks[j];
-                const uint32_t s1 = wm >> 1;
-                homf[j] = ~(wm | s1) & 0x55555555u;          // code 00
-                misf[j] = wm & ~s1 & 0x55555555u;            // code 01
+                // flags of an even word sit on the even bits, those of an odd word on the odd
+                // bits, so that two words share one flag word without any realignment
+                if (!(j & 1)) {
+                    const uint32_t s1 = wm >> 1;
+                    homf[j] = ~(wm | s1) & 0x55555555u;          // code 00
+                    misf[j] = wm & ~s1 & 0x55555555u;            // code 01
+                } else {
+                    const uint32_t s1 = wm << 1;
+                    homf[j] = ~(wm | s1) & 0xaaaaaaaau;
+                    misf[j] = s1 & ~wm & 0xaaaaaaaau;
+                }
                 const uint32_t even = w & 0x33333333u, odd = (w >> 2) & 0x33333333u;
                 a[j * 4 + 0] = prmt(lut, 0u, even);
-                a[j * 4 + 1] = prmt(lut, 0u, even >> 16);
+                a[j * 4 + 1] = prmt(lut, 0u, hi16(even));
                 a[j * 4 + 2] = prmt(lut, 0u, odd);
-                a[j * 4 + 3] = prmt(lut, 0u, odd >> 16);
+                a[j * 4 + 3] = prmt(lut, 0u, hi16(odd));
             }
 #pragma unroll
             for (int pr = 0; pr < 2; ++pr) {
-                // two words share one flag word: even bits = word 2 pr, odd bits = word 2 pr + 1
-                if (!(DBG & 16)) nhom += __popc(homf[2 * pr] + 2u * homf[2 * pr + 1]);
-                const uint32_t mis2 = misf[2 * pr] + 2u * misf[2 * pr + 1];
+                if (!(DBG & 16)) nhom += __popc(homf[2 * pr] | homf[2 * pr + 1]);
+                const uint32_t mis2 = misf[2 * pr] | misf[2 * pr + 1];
                 if (!(DBG & 1)) {
                     // predicated, not branched: (pair index, flags) when any flag is set
                     asm volatile(
