@@ -370,7 +370,7 @@ def measure_side_workload(eng, torch, dist, rank, world, workload, steps,
     return res
 
 
-def measure_h2d_ceiling(torch, dist, world, mib=256, reps=8):
+def measure_h2d_ceiling(torch, dist, world, mib=512, reps=16):
     """What the box can move host -> device when every rank copies at once: each
     rank streams ``reps`` x ``mib`` MiB from pinned memory to its GPU (one
     cudaMemcpyAsync per copy); aggregate GB/s over the slowest rank.  The
@@ -438,6 +438,8 @@ def measure_execute(torch, eng, n, snps, k_cov):
         df = df.iloc[rng.permutation(n)]
         formula = "y ~ SNPs + " + " + ".join(names[:-1])
 
+        names_q = {"rs{}".format(i) for i in range(snps // 4)}
+
         def run(tag, predicates):
             spec._reset()
             out = os.path.join(tmp, tag)
@@ -450,9 +452,15 @@ def measure_execute(torch, eng, n, snps, k_cov):
             rows = sum(1 for _ in open(out + ".tsv")) - 1
             return dt, rows, os.path.getsize(out + ".tsv")
         run("warm", [NameFilter({"rs{}".format(i) for i in range(4096)})])
+        dt_q, rows_q, _ = run("quarter", [NameFilter(names_q)])
         dt, rows, tsv_bytes = run("full", None)
+        # the analysis has a fixed part (phenotype alignment, QR and digit planes of the
+        # design, .bim parsing) and a per-marker part: the rate of the latter from the
+        # two sizes
+        marginal = (rows - rows_q) / max(dt - dt_q, 1e-9)
         return {"value": rows / dt, "unit": "SNP-tests/s", "seconds": dt,
                 "snps": snps, "rows_written": rows,
+                "quarter_file_seconds": dt_q, "marginal_snps_per_s": marginal,
                 "bed_bytes": snps * bps + 3, "tsv_bytes": tsv_bytes,
                 "call": "analysis.execute_formula + GWASWriter on a PLINK .bed "
                         "(tmpfs, mmap -> pinned staging -> H2D), TSV written; "
@@ -646,7 +654,11 @@ def run_ours(args, rank, world, local_rank):
     traffic = None
     try:        # dram bytes per launch of the dominant kernel, from the ncu capture
         prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic = prof.get(workload, {}).get("dram_bytes_per_launch")
+        rec = prof.get(workload, {})
+        traffic = rec.get("dram_bytes_per_launch")
+        if traffic and rec.get("snps_per_launch"):
+            # the capture is one launch of `snps_per_launch` markers: scale to this run's launches
+            traffic = traffic * per_launch_snps / rec["snps_per_launch"]
     except Exception:
         pass
     flop_per_snp = flops_per_snp(workload, n, p, mean_iter)

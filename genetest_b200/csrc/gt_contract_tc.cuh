@@ -1,56 +1,10 @@
-// K1 + K2 on the 5th-generation tensor cores (tcgen05, kind::i8): the exact
-// integer formulation of the genotype contraction.
-//
-// Genotype dosages are the small integers {0,1,2}; every column of E is split
-// on the host into eight balanced base-128 digits (int8, 56-bit fixed point
-// relative to the column's max), so  sum_i g_i E_ic  becomes eight exact int32
-// dot products that are recombined in FP64 in the epilogue -- the same sums
-// the FP64 kernel (gt_contract.cuh) produces, to ~1e-16 relative.
-//
-//   A (128 SNP rows x K samples, int8)  lives in TENSOR MEMORY: each of 128
-//     threads owns one SNP row, streams its 2-bit codes from HBM with 128-bit
-//     loads, expands them with a byte-permute lookup (PRMT) and stores them
-//     with tcgen05.st -- no shared-memory staging of genotypes at all;
-//   B (N = 8 * columns, K-major, 128B swizzle) is a pre-swizzled image of the
-//     digit planes, fetched per 128-sample stage with one cp.async.bulk (TMA
-//     bulk copy) that completes on an mbarrier;
-//   D (128 x N int32) accumulates in TMEM; one elected thread issues
-//     tcgen05.mma.cta_group::1.kind::i8 (M=128, N, K=32), tcgen05.commit
-//     releases the stage.
-// Warp roles: 0-7 expand + epilogue (two threads per SNP row, 64 samples of a
-// stage each), 8 bulk-copy producer, 9 MMA issuer.  Two CTAs per SM.
+// mbarrier / bulk-copy / descriptor helpers shared by the tcgen05 contraction
+// (gt_contract_tc2.cuh) and the streaming correction kernel (gt_corr_stream.cuh).
 #pragma once
 
 #include "gt_common.cuh"
 
 namespace gtk {
-
-constexpr int kTcStages = 4;          // pipeline depth (A in TMEM, B in smem)
-constexpr int kTcStageK = 128;        // samples per stage (4 MMAs of K=32)
-constexpr int kTcThreads = 320;       // 8 expansion warps, 1 producer, 1 MMA issuer
-
-struct TcParams {
-    const uint8_t *geno;      // packed rows
-    long long pitch;
-    int n_snps;
-    const uint8_t *ormask;    // [pitch] (only the class counts need it)
-    const uint8_t *Bimg;      // [n_stages][N*128] pre-swizzled digit planes
-    const double *scale;      // [ncol] column scale * 2^-54
-    int n_stages;
-    int ncol;                 // live E columns (N = 8 * ncol + 1 rounded up to 16)
-    int ones_col;             // D column of the ones plane (design indicator): sum of the dosages
-    int N;
-    int NCP;                  // S row stride
-    double *S;
-    int *counts;
-    double *gsum;
-    int *error_flag;          // set when a bounded wait times out
-    int *mlist;               // [n_snps][2][mcap / 2] positions of the missing samples
-    int mcap;                 // capacity per SNP (two halves)
-    int *mcount;              // [n_snps][2] entries per half, -1 when a half overflowed
-    int mask_zero_lines;      // leading 128-B lines of ormask that are entirely zero
-    int dbg;                  // tuning only: 1 no list emission, 2 no MMA, 4 no TMEM store, 8 no loads, 16 no counts
-};
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return (uint32_t)__cvta_generic_to_shared(p);
@@ -110,248 +64,6 @@ __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr) {
     d |= (uint64_t)1 << 46;                              // descriptor version (Blackwell)
     d |= (uint64_t)2 << 61;                              // SWIZZLE_128B
     return d;
-}
-
-template <int NT /* N / 16, N <= 256 */>
-__global__ void __launch_bounds__(kTcThreads, 2)
-contract_tc_kernel(TcParams P) {
-    constexpr int N = 16 * NT;
-    constexpr int BSTAGE = N * 128;                      // bytes of one B stage
-    constexpr int TMEM_COLS = (N + kTcStages * 32) <= 128 ? 128 : ((N + kTcStages * 32) <= 256 ? 256 : 512);
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    // the 128B swizzle is a function of the shared-memory address: 1024 B alignment
-    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    unsigned char *sB = smem;                                            // kTcStages * BSTAGE
-    uint64_t *bars = (uint64_t *)(smem + kTcStages * BSTAGE);
-    uint64_t *a_full = bars, *b_full = bars + kTcStages, *empty = bars + 2 * kTcStages,
-             *d_full = bars + 3 * kTcStages;
-    uint32_t *tmem_slot = (uint32_t *)(bars + 3 * kTcStages + 1);
-    int *fail = (int *)(tmem_slot + 1);
-    int *cnt_s = (int *)(tmem_slot + 2);                 // [2][128][2]: n_hom, list length of each half row
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid == 0) {
-        for (int s = 0; s < kTcStages; ++s) { mbar_init(&a_full[s], 256); mbar_init(&b_full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(d_full, 1);
-        *fail = 0;
-        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-    }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n"
-                     ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;\n");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;\n");
-    const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_d = tmem_base;                   // columns [0, N)
-    const uint32_t tmem_a = tmem_base + N;               // kTcStages x 32 columns
-    const int n_stages = P.n_stages;
-
-    if (warp < 8) {
-        // ===== expansion: two threads per SNP row, 64 samples of a stage each =====
-        const int half = warp >> 2;
-        const int row = (warp & 3) * 32 + lane;
-        const int snp = min(blockIdx.x * 128 + row, P.n_snps - 1);
-        const unsigned char *grow = P.geno + (long long)snp * P.pitch + half * 16;
-        const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
-        int nhom = 0;
-        // the two threads of a row see disjoint samples: each emits its own
-        // in-order list of missing samples, no atomics
-        const bool owner = blockIdx.x * 128 + row < P.n_snps;
-        const int hcap = P.mcap >> 1;
-        int *mrow = P.mlist + (long long)snp * P.mcap + half * hcap;
-        int mcur = 0;
-        // the thread's 16 B of four consecutive stages live in registers
-        uint4 cur[4], nxt[4], nx2[4];      // two lines of prefetch cover the DRAM latency
-        const int n_lines = (n_stages + 3) / 4;
-        auto load_line = [&](int line, uint4 *dst) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                long long off = (long long)line * 128 + q * 32;
-                dst[q] = (off + half * 16 + 16 <= P.pitch && !(P.dbg & 8)) ? ldg_stream16(grow + off)
-                                                           : make_uint4(~0u, ~0u, ~0u, ~0u);
-            }
-        };
-        load_line(0, cur);
-        if (n_lines > 1) load_line(1, nxt);
-        for (int line = 0; line < n_lines; ++line) {
-#pragma unroll
-            for (int sub = 0; sub < 4; ++sub) {
-                // Prefetch two lines ahead, issued in the MIDDLE of the line: the
-                // scoreboard that guards `cur` at the top of the next line also
-                // counts these loads, so they must be old by then.
-                if (sub == 2 && line + 2 < n_lines) load_line(line + 2, nx2);
-                const int it = line * 4 + sub;
-                if (it >= n_stages) break;
-                const int s = it % kTcStages;
-                const uint32_t par = ((it / kTcStages) & 1) ^ 1;
-                // mask words of this half stage (same for every row: broadcast load)
-                const long long moff = (long long)it * 32 + half * 16;
-                uint4 m4 = make_uint4(0u, 0u, 0u, 0u);       // every sample of the line is a design row
-                if (line >= P.mask_zero_lines)
-                    m4 = (moff + 16 <= P.pitch) ? __ldg((const uint4 *)(P.ormask + moff))
-                                                : make_uint4(~0u, ~0u, ~0u, ~0u);
-                const uint4 pw = cur[sub];
-                const uint32_t words[4] = {pw.x, pw.y, pw.z, pw.w};
-                const uint32_t masks[4] = {m4.x, m4.y, m4.z, m4.w};
-                uint32_t a[16];
-                uint32_t mflag[2];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const uint32_t w = words[j];
-                    const uint32_t wm = w | masks[j];
-                    const uint32_t lo = wm & 0x55555555u, hi = (wm >> 1) & 0x55555555u;
-                    const uint32_t mb = lo & ~hi;
-                    // the only class count taken here: sum g comes from the
-                    // ones plane of B, the missing count from the list lengths
-                    if (!(P.dbg & 16)) nhom += __popc(~(lo | hi) & 0x55555555u);
-                    // flags of two consecutive words share one 32-bit word
-                    if (j & 1) mflag[j >> 1] |= mb << 1; else mflag[j >> 1] = mb;
-                    // code -> dosage byte: 00 -> 2, 01 -> 0, 10 -> 1, 11 -> 0
-                    const uint32_t even = w & 0x33333333u, odd = (w >> 2) & 0x33333333u;
-                    a[j * 4 + 0] = prmt(0x00010002u, 0u, even);
-                    a[j * 4 + 1] = prmt(0x00010002u, 0u, even >> 16);
-                    a[j * 4 + 2] = prmt(0x00010002u, 0u, odd);
-                    a[j * 4 + 3] = prmt(0x00010002u, 0u, odd >> 16);
-                }
-                if (owner && !(P.dbg & 1)) {        // emit the missing samples of this half stage, in order
-                    unsigned long long m = (unsigned long long)mflag[0] | ((unsigned long long)mflag[1] << 32);
-                    while (m) {
-                        int b = __ffsll((long long)m) - 1;
-                        int word = half * 4 + (b >> 5) * 2 + (b & 1);
-                        if (mcur < hcap) mrow[mcur] = it * kTcStageK + word * 16 + ((b & 31) >> 1);
-                        ++mcur;
-                        m &= m - 1;
-                    }
-                }
-                // publish the PREVIOUS stage only now: its TMEM store drained while
-                // this stage's bytes were being expanded
-                if (it > 0) {
-                    asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
-                    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-                    mbar_arrive(&a_full[(it - 1) % kTcStages]);
-                }
-                if (it >= kTcStages && !mbar_wait(&empty[s], par, fail)) { *fail = 1; }
-                asm volatile("tcgen05.fence::after_thread_sync;\n");
-                const uint32_t taddr = tmem_a + lane_base + s * 32 + half * 16;
-                if (!(P.dbg & 4))
-                asm volatile(
-                    "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-                    "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};\n"
-                    ::"r"(taddr),
-                      "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
-                      "r"(a[8]), "r"(a[9]), "r"(a[10]), "r"(a[11]), "r"(a[12]), "r"(a[13]), "r"(a[14]), "r"(a[15])
-                    : "memory");
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) { cur[q] = nxt[q]; nxt[q] = nx2[q]; }
-        }
-        if (n_stages > 0) {
-            asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
-            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-            mbar_arrive(&a_full[(n_stages - 1) % kTcStages]);
-        }
-        // both halves of a row publish their counts; whoever reads the ones
-        // column in the epilogue writes the totals
-        cnt_s[(half * 128 + row) * 2 + 0] = nhom;
-        cnt_s[(half * 128 + row) * 2 + 1] = mcur;
-        asm volatile("bar.sync 1, 256;\n" ::: "memory");
-        const int out_snp = blockIdx.x * 128 + row;
-        if (out_snp < P.n_snps) {
-            P.mcount[(long long)out_snp * 2 + half] = (mcur <= hcap) ? mcur : -1;
-            if (half == 0)
-                for (int col = P.ncol; col < P.NCP; ++col) P.S[(long long)out_snp * P.NCP + col] = 0.0;
-        }
-        // ===== epilogue: D (int32, TMEM) -> FP64 sums; the halves interleave 32-column groups =====
-        if (!mbar_wait(d_full, 0, fail)) *fail = 1;
-        asm volatile("tcgen05.fence::after_thread_sync;\n");
-#pragma unroll 1
-        for (int c0 = half * 32; c0 < N; c0 += 64) {
-            uint32_t d[32];
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-                "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
-                : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7]),
-                  "=r"(d[8]), "=r"(d[9]), "=r"(d[10]), "=r"(d[11]), "=r"(d[12]), "=r"(d[13]), "=r"(d[14]), "=r"(d[15]),
-                  "=r"(d[16]), "=r"(d[17]), "=r"(d[18]), "=r"(d[19]), "=r"(d[20]), "=r"(d[21]), "=r"(d[22]), "=r"(d[23]),
-                  "=r"(d[24]), "=r"(d[25]), "=r"(d[26]), "=r"(d[27]), "=r"(d[28]), "=r"(d[29]), "=r"(d[30]), "=r"(d[31])
-                : "r"(tmem_d + lane_base + c0));
-            asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-#pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-                const int col = c0 / 8 + cc;          // 8 digit planes per E column
-                double acc = (double)(int)d[cc * 8 + 7];
-#pragma unroll
-                for (int sl = 6; sl >= 0; --sl) acc = fma(acc, 128.0, (double)(int)d[cc * 8 + sl]);
-                if (col < P.ncol && out_snp < P.n_snps)
-                    P.S[(long long)out_snp * P.NCP + col] = acc * P.scale[col];
-                if (c0 + cc * 8 == P.ones_col && out_snp < P.n_snps) {
-                    // exact integer: sum of the dosages over the design rows
-                    const int sum_g = (int)d[cc * 8];
-                    const int n_hom = cnt_s[row * 2] + cnt_s[(128 + row) * 2];
-                    const int n_mis = cnt_s[row * 2 + 1] + cnt_s[(128 + row) * 2 + 1];
-                    P.counts[(long long)out_snp * 4 + 0] = sum_g - 2 * n_hom;
-                    P.counts[(long long)out_snp * 4 + 1] = n_hom;
-                    P.counts[(long long)out_snp * 4 + 2] = n_mis;
-                    P.counts[(long long)out_snp * 4 + 3] = 0;
-                    P.gsum[(long long)out_snp * 2 + 0] = (double)sum_g;
-                    P.gsum[(long long)out_snp * 2 + 1] = (double)(sum_g + 2 * n_hom);
-                }
-            }
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-    } else if (warp == 8) {
-        // ===== B producer: one bulk copy per stage =====
-        if (lane == 0) {
-            for (int it = 0; it < n_stages; ++it) {
-                const int s = it % kTcStages;
-                const uint32_t par = ((it / kTcStages) & 1) ^ 1;
-                if (it >= kTcStages && !mbar_wait<true>(&empty[s], par, fail)) { *fail = 1; }
-                mbar_expect_tx(&b_full[s], BSTAGE);
-                bulk_g2s(sB + s * BSTAGE, P.Bimg + (long long)it * BSTAGE, BSTAGE, &b_full[s]);
-            }
-        }
-    } else {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            // instruction descriptor: D=S32, A=U8 (dosages), B=S8 (digits), K-major both
-            const uint32_t idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) |
-                                   ((uint32_t)(128 >> 4) << 24);
-            for (int it = 0; it < n_stages; ++it) {
-                const int s = it % kTcStages;
-                const uint32_t par = (it / kTcStages) & 1;
-                if (!mbar_wait<true>(&a_full[s], par, fail)) *fail = 1;
-                if (!mbar_wait<true>(&b_full[s], par, fail)) *fail = 1;
-                asm volatile("tcgen05.fence::after_thread_sync;\n");
-                const uint32_t bbase = smem_u32(sB + s * BSTAGE);
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                    if (P.dbg & 2) break;
-                    const uint64_t bdesc = tc_smem_desc(bbase + kk * 32);
-                    const uint32_t acol = tmem_a + s * 32 + kk * 8;
-                    const uint32_t accum = (it > 0 || kk > 0) ? 1u : 0u;
-                    asm volatile(
-                        "{\n\t.reg .pred p;\n\t"
-                        "setp.ne.b32 p, %4, 0;\n\t"
-                        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t}\n"
-                        ::"r"(tmem_d), "r"(acol), "l"(bdesc), "r"(idesc), "r"(accum),
-                          "r"(0u), "r"(0u), "r"(0u), "r"(0u) : "memory");
-                }
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
-                             ::"r"(smem_u32(&empty[s])) : "memory");
-            }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
-                         ::"r"(smem_u32(d_full)) : "memory");
-        }
-    }
-    __syncthreads();
-    if (tid == 0 && *fail) atomicExch(P.error_flag, 1);
-    if (warp == 0) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(TMEM_COLS));
-    }
 }
 
 }  // namespace gtk

@@ -1,5 +1,6 @@
 """Time the tcgen05 contraction with parts compiled out (tuning probe):
-option "tc_debug" bits 1 no records, 2 no MMA, 4 no TMEM store, 16 no counts."""
+option "tc_debug" (variants compiled in: 1 no records, 2 no MMA, 6 no MMA / TMEM store,
+14 + genotypes from L2, 61 MMA only, 63 synchronisation skeleton, 128 wait cycles per role)."""
 import sys
 sys.path.insert(0, ".")
 import numpy as np, torch
@@ -14,7 +15,7 @@ eng.set_design("linear", y, C)
 eng.set_option("contract_tc", 1)
 packed = eng.synth_packed(n, snps, seed=1, missing_rate=0.01)
 out, iout = eng.alloc_results(snps)
-for dbg in [int(a) for a in sys.argv[2:]] or (0, 128, 191):
+for dbg in [int(a) for a in sys.argv[2:]] or (0, 1, 2, 6, 14, 61, 63, 128):
     eng.set_option("tc_debug", dbg)
     for _ in range(1):
         eng.run_packed_dev(packed, snps, packed.stride(0), out, iout)
