@@ -139,10 +139,15 @@ missing_corr_stream_kernel(const CorrStreamParams P) {
         for (int c = 0; c < 12; ++c) vA[c] = vB[c] = 0.0;
         uint32_t pairA = 0x7FFFFFFFu, pairB = 0x7FFFFFFFu;   // pair of the row waiting in the buffer
         uint32_t limit = 0;
+        // load_next issues the row of the thread's next sample (or of zeros) into a buffer and
+        // reads the following record speculatively; advance(), called after the FMAs of the other
+        // buffer, consumes that read -- so neither shared-memory latency is waited for.
+        uint2 nr = make_uint2(0u, 0u);
+        bool adv = false;
         auto load_next = [&](double (&v)[12], uint32_t &vp) {
             // the oldest copy in flight (the next record pair) has landed after this
             asm volatile("cp.async.wait_group 5;\n" ::: "memory");
-            const uint2 nr = rec_at(ri + 1);                 // speculative: used when this record runs out
+            nr = rec_at(ri + 1);                             // speculative: used when this record runs out
             const bool have = pair < limit;
             const int bit = __ffs((int)f) - 1;
             const uint32_t fnew = f & (f - 1);
@@ -158,14 +163,22 @@ missing_corr_stream_kernel(const CorrStreamParams P) {
                              : "r"(((c & 1) ? addr1 : addr0) + 32 * (c >> 1)));
             vp = have ? pair : 0x7FFFFFFFu;
             n_miss += have ? 1 : 0;
-            const bool adv = have && fnew == 0;
+            adv = have && fnew == 0;
             f = have ? fnew : f;
-            if (adv) {
-                ++ri;
-                pair = ri < nrec ? nr.x : 0x7FFFFFFFu;
-                f = ri < nrec ? nr.y : 0u;
-                if (!(ri & 1)) fetch((ri >> 1) + 6);
-            }
+        };
+        auto advance = [&]() {           // branch-free: everything is selected / predicated on `adv`
+            ri += adv ? 1 : 0;
+            const bool more = ri < nrec;
+            pair = adv ? (more ? nr.x : 0x7FFFFFFFu) : pair;
+            f = adv ? (more ? nr.y : 0u) : f;
+            const uint32_t q = (uint32_t)(ri >> 1) + 6u;
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "setp.ne.u32 p, %0, 0;\n\t"
+                "@p cp.async.ca.shared.global [%1], [%2], 16;\n\t"
+                "@p cp.async.commit_group;\n\t}\n"
+                ::"r"((uint32_t)(adv && !(ri & 1))), "r"(ring + (q & 7u) * (kCsSnps * 16)), "l"(recs + 2 * q)
+                : "memory");
         };
         auto accumulate = [&](const double (&v)[12]) {
             int e = 0;
@@ -191,10 +204,12 @@ missing_corr_stream_kernel(const CorrStreamParams P) {
                 if (polled) { ++landed; limit += ppb; polled = false; }
                 load_next(vB, pairB);
                 accumulate(vA);
+                advance();
                 if (landed < b + 2 && landed + 1 < nblk)
                     polled = mbar_test(smem_u32(&full[(landed + 1) % kCsBuf]), ((landed + 1) / kCsBuf) & 1);
                 load_next(vA, pairA);
                 accumulate(vB);
+                advance();
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[b % kCsBuf]);
