@@ -200,12 +200,12 @@ missing_corr_stream_kernel(const CorrStreamParams P) {
             bool polled = false;
             // until no lane of the warp has a sample of block b left (in a buffer or in its records)
             while (__any_sync(GT_FULL, pair < end_b || pairA < end_b)) {
-                // a lane that is done with block b runs ahead into the next two blocks once they have landed
+                // a lane that is done with block b runs ahead into the other blocks of the ring once they have landed
                 if (polled) { ++landed; limit += ppb; polled = false; }
                 load_next(vB, pairB);
                 accumulate(vA);
                 advance();
-                if (landed < b + 2 && landed + 1 < nblk)
+                if (landed < b + kCsBuf - 1 && landed + 1 < nblk)
                     polled = mbar_test(smem_u32(&full[(landed + 1) % kCsBuf]), ((landed + 1) / kCsBuf) & 1);
                 load_next(vA, pairA);
                 accumulate(vB);
