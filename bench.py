@@ -241,6 +241,28 @@ def run_reference(args, rank, world):
 
 
 
+def tc_shape(kernel_name):
+    """(N, MMA rows per marker) of the tcgen05 contraction the engine picked, from the
+    kernel name it reports (contract_tc2_kernel<NT=..,TILES=..,HOM=..>), else None."""
+    import re
+    m = re.match(r"contract_tc2_kernel<NT=(\d+),TILES=(\d+),HOM=(\d+)>", kernel_name or "")
+    return (16 * int(m.group(1)), 2 if int(m.group(3)) else 1) if m else None
+
+
+def tc_roofline(kernel_name, n, per_launch_snps, kernel_ms, peaks):
+    """int8 tensor-core figures of one contraction launch: 2 n N operations per MMA row;
+    peak = twice the measured dense bf16 rate (kind::i8 runs at twice the bf16 rate)."""
+    N, rows = tc_shape(kernel_name)
+    ops = 2.0 * n * N * rows
+    peak = 2.0 * float(peaks.get("bf16_tflops", 2250.0))
+    ach = per_launch_snps * ops / (kernel_ms * 1e-3) / 1e12
+    return {"pipe": "tcgen05 kind::i8", "achieved_tops": ach, "peak_tops": peak,
+            "frac": ach / peak,
+            "peak_source": "2 x bf16_tflops of MEASURED_PEAKS.json (burst)" if "bf16_tflops" in peaks
+                           else "2 x nominal dense bf16", "ops_per_snp": ops, "N": N,
+            "mma_rows_per_marker": rows}
+
+
 def flops_per_snp(workload, n, p, mean_iter):
     """FP64 work of one marker."""
     model = base_model(workload)
@@ -328,9 +350,10 @@ def measure_side_workload(eng, torch, dist, rank, world, workload, steps,
     achieved_gbs = per_launch * bytes_per_snp / (kernel_ms * 1e-3) / 1e9
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     model = base_model(workload)
-    if workload == "linear":
+    if model == "linear" and tc_shape(eng.dominant_kernel()):
         roof = {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved_gbs / hbm_peak, "kernel": "contract_tc2_kernel"}
+                "frac": achieved_gbs / hbm_peak, "kernel": eng.dominant_kernel(),
+                "compute": tc_roofline(eng.dominant_kernel(), n, per_launch, kernel_ms, peaks)}
     else:
         # interaction designs run the FP64 FMA contraction, the iterative models
         # accumulate with FP64 tensor-core MMAs: each against its own measured peak
@@ -663,18 +686,15 @@ def run_ours(args, rank, world, local_rank):
         pass
     flop_per_snp = flops_per_snp(workload, n, p, mean_iter)
     fp64_achieved = per_launch_snps * flop_per_snp / (kernel_ms * 1e-3) / 1e12
-    if workload == "linear" and args.contract == "tc":
-        # exact fixed point on the int8 tensor cores: 7 digit planes for each of the
-        # p - 1 columns that are not derived from the constant + the plane of ones,
-        # rounded up to the N = 16 * ceil(.) columns of the MMA
-        ops_per_snp = 2.0 * n * 16 * ((7 * (p - 1) + 1 + 15) // 16)
-        compute = {"pipe": "tcgen05 kind::i8",
-                   "achieved_tops": per_launch_snps * ops_per_snp /
-                   (kernel_ms * 1e-3) / 1e12,
-                   "nominal_dense_peak_tops": 4500.0,
-                   "ops_per_snp": ops_per_snp,
-                   "fp64_fma_peak_tflops_measured": fp64_peak,
-                   "fp64_dmma_peak_tflops_measured": dmma_peak}
+    on_tc = base_model(workload) == "linear" and tc_shape(dominant) is not None
+    if on_tc:
+        # exact fixed point on the int8 tensor cores: 7 digit planes for each column
+        # that is not derived from the constant + the plane of ones, rounded up to the
+        # N = 16 * ceil(.) columns of the MMA (interaction designs: a second MMA row per
+        # marker carries the homozygote indicator for the g^2 sums)
+        compute = tc_roofline(dominant, n, per_launch_snps, kernel_ms, peaks)
+        compute.update({"fp64_fma_peak_tflops_measured": fp64_peak,
+                        "fp64_dmma_peak_tflops_measured": dmma_peak})
     else:
         compute = {"pipe": "fp64", "achieved_tflops": fp64_achieved,
                    "peak_tflops_measured": fp64_peak,
@@ -708,9 +728,7 @@ def run_ours(args, rank, world, local_rank):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak,
                      "unit": "GB/s", "frac": achieved / hbm_peak,
                      "traffic": traffic, "peak_source": peak_src,
-                     "kernel": ("contract_tc2_kernel" if (workload == "linear" and
-                                                        args.contract == "tc")
-                                else dominant),
+                     "kernel": dominant,
                      "kernel_ms_per_launch": kernel_ms,
                      "kernel_share_of_step": kms / ms,
                      "step_breakdown_ms": {k: v / args.steps
@@ -734,7 +752,7 @@ def run_ours(args, rank, world, local_rank):
         "gpu_launches": int(all_launches),
         "clocks": clocks,
     }
-    if workload != "linear":
+    if workload != "linear" and not on_tc:
         # the iterative models are bound by the FP64 tensor pipe, the FP64
         # contraction of interaction designs by the FP64 FMA pipe, not by HBM:
         # report that roofline, keep the HBM figures beside it

@@ -43,6 +43,7 @@ struct gt_engine {
     bool use_thread_solve = true;  // thread-per-SNP solve for narrow designs without interaction
     int tc_dbg = 0;
     int tc_N = 0;              // 0: the design does not run on the tcgen05 kernel
+    int tc_hom = 0;            // interaction design: MMA tiles of 64 markers x (dosage, homozygote) rows
     gtk::Tc2Params tc{};       // constant part of the kernel parameters
     DevBuf dS, dCounts, dGsum, dMlist, dMcount, dCorr; // per-batch workspace
     DevBuf dGeno, dOut, dIout;                 // staging of the *_host entry points
@@ -68,7 +69,7 @@ struct gt_engine {
     size_t events_used = 0;
     double ms_total = 0.0;
     int64_t launches = 0, all_launches = 0;
-    std::string dominant;
+    std::string dominant, dominant_tc;
 };
 
 // ---------------------------------------------------------------------------
@@ -232,6 +233,7 @@ file_maf_packed_kernel(const uint8_t *__restrict__ geno, long long pitch, int n_
 }
 
 // ---------------------------------------------------------------------------
+static int tc_tiles(const gt_engine *e);
 extern "C" {
 
 int gt_engine_set_file_maf_output(gt_engine *e, double *maf_host) {
@@ -503,7 +505,11 @@ int gt_engine_kernel_time(gt_engine *e, double *ms_total, int64_t *launches, int
     return 0;
 }
 
-const char *gt_engine_dominant_kernel(const gt_engine *e) { return e ? e->dominant.c_str() : ""; }
+const char *gt_engine_dominant_kernel(const gt_engine *e) {
+    if (!e) return "";
+    if (e->have_design && e->model == GT_MODEL_LINEAR && e->use_tc && e->tc_N > 0) return e->dominant_tc.c_str();
+    return e->dominant.c_str();
+}
 
 int gt_engine_kernel_breakdown(gt_engine *e, double *ms4) {
     if (!e || !ms4) return fail(GT_E_ARG, "gt_engine_kernel_breakdown: NULL argument");
@@ -634,9 +640,9 @@ int gt_engine_set_design(gt_engine *e, const gt_design_desc *d) {
                 }
         }
         if ((rc = upload(e->dE, E.data(), E.size() * 8, st))) return rc;
-        // ---- digit planes for the tcgen05 int8 contraction (lean designs) ----
-        e->tc_N = 0;
-        if (lean) {
+        // ---- digit planes for the tcgen05 int8 contraction ----
+        e->tc_N = 0; e->tc_hom = lean ? 0 : 1; e->cs_nv = 0;
+        {
             const int ncol = NC1;
             std::vector<char> is_design(n_pad, 0);
             for (int i = 0; i < n; ++i) is_design[pos[i]] = 1;
@@ -645,7 +651,7 @@ int gt_engine_set_design(gt_engine *e, const gt_design_desc *d) {
             // If the constant vector is a combination of the E columns (a design with
             // an intercept: 1 = Q a), the column with the largest |a_j| needs no digit
             // planes: the kernel derives its sum from sum(g) and the other columns.
-            T.ncolL = 0; T.drv_col = -1; T.drv_inv = 0.0;
+            T.ncolL = 0; T.drv_col = -1; T.drv_inv = 0.0; T.ones_out = -1; T.n_s2 = 0;
             std::vector<long double> acoef(ncol, 0.0L);
             if (H.has_const && !H.degenerate && k > 0) {
                 for (int c = 0; c < k; ++c) {
@@ -663,22 +669,55 @@ int gt_engine_set_design(gt_engine *e, const gt_design_desc *d) {
                 for (int c = 1; c < k; ++c) if (fabsl(acoef[c]) > fabsl(acoef[j])) j = c;
                 if (worst <= 1e-12L && fabsl(acoef[j]) > 0.5L) { T.drv_col = j; T.drv_inv = (double)(1.0L / acoef[j]); }
             }
+            // Interaction designs: E holds the products m_c v_b (m_0 = 1, m_c = w_c).  The column
+            // of ones needs no digits (it is the ones plane), and equal columns (w_a = w_a * 1,
+            // w_a w_b twice) share theirs.
+            auto same_col = [&](int c1, int c2) {
+                for (int i = 0; i < n; ++i)
+                    if (E[(size_t)pos[i] * NCP + c1] != E[(size_t)pos[i] * NCP + c2]) return false;
+                return true;
+            };
+            std::vector<int> colmap(ncol, -3);           // digit column of E column c; -1 ones plane, -2 derived
             std::vector<int> dig_src;                    // E column of digit column cl
-            for (int c = 0; c < ncol; ++c) {
-                if (c == T.drv_col) continue;
-                if (T.ncolL >= gtk::kT2MaxCols) { T.ncolL = gtk::kT2MaxCols + 1; break; }   // too wide
+            bool too_wide = false;
+            for (int c = 0; c < ncol && !too_wide; ++c) {
+                if (c == T.drv_col) { colmap[c] = -2; continue; }
+                if (!lean) {
+                    bool ones = true;
+                    for (int i = 0; i < n && ones; ++i) ones = E[(size_t)pos[i] * NCP + c] == 1.0;
+                    if (ones && T.ones_out < 0) { T.ones_out = c; colmap[c] = -1; continue; }
+                    int twin = -1;
+                    for (int cl = 0; cl < T.ncolL && twin < 0; ++cl)
+                        if (T.out_col2[cl] < 0 && same_col(dig_src[cl], c)) twin = cl;
+                    if (twin >= 0) { T.out_col2[twin] = c; colmap[c] = twin; continue; }
+                }
+                if (T.ncolL >= gtk::kT2MaxCols) { too_wide = true; break; }
                 double mx = 0.0;
                 for (int i = 0; i < n; ++i) mx = std::max(mx, std::fabs(E[(size_t)pos[i] * NCP + c]));
                 T.out_col[T.ncolL] = c;
+                T.out_col2[T.ncolL] = -1;
                 T.scale[T.ncolL] = mx > 0.0 ? mx : 1.0;
-                T.drv_a[T.ncolL] = (double)acoef[c];
+                T.drv_a[T.ncolL] = c < k ? (double)acoef[c] : 0.0;
+                colmap[c] = T.ncolL;
                 dig_src.push_back(c);
                 ++T.ncolL;
+            }
+            if (!lean && !too_wide) {
+                // g^2 block: m_a m_b is the E column of block a, entry w_b (block 0: the base vector)
+                T.n_s2 = NC2; T.s2_out = NCA;
+                int idx = 0;
+                for (int a = 0; a <= I && !too_wide; ++a)
+                    for (int b = a; b <= I; ++b, ++idx) {
+                        const int c = a * L + (b == 0 ? k + 1 : k + 1 + b);
+                        if (colmap[c] < -1 || idx >= 12) { too_wide = true; break; }
+                        T.s2_cl[idx] = colmap[c];
+                    }
+                T.pad0[0] = NC1; T.pad1[0] = NCA; T.pad0[1] = NCA + NC2; T.pad1[1] = NCP;
             }
             // seven digit planes per column + one plane of ones over the design
             // rows (its D column is the exact sum of the dosages)
             const int N = (gtk::kT2Digits * T.ncolL + 1 + 15) / 16 * 16;
-            if (T.ncolL <= gtk::kT2MaxCols && N <= 256 && (long long)n_file <= (1ll << 22)) {
+            if (!too_wide && N <= 256 && (long long)n_file <= (1ll << 22)) {
                 const int n_gst = (int)(pitch / 128);
                 const int n_slots = 4 * n_gst;
                 static const int perm16[16] = {0, 2, 4, 6, 8, 10, 12, 14, 1, 3, 5, 7, 9, 11, 13, 15};
@@ -722,29 +761,33 @@ int gt_engine_set_design(gt_engine *e, const gt_design_desc *d) {
                 T.ncol = ncol; T.NCP = NCP; T.rcap = 16 * n_gst;
                 T.error_flag = (int *)e->dErr.p;
                 e->tc_N = N;
-                // ---- compact rows (the digit columns only) for the streaming corrections ----
-                e->cs_nv = 0;
-                if (T.ncolL <= gtk::kCsRow) {
+                // ---- compact rows for the streaming corrections: the base-vector columns
+                //      that carry digits (block 0 of E, without the ones) ----
+                std::vector<int> cs_cl;
+                for (int cl = 0; cl < T.ncolL; ++cl) if (dig_src[cl] < L) cs_cl.push_back(cl);
+                // (every entry of v must be streamed, derived or the constant)
+                if ((int)cs_cl.size() <= gtk::kCsRow && (int)cs_cl.size() + (T.drv_col >= 0 ? 1 : 0) + 1 == L) {
                     const int nblk = (n_file + gtk::kCsBlk - 1) / gtk::kCsBlk;
                     std::vector<double> Ec((size_t)nblk * gtk::kCsBlk * gtk::kCsRow, 0.0);
                     gtk::CorrStreamParams &C = e->cs;
                     C = gtk::CorrStreamParams{};
-                    for (int cl = 0; cl < T.ncolL; ++cl) {
-                        C.vcol[cl] = dig_src[cl];
-                        C.drv_a[cl] = T.drv_a[cl];
+                    for (int cc = 0; cc < (int)cs_cl.size(); ++cc) {
+                        const int cl = cs_cl[cc];
+                        C.vcol[cc] = dig_src[cl];
+                        C.drv_a[cc] = T.drv_a[cl];
                         // 16-byte chunks (column pairs) of row i are stored at chunk ^ ((i >> 2) & 1)
                         for (int i = 0; i < n; ++i) {
                             const int ps = pos[i];
-                            const int slot = (((cl >> 1) ^ ((ps >> 2) & 1)) << 1) | (cl & 1);
+                            const int slot = (((cc >> 1) ^ ((ps >> 2) & 1)) << 1) | (cc & 1);
                             Ec[(size_t)ps * gtk::kCsRow + slot] = E[(size_t)ps * NCP + dig_src[cl]];
                         }
                     }
                     C.drv_col = T.drv_col; C.drv_inv = T.drv_inv;
-                    C.n_blocks = nblk; C.L = L; C.rcap = T.rcap;
+                    C.n_blocks = nblk; C.L = L; C.one = k + 1; C.rcap = T.rcap;
                     if ((rc = upload(e->dEi, Ec.data(), Ec.size() * 8, st))) return rc;
                     C.Ec = (const double *)e->dEi.p;
                     C.error_flag = (int *)e->dErr.p;
-                    e->cs_nv = T.ncolL;
+                    e->cs_nv = (int)cs_cl.size();
                 }
                 CK(cudaStreamSynchronize(st));           // Bimg / Ei go out of scope
             }
@@ -773,6 +816,11 @@ int gt_engine_set_design(gt_engine *e, const gt_design_desc *d) {
         D.Rinv = (const double *)e->dRinv.p; D.tq = (const double *)e->dTq.p;
         D.maf_o = nullptr; D.flip_o = nullptr;
         e->dominant = "contract_packed_kernel";
+        if (e->tc_N > 0) {
+            char nm[96];
+            snprintf(nm, sizeof nm, "contract_tc2_kernel<NT=%d,TILES=%d,HOM=%d>", e->tc_N / 16, tc_tiles(e), e->tc_hom);
+            e->dominant_tc = nm;
+        }
         CK(cudaStreamSynchronize(st));   // host vectors go out of scope
     } else if (d->model == GT_MODEL_LOGISTIC || d->model == GT_MODEL_COXPH) {
         rc = gtk::iter_set_design(d, pos, n_file, n_chunks, pitch, (const uint8_t *)e->dMask.p,
@@ -827,8 +875,11 @@ static tmap_encode_fn tmap_encoder() {
 }
 
 // SNP rows per CTA of the tcgen05 contraction for this design
-static int tc_tiles(const gt_engine *e) { return e->tc_N <= 96 ? 4 : (e->tc_N <= 128 ? 2 : 1); }
-static int tc_rows(const gt_engine *e) { return 128 * tc_tiles(e); }
+static int tc_tiles(const gt_engine *e) {
+    if (e->tc_hom) return e->tc_N <= 224 ? 2 : 1;
+    return e->tc_N <= 96 ? 4 : (e->tc_N <= 128 ? 2 : 1);
+}
+static int tc_rows(const gt_engine *e) { return (e->tc_hom ? 64 : 128) * tc_tiles(e); }
 
 static int launch_contract_tc(gt_engine *e, const uint8_t *g, int64_t pitch, int nb) {
     gtk::Tc2Params P = e->tc;
@@ -867,6 +918,25 @@ static int launch_contract_tc(gt_engine *e, const uint8_t *g, int64_t pitch, int
         CK(cudaGetLastError());                                                                   \
         return 0;                                                                                 \
     }
+#define GT_TCH(T, TL)                                                                             \
+    case T: {                                                                                     \
+        const int smem = gtk::Tc2Cfg<TL, 1>::smem_bytes(16 * T);                                  \
+        CK(cudaFuncSetAttribute((const void *)gtk::contract_tc2_kernel<T, TL, 0, 1>,              \
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, smem));              \
+        gtk::contract_tc2_kernel<T, TL, 0, 1><<<grid, gtk::Tc2Cfg<TL, 1>::kThreads, smem, e->stream>>>(gmap, P); \
+    } break;
+    if (e->tc_hom) {
+        // interaction designs: 64 markers x (dosage, homozygote indicator) per MMA tile
+        switch (NT) {
+            GT_TCH(2, 2) GT_TCH(3, 2) GT_TCH(4, 2) GT_TCH(5, 2) GT_TCH(6, 2) GT_TCH(7, 2) GT_TCH(8, 2)
+            GT_TCH(9, 2) GT_TCH(10, 2) GT_TCH(11, 2) GT_TCH(12, 2) GT_TCH(13, 2) GT_TCH(14, 2)
+            GT_TCH(15, 1) GT_TCH(16, 1)
+            default: return fail(GT_E_UNSUPPORTED, "tcgen05 contraction (interaction design): N=%d not instantiated", e->tc_N);
+        }
+        CK(cudaGetLastError());
+        return 0;
+    }
+#undef GT_TCH
     // tuning probes (option "tc_debug") of the 5 x 16 column instantiation only
     GT_TCD(5, 4, 1) GT_TCD(5, 4, 2) GT_TCD(5, 4, 6) GT_TCD(5, 4, 14) GT_TCD(5, 4, 61) GT_TCD(5, 4, 63) GT_TCD(5, 4, 128)
 #undef GT_TCD

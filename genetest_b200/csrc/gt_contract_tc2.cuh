@@ -55,6 +55,14 @@ struct Tc2Params {
     const uint8_t *Bimg;      // [4 * n_gstages][N * 128] pre-swizzled digit planes
     int ncolL;                // digit columns (7 planes each), then the ones plane
     int out_col[kT2MaxCols];  // S column of digit column cl
+    int out_col2[kT2MaxCols]; // second S column holding the same values (interaction designs), or -1
+    int ones_out;             // S column that is the plain dosage sum (E column identically one), or -1
+    // interaction designs (HOM kernels): the sums of g^2 m over the columns m = 1, w_a, w_a w_b are
+    // sum(g m) + 2 sum(h m) with h the homozygote indicator (rows 64..127 of every MMA tile)
+    int n_s2;                 // columns of the g^2 block (0: none)
+    int s2_cl[12];            // digit column of g^2 column idx (-1: the ones plane)
+    int s2_out;               // S column of g^2 column 0 (the others follow)
+    int pad0[4], pad1[4];     // S column ranges [pad0[i], pad1[i]) to clear
     double scale[kT2MaxCols]; // column maximum * 2^-54
     // When the constant vector lies in the span of the digit columns plus one more
     // column j (1 = sum_c a_c E_c over the design rows), column j needs no digits:
@@ -137,12 +145,14 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     return r;
 }
 
-template <int TILES> struct Tc2Cfg {
+// HOM = 1: every 128-row MMA tile holds 64 markers twice -- rows 0..63 their dosages,
+// rows 64..127 their homozygote indicators (same packed bytes, another lookup table)
+template <int TILES, int HOM = 0> struct Tc2Cfg {
     static constexpr int kExpWarps = 4 * TILES;
     static constexpr int kThreads = (kExpWarps + 3) * 32;
-    static constexpr int kRows = 128 * TILES;
+    static constexpr int kRows = (HOM ? 64 : 128) * TILES;  // markers (packed rows) of a CTA
     static constexpr int kGStage = kRows * 128;          // bytes of one genotype stage (512 samples)
-    static constexpr int kGStages = TILES >= 4 ? 2 : (TILES == 2 ? 3 : 4);
+    static constexpr int kGStages = kRows >= 512 ? 2 : (kRows == 256 ? 3 : 4);
     static constexpr int kBoxRows = kRows < 256 ? kRows : 256;   // rows of one TMA box
     __host__ __device__ static constexpr int a_slots(int N) {   // 64-sample A slots in TMEM
         return ((512 - TILES * N) / (TILES * 16)) < 8 ? ((512 - TILES * N) / (TILES * 16)) : 8;
@@ -155,16 +165,17 @@ template <int TILES> struct Tc2Cfg {
     // staging ring of the missing-pair records: 8 records of 8 B per expansion thread
     static constexpr int kRecRing = kRows * 64;
     __host__ __device__ static constexpr int smem_bytes(int N) {
-        return 1024 + kGStages * kGStage + b_stages(N) * N * 128 + 512 + kRecRing;
+        return 1024 + kGStages * kGStage + b_stages(N) * N * 128 + 512 + kRecRing + (HOM ? kRows * 13 * 8 : 0);
     }
 };
 
 template <int NT /* N / 16 */, int TILES,
           int DBG = 0 /* tuning: 1 no records, 2 no MMA, 4 no TMEM store, 8 genotypes from L2, 16 no counts,
-                         32 no B copies, 128 print the roles' wait cycles */>
-__global__ void __launch_bounds__(Tc2Cfg<TILES>::kThreads, 1)
+                         32 no B copies, 128 print the roles' wait cycles */,
+          int HOM = 0>
+__global__ void __launch_bounds__(Tc2Cfg<TILES, HOM>::kThreads, 1)
 contract_tc2_kernel(const __grid_constant__ CUtensorMap gmap, const Tc2Params P) {
-    using Cfg = Tc2Cfg<TILES>;
+    using Cfg = Tc2Cfg<TILES, HOM>;
     constexpr int N = 16 * NT;
     constexpr int BSTAGE = N * 128;
     constexpr int BST = Cfg::b_stages(N);
@@ -187,6 +198,7 @@ contract_tc2_kernel(const __grid_constant__ CUtensorMap gmap, const Tc2Params P)
     int *fail = (int *)(tmem_slot + 1);
     uint32_t *lut_s = tmem_slot + 2;
     unsigned char *sRec = (unsigned char *)(bars + 64);         // [8][kRows] records (uint2)
+    double *sHom = (double *)(sRec + Cfg::kRecRing);            // HOM: [13][kRows] sums of h m
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // probe (DBG & 128): cycles the roles of CTA 0 spend in their waits
@@ -199,7 +211,8 @@ contract_tc2_kernel(const __grid_constant__ CUtensorMap gmap, const Tc2Params P)
         for (int s = 0; s < S; ++s) { mbar_init(&a_full[s], EW); mbar_init(&a_empty[s], 1); }
         mbar_init(d_full, 1);
         *fail = 0;
-        *lut_s = 0x00010002u;
+        lut_s[0] = 0x00010002u;
+        lut_s[1] = 0x00000001u;
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (warp == 0) {
@@ -220,7 +233,11 @@ contract_tc2_kernel(const __grid_constant__ CUtensorMap gmap, const Tc2Params P)
         // ===== expansion: one thread per SNP row, 64 samples per slot =====
         const int tile = warp >> 2;
         const int lgrp = warp & 3;                       // TMEM lanes 32 * lgrp .. of this warp
-        const int row = tile * 128 + lgrp * 32 + lane;   // row of the CTA
+        // HOM: warps 0, 1 of a tile expand the dosages of its 64 markers, warps 2, 3 their
+        // homozygote indicators (the class counts and the records are the dosage threads' job)
+        const bool is_h = HOM && lgrp >= 2;
+        const int row = HOM ? tile * 64 + (lgrp & 1) * 32 + lane
+                            : tile * 128 + lgrp * 32 + lane;   // marker (packed row) of the CTA
         const int snp = row0 + row;
         const bool owner = snp < P.n_snps;
         const uint32_t lane_base = ((uint32_t)(lgrp * 32)) << 16;
@@ -239,7 +256,7 @@ contract_tc2_kernel(const __grid_constant__ CUtensorMap gmap, const Tc2Params P)
         // code -> dosage byte: 00 -> 2, 01 -> 0, 10 -> 1, 11 -> 0.  Opaque to the
         // compiler (read back from shared memory) so that it stays in one vector
         // register: a known constant lands in a uniform register and is copied per PRMT.
-        const uint32_t lut = *(volatile uint32_t *)lut_s;
+        const uint32_t lut = ((volatile uint32_t *)lut_s)[is_h ? 1 : 0];
 
         auto publish = [&](int it) {     // slot `it` is in tensor memory: tell the MMA thread
             GT_PROF(2, asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"));
@@ -279,9 +296,10 @@ contract_tc2_kernel(const __grid_constant__ CUtensorMap gmap, const Tc2Params P)
                 a[j * 4 + 2] = prmt(lut, 0u, odd);
                 a[j * 4 + 3] = prmt(lut, 0u, hi16(odd));
             }
+            if (!is_h) {
 #pragma unroll
             for (int pr = 0; pr < 2; ++pr) {
-                if (!(DBG & 16)) nhom += __popc(homf[2 * pr] | homf[2 * pr + 1]);
+                if (!(DBG & 16) && !HOM) nhom += __popc(homf[2 * pr] | homf[2 * pr + 1]);
                 const uint32_t mis2 = misf[2 * pr] | misf[2 * pr + 1];
                 if (!(DBG & 1)) {
                     // predicated, not branched: (pair index, flags) when any flag is set
@@ -294,6 +312,7 @@ contract_tc2_kernel(const __grid_constant__ CUtensorMap gmap, const Tc2Params P)
                           "r"((uint32_t)(it * 2 + pr)), "r"(mis2)
                         : "memory");
                 }
+            }
             }
             // publish the PREVIOUS slot only now: its TMEM store drained while
             // this slot's bytes were being expanded
@@ -313,7 +332,7 @@ contract_tc2_kernel(const __grid_constant__ CUtensorMap gmap, const Tc2Params P)
 
         // every two slots (at most four new records): one whole sector leaves when four are staged
         auto flush4 = [&]() {
-            if ((DBG & 1) || wcnt - flushed < 4u) return;
+            if ((DBG & 1) || is_h || wcnt - flushed < 4u) return;
             const uint32_t src = rec_s + ((flushed & 4u) * (uint32_t)(Cfg::kRows * 8));
             uint2 r0, r1, r2, r3;
             asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];\n" : "=r"(r0.x), "=r"(r0.y) : "r"(src));
@@ -361,7 +380,7 @@ contract_tc2_kernel(const __grid_constant__ CUtensorMap gmap, const Tc2Params P)
             printf("expansion warp %d: total %lld  g_full %lld  a_empty %lld  wait_st %lld\n", warp,
                    clock64() - prof_t0, prof[0], prof[1], prof[2]);
         const int nrec = (int)wcnt;
-        if (!(DBG & 1)) {
+        if (!(DBG & 1) && !is_h) {
             // at most three staged records are left
             for (; flushed < wcnt; ++flushed) {
                 uint2 r;
@@ -370,9 +389,13 @@ contract_tc2_kernel(const __grid_constant__ CUtensorMap gmap, const Tc2Params P)
                 *(uint2 *)(mbase + (size_t)flushed * 8) = r;
             }
         }
-        if (owner) {
+        if (owner && !is_h) {
             P.mcount[snp] = nrec;
-            for (int col = P.ncol; col < P.NCP; ++col) P.S[(long long)snp * P.NCP + col] = 0.0;
+            if (!HOM)
+                for (int col = P.ncol; col < P.NCP; ++col) P.S[(long long)snp * P.NCP + col] = 0.0;
+            else
+                for (int r = 0; r < 4; ++r)
+                    for (int col = P.pad0[r]; col < P.pad1[r]; ++col) P.S[(long long)snp * P.NCP + col] = 0.0;
         }
         // ===== epilogue: D (int32, TMEM) -> FP64 sums =====
         if (!mbar_wait2(d_full, 0, fail)) *fail = 1;
@@ -406,6 +429,45 @@ contract_tc2_kernel(const __grid_constant__ CUtensorMap gmap, const Tc2Params P)
                 }
             }
         }
+        if constexpr (HOM != 0) {
+            // value of digit column `c` (or of the ones plane for c < 0) in this thread's D row
+            auto pick = [&](int c) {
+                double r = (double)sum_g;
+#pragma unroll
+                for (int cl = 0; cl < NCL; ++cl) r = (c == cl) ? acc[cl] * P.scale[cl] : r;
+                return r;
+            };
+            // the indicator rows hand sum(h), sum(h m) to the dosage thread of the same marker
+            if (is_h) {
+                sHom[row] = (double)sum_g;
+                for (int idx = 0; idx < P.n_s2; ++idx) sHom[(1 + idx) * Cfg::kRows + row] = pick(P.s2_cl[idx]);
+            }
+            asm volatile("bar.sync 1, %0;\n" ::"n"(EW * 32) : "memory");
+            if (!is_h && owner) {
+                double *Srow = P.S + (long long)snp * P.NCP;
+                double part = 0.0;
+#pragma unroll
+                for (int cl = 0; cl < NCL; ++cl)
+                    if (cl < P.ncolL) {
+                        const double sv = acc[cl] * P.scale[cl];
+                        Srow[P.out_col[cl]] = sv;
+                        if (P.out_col2[cl] >= 0) Srow[P.out_col2[cl]] = sv;
+                        part = fma(P.drv_a[cl], sv, part);
+                    }
+                if (P.drv_col >= 0) Srow[P.drv_col] = ((double)sum_g - part) * P.drv_inv;
+                if (P.ones_out >= 0) Srow[P.ones_out] = (double)sum_g;
+                // sum g^2 m = sum g m + 2 sum h m   (g in {0, 1, 2}: g^2 = g + 2 [g == 2])
+                for (int idx = 0; idx < P.n_s2; ++idx)
+                    Srow[P.s2_out + idx] = fma(2.0, sHom[(1 + idx) * Cfg::kRows + row], pick(P.s2_cl[idx]));
+                const int nh = (int)sHom[row];
+                P.counts[(long long)snp * 4 + 0] = sum_g - 2 * nh;
+                P.counts[(long long)snp * 4 + 1] = nh;
+                P.counts[(long long)snp * 4 + 2] = nrec > 0 ? -1 : 0;
+                P.counts[(long long)snp * 4 + 3] = 0;
+                P.gsum[(long long)snp * 2 + 0] = (double)sum_g;
+                P.gsum[(long long)snp * 2 + 1] = (double)(sum_g + 2 * nh);
+            }
+        } else
         if (owner) {
             double part = 0.0;
 #pragma unroll

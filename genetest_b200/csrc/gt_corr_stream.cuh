@@ -46,7 +46,8 @@ struct CorrStreamParams {
     const uint2 *mrec;        // [n_snps][rcap]
     int rcap;
     const int *mcount;        // [n_snps]
-    int L;                    // base vector length k + 2 + I (here I = 0): [q | y | 1]
+    int L;                    // base vector length k + 2 + I: [q | y | 1 | w]
+    int one;                  // position of the constant in v (k + 1)
     int vcol[12];             // position in v of streamed column c
     int drv_col;              // position in v of the column derived from the constant, or -1
     double drv_a[12];         // 1 = sum_c drv_a[c] v[vcol[c]] + a_j v[drv_col]
@@ -222,7 +223,7 @@ missing_corr_stream_kernel(const CorrStreamParams P) {
             double *out = P.corrT + snp;
             const long long ld = P.ldc;
             const double dn = (double)n_miss;
-            const int one = L - 1;
+            const int one = P.one;
             const double *sm = sum;
             // streamed x streamed, streamed x ones
             int e = 0;
@@ -233,7 +234,7 @@ missing_corr_stream_kernel(const CorrStreamParams P) {
                     const int ia = P.vcol[a], ic = P.vcol[c];
                     out[(long long)cs_tri(min(ia, ic), max(ia, ic), L) * ld] = acc[e];
                 }
-                out[(long long)cs_tri(P.vcol[a], one, L) * ld] = sm[a];
+                out[(long long)cs_tri(min(P.vcol[a], one), max(P.vcol[a], one), L) * ld] = sm[a];
             }
             out[(long long)cs_tri(one, one, L) * ld] = dn;
             if (P.drv_col >= 0) {
@@ -253,7 +254,7 @@ missing_corr_stream_kernel(const CorrStreamParams P) {
                     const int ia = P.vcol[a];
                     out[(long long)cs_tri(min(ia, j), max(ia, j), L) * ld] = (sm[a] - t) * P.drv_inv;
                 }
-                out[(long long)cs_tri(j, one, L) * ld] = (dn - s1) * P.drv_inv;
+                out[(long long)cs_tri(min(j, one), max(j, one), L) * ld] = (dn - s1) * P.drv_inv;
                 out[(long long)cs_tri(j, j, L) * ld] = (dn - 2.0 * s1 + s2) * P.drv_inv * P.drv_inv;
             }
             P.counts[(long long)snp * 4 + 2] = n_miss;
