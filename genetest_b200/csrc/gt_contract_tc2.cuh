@@ -138,6 +138,11 @@ __device__ __forceinline__ uint32_t hi16(uint32_t x) {
     asm("mul.hi.u32 %0, %1, 65536;\n" : "=r"(r) : "r"(x));
     return r;
 }
+template <int K> __device__ __forceinline__ uint32_t shr_fma(uint32_t x) {
+    uint32_t r;
+    asm("mul.hi.u32 %0, %1, %2;\n" : "=r"(r) : "r"(x), "n"(1u << (32 - K)));
+    return r;
+}
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     uint4 r;
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n"
@@ -180,7 +185,7 @@ contract_tc2_kernel(const __grid_constant__ CUtensorMap gmap, const Tc2Params P)
     constexpr int BSTAGE = N * 128;
     constexpr int BST = Cfg::b_stages(N);
     constexpr int G = Cfg::kGStages;
-    constexpr int S = Cfg::a_slots(N);
+    constexpr int S = (DBG & 256) ? 2 : Cfg::a_slots(N);
     constexpr int EW = Cfg::kExpWarps;
     constexpr int TMEM_NEED = TILES * N + S * TILES * 16;
     constexpr int TMEM_COLS = TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512);
@@ -262,7 +267,12 @@ contract_tc2_kernel(const __grid_constant__ CUtensorMap gmap, const Tc2Params P)
             GT_PROF(2, asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"));
             asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(&a_full[it % S]);
+            // lane 0 arrives -- predicated, not branched
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "setp.eq.u32 p, %1, 0;\n\t"
+                "@p mbarrier.arrive.shared::cta.b64 _, [%0];\n\t}\n"
+                ::"r"(smem_u32(&a_full[it % S])), "r"(lane) : "memory");
         };
         // one 64-sample slot: this thread's 16 bytes -> 16 registers of dosages
         auto do_slot = [&](const uint4 pw, const uint4 m4, const int it) {
@@ -282,7 +292,7 @@ contract_tc2_kernel(const __grid_constant__ CUtensorMap gmap, const Tc2Params P)
                 // flags of an even word sit on the even bits, those of an odd word on the odd
                 // bits, so that two words share one flag word without any realignment
                 if (!(j & 1)) {
-                    const uint32_t s1 = wm >> 1;
+                    const uint32_t s1 = (DBG & 512) ? shr_fma<1>(wm) : wm >> 1;
                     homf[j] = ~(wm | s1) & 0x55555555u;          // code 00
                     misf[j] = wm & ~s1 & 0x55555555u;            // code 01
                 } else {
@@ -290,7 +300,7 @@ contract_tc2_kernel(const __grid_constant__ CUtensorMap gmap, const Tc2Params P)
                     homf[j] = ~(wm | s1) & 0xaaaaaaaau;
                     misf[j] = s1 & ~wm & 0xaaaaaaaau;
                 }
-                const uint32_t even = w & 0x33333333u, odd = (w >> 2) & 0x33333333u;
+                const uint32_t even = w & 0x33333333u, odd = ((DBG & 512) ? shr_fma<2>(w) : (w >> 2)) & 0x33333333u;
                 a[j * 4 + 0] = prmt(lut, 0u, even);
                 a[j * 4 + 1] = prmt(lut, 0u, hi16(even));
                 a[j * 4 + 2] = prmt(lut, 0u, odd);
@@ -317,7 +327,7 @@ contract_tc2_kernel(const __grid_constant__ CUtensorMap gmap, const Tc2Params P)
             // publish the PREVIOUS slot only now: its TMEM store drained while
             // this slot's bytes were being expanded
             if (it > 0) publish(it - 1);
-            GT_PROF(1, if (!freed) { if (lane == 0 && !mbar_wait_slow(a_emp, a_par, fail)) *fail = 1; __syncwarp(); });
+            GT_PROF(1, if (!freed) { if (!mbar_wait_slow(a_emp, a_par, fail)) *fail = 1; });
             asm volatile("tcgen05.fence::after_thread_sync;\n");
             const uint32_t taddr = tmem_a + lane_base + (s * TILES + tile) * 16;
             if (!(DBG & 4))
