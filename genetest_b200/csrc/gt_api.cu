@@ -21,6 +21,7 @@
 #include "gt_solve.cuh"
 #include "gt_solve_thread.cuh"
 #include "gt_logistic.cuh"
+#include "gt_logistic_thread.cuh"
 #include "gt_cox.cuh"
 #include "gt_format.cuh"
 #include "gt_sexmaf.cuh"
@@ -41,6 +42,9 @@ struct gt_engine {
     bool use_stream_corr = true;   // ... and their corrections on the streaming kernel
     int cox_maxiter = 100;     // Newton step limit of the Cox model (statsmodels' default)
     bool use_thread_solve = true;  // thread-per-SNP solve for narrow designs without interaction
+    bool use_thread_iter = true;   // thread-per-SNP IRLS for binary outcomes without interaction
+    int thread_iter_min = 4096;    // ... for batches of at least this many markers (fewer: warp per SNP)
+    DevBuf dIterScratch;
     int tc_dbg = 0;
     int tc_N = 0;              // 0: the design does not run on the tcgen05 kernel
     int tc_hom = 0;            // interaction design: MMA tiles of 64 markers x (dosage, homozygote) rows
@@ -371,6 +375,8 @@ int64_t gt_format_rows(int32_t n_rows, int32_t n_cols, const int32_t *col_type,
 double gt_host_t_sf2(double t, double df) { return gt_t_sf2(t, df); }
 double gt_host_t_ppf975(double df) { return gt_t_ppf975(df); }
 double gt_host_norm_sf2(double z) { return gt_norm_sf2(z); }
+double gt_host_lt_exp_neg(double a) { return gtk::lt_exp_neg(a); }
+double gt_host_lt_log1p01(double t) { double inv; return gtk::lt_log1p01(t, inv); }
 const char *gt_last_error(void) { return g_err.c_str(); }
 
 int64_t gt_packed_pitch(int32_t n_file) {
@@ -404,7 +410,7 @@ int gt_engine_destroy(gt_engine *e) {
     for (auto &ev : e->events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     DevBuf *bufs[] = {&e->dE, &e->dMask, &e->dFF0, &e->dR, &e->dRinv, &e->dTq, &e->dIter, &e->dBimg, &e->dScale, &e->dErr, &e->dEi,
                       &e->dS, &e->dCounts, &e->dGsum, &e->dMlist, &e->dMcount, &e->dCorr, &e->dGeno, &e->dOut, &e->dIout,
-                      &e->dSexM, &e->dSexF, &e->dSexRow, &e->dMafO, &e->dFlipO, &e->dCounter, &e->dFileMaf};
+                      &e->dSexM, &e->dSexF, &e->dSexRow, &e->dMafO, &e->dFlipO, &e->dCounter, &e->dFileMaf, &e->dIterScratch};
     for (DevBuf *b : bufs) b->release();
     for (int i = 0; i < 2; ++i) {
         if (e->pin[i]) cudaFreeHost(e->pin[i]);
@@ -458,6 +464,8 @@ int gt_engine_set_option(gt_engine *e, const char *name, int value) {
     if (std::strcmp(name, "tc_debug") == 0) { e->tc_dbg = value; return 0; }
     if (std::strcmp(name, "stream_corrections") == 0) { e->use_stream_corr = value != 0; return 0; }
     if (std::strcmp(name, "thread_solve") == 0) { e->use_thread_solve = value != 0; return 0; }
+    if (std::strcmp(name, "thread_iter") == 0) { e->use_thread_iter = value != 0; return 0; }
+    if (std::strcmp(name, "thread_iter_min") == 0) { e->thread_iter_min = value > 0 ? value : 4096; return 0; }
     if (std::strcmp(name, "cox_maxiter") == 0) { e->cox_maxiter = value > 0 ? value : 100; return 0; }
     if (std::strcmp(name, "host_chunk") == 0) { e->host_chunk = (int)std::max<int64_t>(0, value); return 0; }
     return fail(GT_E_ARG, "gt_engine_set_option: unknown option '%s'", name);
@@ -508,6 +516,9 @@ int gt_engine_kernel_time(gt_engine *e, double *ms_total, int64_t *launches, int
 const char *gt_engine_dominant_kernel(const gt_engine *e) {
     if (!e) return "";
     if (e->have_design && e->model == GT_MODEL_LINEAR && e->use_tc && e->tc_N > 0) return e->dominant_tc.c_str();
+    if (e->have_design && e->model == GT_MODEL_LOGISTIC && e->use_thread_iter && e->T.I == 0 && e->T.p >= 2 &&
+        e->T.p <= 13 && e->T.y_binary && !e->T.degenerate)
+        return "logistic_thread_kernel";       // (calls of at least thread_iter_min .bed markers)
     return e->dominant.c_str();
 }
 
@@ -1150,9 +1161,13 @@ static int run_any(gt_engine *e, const void *geno, int64_t pitch, bool packed, i
     {
         int rc = e->dCounter.reserve(16);
         if (rc) return rc;
+        // coef / se of the last solve of every marker (thread-per-SNP logistic kernel)
+        if (e->model == GT_MODEL_LOGISTIC && packed && e->use_thread_iter &&
+            (rc = e->dIterScratch.reserve((size_t)(n_snps + 32) * 2 * 13 * 8))) return rc;
     }
     return gtk::iter_run(T, e->model, geno, pitch, packed, n_snps, out, iout, ldo, e->stream,
                          (int *)e->dCounter.p, e->timing,
+                         (double *)e->dIterScratch.p, e->use_thread_iter, e->thread_iter_min,
                          [&]() { return time_begin(e); }, [&](int s) { time_end(e, s); },
                          e->all_launches, g_err);
 }
@@ -1200,6 +1215,10 @@ static int run_host(gt_engine *e, const void *src, int64_t src_pitch_bytes, int6
         // the iterative models are compute-bound by orders of magnitude and
         // pay a partial last wave per chunk: keep their chunks large
         chunk = std::max<int64_t>(chunk, e->model == GT_MODEL_LINEAR ? 8192 : 65536);
+        // thread-per-SNP IRLS: whole waves of 148 CTAs x 224 markers
+        if (packed && e->model == GT_MODEL_LOGISTIC && e->use_thread_iter && e->T.I == 0 && e->T.p <= 13 &&
+            e->T.y_binary && chunk >= 148 * gtk::kLtMaxThreads)
+            chunk = chunk / (148 * gtk::kLtMaxThreads) * (148 * gtk::kLtMaxThreads);
         chunk = std::min<int64_t>(chunk, std::max<int64_t>(1024, ((int64_t)512 << 20) / dev_pitch_bytes / 1024 * 1024));
         // whole half-waves of the tcgen05 contraction (148 CTAs x 128 .. 512 SNP rows)
         if (packed && e->model == GT_MODEL_LINEAR && e->use_tc && e->tc_N > 0) {

@@ -9,6 +9,7 @@
 #include "gt_common.cuh"
 #include "gt_host.cuh"
 #include "gt_logistic.cuh"
+#include "gt_logistic_thread.cuh"
 #include "gt_coxk.cuh"
 
 namespace gtk {
@@ -150,6 +151,8 @@ static int iter_set_design(const gt_design_desc *d, const std::vector<int> &pos,
     T.n_file = n_file; T.n = n; T.k = k; T.I = I; T.p = p; T.XS = XSs; T.n_pad = (int)n_pad;
     T.raw_mode = d->raw_mode; T.use_maf_t = d->use_maf_t; T.maf_t = d->maf_t;
     T.degenerate = H.degenerate ? 1 : 0;
+    T.y_binary = 1;
+    for (int i = 0; i < n && T.y_binary; ++i) T.y_binary = d->y[i] == 0.0 || d->y[i] == 1.0;
     T.maf_o = nullptr; T.flip_o = nullptr;
     T.X = (const double *)buf.p; T.y = T.X + n_pad * XSs; T.Rinv = T.y + n_pad;
     if (d->model == GT_MODEL_COXPH) {
@@ -171,7 +174,8 @@ static int iter_set_design(const gt_design_desc *d, const std::vector<int> &pos,
 
 template <bool PACKED, int NT>
 static int launch_logistic(const IterDesignDev &T, const void *geno, int64_t pitch, int n_snps,
-                      double *out, int32_t *iout, long long ldo, cudaStream_t st, int *counter) {
+                      double *out, int32_t *iout, long long ldo, cudaStream_t st, int *counter,
+                      int only_deferred = 0) {
     using Cfg = LogitCfg<NT>;
     const int wpc = 8;
     size_t smem = (size_t)wpc * Cfg::perWarp * 8;   // NT = 2: 92 KB -> two CTAs per SM
@@ -181,7 +185,27 @@ static int launch_logistic(const IterDesignDev &T, const void *geno, int64_t pit
     // a work counter measured 3 % slower here)
     (void)counter;
     logistic_irls_kernel<PACKED, NT><<<(n_snps + wpc - 1) / wpc, wpc * 32, smem, st>>>(
-        T, geno, pitch, n_snps, out, iout, ldo);
+        T, geno, pitch, n_snps, out, iout, ldo, only_deferred);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// thread-per-SNP IRLS (gt_logistic_thread.cuh): whole waves of 148 CTAs where the batch allows
+template <int P>
+static int launch_logistic_thread(const IterDesignDev &T, const void *geno, int64_t pitch, int n_snps,
+                                  double *out, int32_t *iout, long long ldo, cudaStream_t st,
+                                  double *scratch, long long lds, int maxpass) {
+    // markers per CTA: the batch spread over the 148 SMs (whole warps), at most kLtMaxThreads
+    const int waves = (n_snps + 148 * kLtMaxThreads - 1) / (148 * kLtMaxThreads);
+    int nthr = ((n_snps + 148 * waves - 1) / (148 * waves) + 31) / 32 * 32;
+    nthr = std::max(32, std::min(nthr, kLtMaxThreads));
+    const int XSs = std::max(2, (P & ~1));                       // (K + 1) & ~1 with K = P - 1
+    const size_t smem = 128 + (size_t)kLtBuf * (kLtBlk * XSs * 8 + kLtBlk * 8) + 128 +
+                        (size_t)(((P - 1) * (P - 1) + 1) & ~1) * 8 + (size_t)P * nthr * 8;
+    CK(cudaFuncSetAttribute((const void *)logistic_thread_kernel<P>,
+                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    logistic_thread_kernel<P><<<(n_snps + nthr - 1) / nthr, nthr + 32, smem, st>>>(
+        T, (const uint8_t *)geno, pitch, n_snps, out, iout, ldo, scratch, lds, maxpass);
     CK(cudaGetLastError());
     return 0;
 }
@@ -207,6 +231,7 @@ static int launch_cox(const IterDesignDev &T, const void *geno, int64_t pitch, i
 
 static int iter_run(const IterDesignDev &T, int model, const void *geno, int64_t pitch, bool packed,
                     int32_t n_snps, double *out, int32_t *iout, long long ldo, cudaStream_t st, int *counter, bool timing,
+                    double *lt_scratch, bool use_thread, int thread_min,
                     const std::function<int()> &tbegin, const std::function<void(int)> &tend,
                     int64_t &all_launches, std::string &err) {
     (void)timing; (void)err;
@@ -224,9 +249,27 @@ static int iter_run(const IterDesignDev &T, int model, const void *geno, int64_t
                          : launch_cox<false, 3>(T, geno, pitch, n_snps, out, iout, ldo, st, counter);
         }
     } else if (packed) {
-        rc = NT == 1 ? launch_logistic<true, 1>(T, geno, pitch, n_snps, out, iout, ldo, st, counter)
-           : NT == 2 ? launch_logistic<true, 2>(T, geno, pitch, n_snps, out, iout, ldo, st, counter)
-                     : launch_logistic<true, 3>(T, geno, pitch, n_snps, out, iout, ldo, st, counter);
+        // .bed rows, binary outcome, no interaction, p <= 13, enough markers to fill the SMs:
+        // one thread per marker first, the warp kernel then only finishes what that one deferred
+        int deferred = 0;
+        rc = 0;
+        if (use_thread && lt_scratch && T.I == 0 && T.p >= 2 && T.p <= 13 && T.y_binary && !T.degenerate &&
+            n_snps >= thread_min) {
+            const long long lds = (n_snps + 31) / 32 * 32;
+            const int maxpass = 9;
+#define GT_LT(PP) case PP: rc = launch_logistic_thread<PP>(T, geno, pitch, n_snps, out, iout, ldo, st, lt_scratch, lds, maxpass); break;
+            switch (T.p) {
+                GT_LT(2) GT_LT(3) GT_LT(4) GT_LT(5) GT_LT(6) GT_LT(7) GT_LT(8) GT_LT(9) GT_LT(10)
+                GT_LT(11) GT_LT(12) GT_LT(13)
+            }
+#undef GT_LT
+            if (rc) return rc;
+            deferred = 1;
+            all_launches += 1;
+        }
+        rc = NT == 1 ? launch_logistic<true, 1>(T, geno, pitch, n_snps, out, iout, ldo, st, counter, deferred)
+           : NT == 2 ? launch_logistic<true, 2>(T, geno, pitch, n_snps, out, iout, ldo, st, counter, deferred)
+                     : launch_logistic<true, 3>(T, geno, pitch, n_snps, out, iout, ldo, st, counter, deferred);
     } else {
         rc = NT == 1 ? launch_logistic<false, 1>(T, geno, pitch, n_snps, out, iout, ldo, st, counter)
            : NT == 2 ? launch_logistic<false, 2>(T, geno, pitch, n_snps, out, iout, ldo, st, counter)

@@ -27,6 +27,7 @@ struct IterDesignDev {
     int n_pad;
     int raw_mode, use_maf_t;
     int degenerate;         // covariates alone are rank deficient
+    int y_binary;           // every outcome of the design is 0 or 1 (logistic: thread-per-SNP kernel)
     double maf_t;
     const double *X;        // [n_pad][XS]  q (k) | w (I), genotype-file order, zeros when excluded
     const double *y;        // [n_pad]      outcome / event, NaN = sample not in the design
@@ -80,13 +81,15 @@ struct LogitCfg {
 template <bool PACKED, int NT>
 __global__ void __launch_bounds__(256)
 logistic_irls_kernel(IterDesignDev T, const void *__restrict__ geno, long long pitch, int n_snps,
-                     double *__restrict__ out, int *__restrict__ iout, long long ostride) {
+                     double *__restrict__ out, int *__restrict__ iout, long long ostride, int only_deferred) {
     using Cfg = LogitCfg<NT>;
     constexpr int PH = Cfg::PH, XT = Cfg::XT;
     extern __shared__ __align__(16) double sm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int snp = blockIdx.x * (blockDim.x >> 5) + warp;
     if (snp >= n_snps) return;
+    // second pass behind logistic_thread_kernel: only the markers it left unfinished
+    if (only_deferred && iout[(long long)GT_I_STATUS * ostride + snp] != -77) return;
     const int k = T.k, I = T.I, p = T.p;
     const int nf = GT_F_PARAM0 + 6 * p;
     const double EPS = 2.220446049250313e-16;

@@ -38,6 +38,7 @@ ABI_SYMBOLS = [
     "gt_engine_dominant_kernel", "gt_engine_kernel_breakdown", "gt_measure_fp64_peak",
     "gt_measure_dmma_peak", "gt_debug_read_pattern", "gt_format_rows",
     "gt_host_t_sf2", "gt_host_t_ppf975", "gt_host_norm_sf2",
+    "gt_host_lt_exp_neg", "gt_host_lt_log1p01",
 ]
 
 
@@ -91,8 +92,11 @@ def load_library():
     lib.gt_engine_set_design.argtypes = [vp, c.POINTER(_DesignDesc)]
     lib.gt_engine_set_sample_sex.argtypes = [vp, vp]
     lib.gt_engine_set_file_maf_output.argtypes = [vp, vp]
-    for name in ("gt_host_t_sf2", "gt_host_t_ppf975", "gt_host_norm_sf2"):
+    for name in ("gt_host_t_sf2", "gt_host_t_ppf975", "gt_host_norm_sf2",
+                 "gt_host_lt_exp_neg", "gt_host_lt_log1p01"):
         getattr(lib, name).restype = c.c_double
+    lib.gt_host_lt_exp_neg.argtypes = [c.c_double]
+    lib.gt_host_lt_log1p01.argtypes = [c.c_double]
     lib.gt_host_t_sf2.argtypes = [c.c_double, c.c_double]
     lib.gt_host_t_ppf975.argtypes = [c.c_double]
     lib.gt_host_norm_sf2.argtypes = [c.c_double]

@@ -111,16 +111,21 @@ int gt_engine_destroy(gt_engine *e);
  * use cudaStreamLegacy / cudaStreamPerThread for a default stream. */
 int gt_engine_set_stream(gt_engine *e, void *cuda_stream);
 int gt_engine_synchronize(gt_engine *e);
-/* Engine options.  "contract_tc" = 1 (default): run the linear contraction of
- * designs without interaction on the tcgen05 int8 tensor-core kernel (exact
- * fixed point) instead of the FP64 kernel.  "host_chunk" = n: markers per
+/* Engine options.  "contract_tc" = 1 (default): run the linear contraction
+ * (designs with and without SNP x covariate interactions) on the tcgen05 int8
+ * tensor-core kernel (exact fixed point) instead of the FP64 kernel.  "host_chunk" = n: markers per
  * stage of the copy-in / compute / copy-back pipeline of the *_host entry
  * points (0 = automatic).  "stream_corrections" = 1 (default): missing-sample
  * corrections of those designs on the streaming thread-per-SNP kernel instead
  * of the gather kernel.  "cox_maxiter" = n: Newton step limit of the Cox model
  * (PHReg.fit's maxiter, default 100; reaching it is "Maximum Likelihood
- * optimization failed to converge", survival.py:87-88).  "tc_debug": tuning
- * probes of the tcgen05 kernel. */
+ * optimization failed to converge", survival.py:87-88).  "thread_solve" = 1
+ * (default): thread-per-SNP solve of narrow linear designs.  "thread_iter" = 1
+ * (default): logistic fits of .bed rows with a binary outcome, no interaction
+ * and at most 13 parameters run on the thread-per-SNP IRLS kernel when the
+ * call has at least "thread_iter_min" markers (default 4096), the warp-per-SNP
+ * kernel finishing what it defers.  "tc_debug": tuning probes of the tcgen05
+ * kernel. */
 int gt_engine_set_option(gt_engine *e, const char *name, int value);
 
 /* Replaces the per-worker setup of _gwas_worker (analysis.py:68-106) and the
@@ -197,6 +202,10 @@ int gt_debug_read_pattern(gt_engine *e, const uint8_t *packed_dev, int64_t pitch
 double gt_host_t_sf2(double t, double df);
 double gt_host_t_ppf975(double df);
 double gt_host_norm_sf2(double z);
+/* exp(-a), a >= 0, and log(1 + t), t in [0, 1], as the thread-per-SNP logistic kernel
+ * evaluates them (GLM Binomial mean and deviance, statsmodels genmod/families). */
+double gt_host_lt_exp_neg(double a);
+double gt_host_lt_log1p01(double t);
 
 /* Streaming result sink (host only): format `n_rows` result rows as delimited
  * text, the way GWASWriter / RowWriter.handle() does one dict at a time

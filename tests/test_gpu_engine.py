@@ -211,6 +211,47 @@ def test_logistic_packed(engine):
     print("logistic worst rel err", worst)
 
 
+def test_logistic_thread_kernel_matches_oracle_and_warp_kernel(engine):
+    """The thread-per-SNP IRLS kernel (binary outcome, no interaction): every marker against
+    the oracle, and statuses / iteration counts / values against the warp-per-SNP kernel.
+    Edge markers: perfect separation (deferred to the warp kernel), monomorphic, all
+    missing, MAF above one half (flip), MAF under the threshold; samples are a permuted
+    subset of the file."""
+    rng = np.random.default_rng(77)
+    n_file, n, n_snps = 1500, 1300, 500
+    C, names = synth_design(rng, n, k_extra=3)
+    pos = rng.permutation(n_file)[:n].astype(np.int32)
+    Gfile = synth_genotypes(rng, n_snps, n_file, missing=0.03, maf_lo=0.02, maf_hi=0.98)
+    eta = -0.3 + 0.4 * C[:, 0] + 0.25 * np.nan_to_num(Gfile[7, pos])
+    y = (rng.random(n) < 1 / (1 + np.exp(-eta))).astype(float)
+    Gfile[0, pos] = 2.0 * y            # separates the outcome
+    Gfile[1] = 0.0                     # monomorphic
+    Gfile[2] = np.nan                  # all missing
+    Gfile[3] = (rng.random(n_file) < 0.004) * 1.0   # MAF below the threshold
+    engine.set_design("logistic", y, C, sample_pos=pos, n_file=n_file, maf_t=0.01)
+    packed = pack_rows(Gfile)
+    try:
+        engine.set_option("thread_iter_min", 64)
+        res = engine.run_packed_host(packed)
+        engine.set_option("thread_iter", 0)
+        ref = engine.run_packed_host(packed)
+    finally:
+        engine.set_option("thread_iter", 1)
+        engine.set_option("thread_iter_min", 4096)
+    G = Gfile[:, pos]
+    oracle = run_oracle("logistic", y[:, None], C, names, G, maf_t=0.01)
+    problems, worst, n_ok = compare("logistic", res, oracle, names, rtol=LOGIT_TOL)
+    assert not problems, problems[:10]
+    assert res.status[0] == 6 and res.status[2] == 1 and res.status[3] == 2
+    assert n_ok >= n_snps - 5
+    assert (res.status == ref.status).all() and (res.niter == ref.niter).all()
+    assert (res.nobs == ref.nobs).all() and (res.flip == ref.flip).all()
+    assert res.flip.sum() > 100
+    ok = res.status == 0
+    np.testing.assert_allclose(res.out[:, ok], ref.out[:, ok], rtol=1e-9, atol=0, equal_nan=True)
+    print("logistic thread kernel worst rel err", worst, "ok", n_ok)
+
+
 def test_logistic_interaction_subset_and_separation(engine):
     rng = np.random.default_rng(22)
     n_file, n, n_snps = 1200, 1000, 60
@@ -665,7 +706,10 @@ def test_baseline_configs_full_size_properties(engine, config):
         assert ((p >= 0) & (p <= 1)).all()
     p_snp = np.sort(res.param(len(names))[5])
     assert np.abs(p_snp - (np.arange(n_snps) + 0.5) / n_snps).max() < 0.02
-    a, b = n_snps // 2 - 777, n_snps // 2 + 1234
+    # (logistic: calls of at least 4,096 markers run on the thread-per-SNP kernel, smaller
+    # ones on the warp-per-SNP kernel, which sums in another order: keep the sub-range on
+    # the same kernel)
+    a, b = n_snps // 2 - 777, n_snps // 2 + (4321 if model == "logistic" else 1234)
     out2, iout2 = engine.run_packed_dev(dev[a:b], b - a)
     sub = engine.fetch(out2, iout2)
     np.testing.assert_array_equal(sub.iout, res.iout[:, a:b])

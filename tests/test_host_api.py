@@ -635,6 +635,29 @@ def test_p_value_formulas_match_scipy():
         assert lib.gt_host_norm_sf2(float(-z)) == lib.gt_host_norm_sf2(float(z))
 
 
+def test_logistic_thread_exp_log_formulas():
+    """exp(-a) and log(1 + t) of the thread-per-SNP logistic kernel (host build of the same
+    source) against numpy: the deviance stop rule compares sums of these to 1e-8."""
+    from genetest_b200 import engine
+    lib = engine.load_library()
+    rng = np.random.default_rng(11)
+    a = np.concatenate([[0.0, 1e-300, 1e-17, 1e-9, 0.3, 0.34657, 0.6931471805599453, 1.0, 36.0,
+                         37.5, 699.9, 700.0, 800.0], rng.uniform(0, 40, 4000),
+                        rng.exponential(1.0, 4000)])
+    got = np.array([lib.gt_host_lt_exp_neg(float(v)) for v in a])
+    want = np.exp(-np.minimum(a, 700.0))
+    assert np.max(np.abs(got - want) / want) < 6e-16
+    t = np.concatenate([[0.0, 1e-300, 1e-20, 1e-9, 0.4142135623730950, 0.4142135623730951,
+                         0.41421356237309515, 0.5, 1.0], rng.uniform(0, 1, 4000),
+                        np.exp(-rng.uniform(0, 40, 4000))])
+    got = np.array([lib.gt_host_lt_log1p01(float(v)) for v in t])
+    want = np.log1p(t)
+    # log(1 + t) through d = 1 + t: absolute accuracy of one ulp of d (the deviance needs no more)
+    assert np.max(np.abs(got - want)) < 2.3e-16
+    big = t > 1e-3
+    assert np.max(np.abs(got[big] - want[big]) / want[big]) < 3e-13
+
+
 def test_properties_pack_roundtrip_and_float_repr():
     """Property tests (hypothesis): 2-bit packing round-trips for any shape,
     and the native formatter reproduces ``repr(float)`` for any double."""
