@@ -61,12 +61,13 @@ def unpack_rows(packed, n_samples):
 class PlinkReader(GenotypesReader):
     def __init__(self, prefix):
         self.prefix = prefix
-        self._fam = []
-        with open(prefix + ".fam") as f:
-            for line in f:
-                row = line.split()
-                if row:
-                    self._fam.append(row)
+        # (the C parser: biobank-size .fam files are 1e5 .. 1e6 lines)
+        if os.path.getsize(prefix + ".fam"):
+            fam = pd.read_csv(prefix + ".fam", sep=r"\s+", header=None, dtype=str,
+                              keep_default_na=False, na_filter=False, engine="c")
+            self._fam = fam.values.tolist()
+        else:
+            self._fam = []
         fids = [r[0] for r in self._fam]
         iids = [r[1] for r in self._fam]
         # geneparse's plink reader uses the IID, falling back to FID_IID when
