@@ -30,6 +30,10 @@
 #include "gt_contract_tc.cuh"
 #include "gt_contract_tc2.cuh"
 
+#ifndef GT_CS_UNROLL4
+#define GT_CS_UNROLL4 0
+#endif
+
 namespace gtk {
 
 constexpr int kCsBlk = 512;             // samples per shared-memory block
@@ -211,6 +215,16 @@ missing_corr_stream_kernel(const CorrStreamParams P) {
                 load_next(vA, pairA);
                 accumulate(vB);
                 advance();
+#if GT_CS_UNROLL4
+                // a second pair of samples before the warp votes again (a lane that is out of
+                // samples of the blocks it may touch adds zeros)
+                load_next(vB, pairB);
+                accumulate(vA);
+                advance();
+                load_next(vA, pairA);
+                accumulate(vB);
+                advance();
+#endif
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[b % kCsBuf]);
