@@ -44,7 +44,7 @@ struct gt_engine {
     bool use_thread_solve = true;  // thread-per-SNP solve for narrow designs without interaction
     bool use_thread_iter = true;   // thread-per-SNP IRLS for binary outcomes without interaction
     int thread_iter_min = 4096;    // ... for batches of at least this many markers (fewer: warp per SNP)
-    DevBuf dIterScratch;
+    DevBuf dIterScratch, dIterT;
     int tc_dbg = 0;
     int tc_N = 0;              // 0: the design does not run on the tcgen05 kernel
     int tc_hom = 0;            // interaction design: MMA tiles of 64 markers x (dosage, homozygote) rows
@@ -410,7 +410,7 @@ int gt_engine_destroy(gt_engine *e) {
     for (auto &ev : e->events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     DevBuf *bufs[] = {&e->dE, &e->dMask, &e->dFF0, &e->dR, &e->dRinv, &e->dTq, &e->dIter, &e->dBimg, &e->dScale, &e->dErr, &e->dEi,
                       &e->dS, &e->dCounts, &e->dGsum, &e->dMlist, &e->dMcount, &e->dCorr, &e->dGeno, &e->dOut, &e->dIout,
-                      &e->dSexM, &e->dSexF, &e->dSexRow, &e->dMafO, &e->dFlipO, &e->dCounter, &e->dFileMaf, &e->dIterScratch};
+                      &e->dSexM, &e->dSexF, &e->dSexRow, &e->dMafO, &e->dFlipO, &e->dCounter, &e->dFileMaf, &e->dIterScratch, &e->dIterT};
     for (DevBuf *b : bufs) b->release();
     for (int i = 0; i < 2; ++i) {
         if (e->pin[i]) cudaFreeHost(e->pin[i]);
@@ -519,6 +519,8 @@ const char *gt_engine_dominant_kernel(const gt_engine *e) {
     if (e->have_design && e->model == GT_MODEL_LOGISTIC && e->use_thread_iter && e->T.I == 0 && e->T.p >= 2 &&
         e->T.p <= 13 && e->T.y_binary && !e->T.degenerate)
         return "logistic_thread_kernel";       // (calls of at least thread_iter_min .bed markers)
+    if (e->have_design && e->model == GT_MODEL_COXPH && e->use_thread_iter && e->T.th_ok)
+        return "cox_thread_kernel";
     return e->dominant.c_str();
 }
 
@@ -835,7 +837,7 @@ int gt_engine_set_design(gt_engine *e, const gt_design_desc *d) {
         CK(cudaStreamSynchronize(st));   // host vectors go out of scope
     } else if (d->model == GT_MODEL_LOGISTIC || d->model == GT_MODEL_COXPH) {
         rc = gtk::iter_set_design(d, pos, n_file, n_chunks, pitch, (const uint8_t *)e->dMask.p,
-                                  e->dIter, e->T, st, g_err);
+                                  e->dIter, e->dIterT, e->T, st, g_err);
         if (rc) return rc;
         e->dominant = d->model == GT_MODEL_LOGISTIC ? "logistic_irls_kernel" : "cox_newton_kernel";
     } else {
@@ -1164,6 +1166,10 @@ static int run_any(gt_engine *e, const void *geno, int64_t pitch, bool packed, i
         // coef / se of the last solve of every marker (thread-per-SNP logistic kernel)
         if (e->model == GT_MODEL_LOGISTIC && packed && e->use_thread_iter &&
             (rc = e->dIterScratch.reserve((size_t)(n_snps + 32) * 2 * 13 * 8))) return rc;
+        // the codes of every marker in schedule order (thread-per-SNP Cox kernel)
+        if (e->model == GT_MODEL_COXPH && packed && e->use_thread_iter && e->T.th_ok &&
+            n_snps >= e->thread_iter_min &&
+            (rc = e->dIterScratch.reserve((size_t)(n_snps + 32) * (size_t)(e->T.th_n / 16) * 4))) return rc;
     }
     return gtk::iter_run(T, e->model, geno, pitch, packed, n_snps, out, iout, ldo, e->stream,
                          (int *)e->dCounter.p, e->timing,
@@ -1216,8 +1222,9 @@ static int run_host(gt_engine *e, const void *src, int64_t src_pitch_bytes, int6
         // pay a partial last wave per chunk: keep their chunks large
         chunk = std::max<int64_t>(chunk, e->model == GT_MODEL_LINEAR ? 8192 : 65536);
         // thread-per-SNP IRLS: whole waves of 148 CTAs x 224 markers
-        if (packed && e->model == GT_MODEL_LOGISTIC && e->use_thread_iter && e->T.I == 0 && e->T.p <= 13 &&
-            e->T.y_binary && chunk >= 148 * gtk::kLtMaxThreads)
+        if (packed && e->use_thread_iter && chunk >= 148 * gtk::kLtMaxThreads &&
+            ((e->model == GT_MODEL_LOGISTIC && e->T.I == 0 && e->T.p <= 13 && e->T.y_binary) ||
+             (e->model == GT_MODEL_COXPH && e->T.th_ok)))
             chunk = chunk / (148 * gtk::kLtMaxThreads) * (148 * gtk::kLtMaxThreads);
         chunk = std::min<int64_t>(chunk, std::max<int64_t>(1024, ((int64_t)512 << 20) / dev_pitch_bytes / 1024 * 1024));
         // whole half-waves of the tcgen05 contraction (148 CTAs x 128 .. 512 SNP rows)

@@ -11,12 +11,13 @@
 #include "gt_logistic.cuh"
 #include "gt_logistic_thread.cuh"
 #include "gt_coxk.cuh"
+#include "gt_cox_thread.cuh"
 
 namespace gtk {
 
 // Uploads, into one device allocation:  X [n_pad][XS] | y [n_pad] | Rinv [k*k]
 static int iter_set_design(const gt_design_desc *d, const std::vector<int> &pos, int n_file,
-                           int n_chunks, int64_t pitch, const uint8_t *dmask, DevBuf &buf,
+                           int n_chunks, int64_t pitch, const uint8_t *dmask, DevBuf &buf, DevBuf &bufT,
                            IterDesignDev &T, cudaStream_t st, std::string &err) {
     (void)pitch; (void)dmask; (void)err;
     const int n = d->n, k = d->k, I = d->n_inter;
@@ -145,6 +146,35 @@ static int iter_set_design(const gt_design_desc *d, const std::vector<int> &pos,
         // pointers may have moved
         X = host.data(); y = X + n_pad * XSs; Rinv = y + n_pad;
         T.n_slots = (int)ns;
+        // ---- schedule of the thread-per-SNP kernel (gt_cox_thread.cuh): the design rows in
+        //      descending time, censored samples of a time point before its event, no padding
+        //      inside; only without strata, interactions and tied events ----
+        T.th_ok = 0;
+        bool tied = !big_first.empty();
+        for (size_t t = 0; t < ns && !tied; ++t)
+            tied = (slot_info[t] & 31) != ((slot_info[t] >> 5) & 31);
+        if (!strata && !tied && I == 0 && !H.degenerate && p >= 2 && p <= 12) {
+            const int XST = (k + 2) & ~1;                 // q (k) | event flag, rounded up to even
+            const size_t nT = ((size_t)n + 255) / 256 * 256;
+            std::vector<double> ht(nT * XST + nT / 2 + 2, 0.0);
+            int *tp = (int *)&ht[nT * XST];
+            for (size_t t = 0; t < nT; ++t) tp[t] = -1;
+            size_t w = 0;
+            for (size_t t = 0; t < ns; ++t) {
+                if (slot_pos[t] < 0) continue;
+                const int row = row_of_pos[slot_pos[t]];
+                for (int j = 0; j < k; ++j) ht[w * XST + j] = H.Q[(size_t)j * n + row];
+                ht[w * XST + k] = (double)((slot_info[t] >> 10) & 1);
+                tp[w] = slot_pos[t];
+                ++w;
+            }
+            int rct = upload(bufT, ht.data(), ht.size() * 8, st);
+            if (rct) return rct;
+            CK(cudaStreamSynchronize(st));
+            T.th_ok = 1; T.th_n = (int)nT; T.th_XS = XST;
+            T.th_X = (const double *)bufT.p;
+            T.th_pos = (const int *)((const double *)bufT.p + nT * XST);
+        }
     }
     int rc = upload(buf, host.data(), host.size() * 8, st);
     if (rc) return rc;
@@ -165,6 +195,7 @@ static int iter_set_design(const gt_design_desc *d, const std::vector<int> &pos,
         T.n_seg = (int)seg_start.size() - 1;
         T.colmax = (const double *)buf.p + (host.size() - p);
     } else {
+        T.th_ok = 0;
         T.n_slots = 0; T.Xs = nullptr; T.slot_pos = nullptr; T.slot_info = nullptr; T.blk_info = nullptr; T.colmax = nullptr;
         T.n_seg = 0; T.seg_start = nullptr;
     }
@@ -212,7 +243,8 @@ static int launch_logistic_thread(const IterDesignDev &T, const void *geno, int6
 
 template <bool PACKED, int NT>
 static int launch_cox(const IterDesignDev &T, const void *geno, int64_t pitch, int n_snps,
-                      double *out, int32_t *iout, long long ldo, cudaStream_t st, int *counter) {
+                      double *out, int32_t *iout, long long ldo, cudaStream_t st, int *counter,
+                      int only_deferred = 0) {
     using Cfg = CoxCfg<NT>;
     // two CTAs per SM: as many warps as fit half of the shared memory
     int wpc = 8;
@@ -224,7 +256,26 @@ static int launch_cox(const IterDesignDev &T, const void *geno, int64_t pitch, i
     CK(cudaMemsetAsync(counter, 0, sizeof(int), st));
     const int grid = std::min((n_snps + wpc - 1) / wpc, 148 * 2);
     cox_newton_kernel<PACKED, NT><<<grid, wpc * 32, smem, st>>>(
-        T, geno, pitch, n_snps, out, iout, ldo, counter);
+        T, geno, pitch, n_snps, out, iout, ldo, counter, only_deferred);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// thread-per-SNP Newton solver (gt_cox_thread.cuh)
+template <int P>
+static int launch_cox_thread(const IterDesignDev &T, const void *geno, int64_t pitch, int n_snps,
+                             double *out, int32_t *iout, long long ldo, cudaStream_t st,
+                             uint32_t *gperm, long long ldw, int maxround) {
+    const int waves = (n_snps + 148 * kLtMaxThreads - 1) / (148 * kLtMaxThreads);
+    int nthr = ((n_snps + 148 * waves - 1) / (148 * waves) + 31) / 32 * 32;
+    nthr = std::max(32, std::min(nthr, kLtMaxThreads));
+    const int XST = (P + 1) & ~1;                               // (K + 2) & ~1 with K = P - 1
+    const size_t smem = 128 + (size_t)kLtBuf * (kLtBlk * XST * 8) + 128 +
+                        (size_t)((((P - 1) * (P - 1) + 1) & ~1) + ((P + 1) & ~1)) * 8 + (size_t)P * nthr * 8;
+    CK(cudaFuncSetAttribute((const void *)cox_thread_kernel<P>,
+                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cox_thread_kernel<P><<<(n_snps + nthr - 1) / nthr, nthr + 32, smem, st>>>(
+        T, (const uint8_t *)geno, pitch, n_snps, out, iout, ldo, gperm, ldw, maxround);
     CK(cudaGetLastError());
     return 0;
 }
@@ -240,9 +291,25 @@ static int iter_run(const IterDesignDev &T, int model, const void *geno, int64_t
     int rc;
     if (model == GT_MODEL_COXPH) {
         if (packed) {
-            rc = NT == 1 ? launch_cox<true, 1>(T, geno, pitch, n_snps, out, iout, ldo, st, counter)
-               : NT == 2 ? launch_cox<true, 2>(T, geno, pitch, n_snps, out, iout, ldo, st, counter)
-                         : launch_cox<true, 3>(T, geno, pitch, n_snps, out, iout, ldo, st, counter);
+            // .bed rows, no strata / interaction / tied event times, p <= 12, enough markers:
+            // one thread per marker first, the warp kernel finishes what that one deferred
+            int deferred = 0;
+            if (use_thread && lt_scratch && T.th_ok && T.p >= 2 && T.p <= 12 && n_snps >= thread_min) {
+                const long long ldw = (n_snps + 31) / 32 * 32;
+                rc = 0;
+#define GT_CT(PP) case PP: rc = launch_cox_thread<PP>(T, geno, pitch, n_snps, out, iout, ldo, st, (uint32_t *)lt_scratch, ldw, 8); break;
+                switch (T.p) {
+                    GT_CT(2) GT_CT(3) GT_CT(4) GT_CT(5) GT_CT(6) GT_CT(7) GT_CT(8) GT_CT(9) GT_CT(10)
+                    GT_CT(11) GT_CT(12)
+                }
+#undef GT_CT
+                if (rc) return rc;
+                deferred = 1;
+                all_launches += 1;
+            }
+            rc = NT == 1 ? launch_cox<true, 1>(T, geno, pitch, n_snps, out, iout, ldo, st, counter, deferred)
+               : NT == 2 ? launch_cox<true, 2>(T, geno, pitch, n_snps, out, iout, ldo, st, counter, deferred)
+                         : launch_cox<true, 3>(T, geno, pitch, n_snps, out, iout, ldo, st, counter, deferred);
         } else {
             rc = NT == 1 ? launch_cox<false, 1>(T, geno, pitch, n_snps, out, iout, ldo, st, counter)
                : NT == 2 ? launch_cox<false, 2>(T, geno, pitch, n_snps, out, iout, ldo, st, counter)

@@ -1,0 +1,395 @@
+// K5, thread-per-SNP version: batched Newton solver for the Cox proportional
+// hazards model, FP64, for .bed rows, designs without interaction or strata and
+// without tied event times (Efron's and Breslow's likelihoods coincide then) and
+// at most 12 parameters.
+//
+// Restates sm.PHReg(tte, X, status=event, ties="efron").fit() as called by
+// genetest/statistics/models/survival.py:77-82 -- Newton from beta = 0 on
+// loglike / nobs with a 1e-10 ridge on the Hessian diagonal, until every
+// abs(step) <= 1e-8, covariance inv(-H(beta_hat)) -- after _gwas_worker's
+// complete-case mask, MAF and flip (genetest/analysis.py:119-157): the same
+// quantities as the warp-per-SNP kernel (gt_coxk.cuh), laid out the other way
+// round.  With the samples in descending time, S0 / S1 the running risk-set sums
+// and inv_t = 1 / S0 at the event times,
+//   -H    = sum_i W_i x_i x_i'  -  sum_t u_t u_t',   u_t = S1 / S0 at event t
+//   score = sum_events x_i  -  sum_i W_i x_i
+//   W_i   = e_i * (sum of inv_t over the event times <= t_i)
+// so ONE THREAD PER MARKER keeps one p x p triangle, S1 and the score in
+// registers and walks the samples twice per Newton step: pass 1 totals inv_t,
+// pass 2 accumulates.  No warp scans, no shuffles, no tensor-core tiles that
+// compute 64 products for the 66 of an 11 x 11 triangle twice over.
+//   * the design rows [q | event flag] (descending time, the same for every
+//     marker) come through a TMA-fed shared-memory ring, read by all lanes at
+//     the same address (broadcast);
+//   * a first sweep gathers the marker's genotype codes into that order once
+//     and writes them word-major (word w of all markers side by side): the
+//     passes read them coalesced;
+//   * the p x p Cholesky solve, the triangular inverse and the map back to the
+//     reference's parameterisation run fully unrolled in registers.
+// The markers of a CTA take their Newton steps in lockstep; whatever is not
+// finished after `maxround` rounds (or needs the exact maximum of the linear
+// predictor again) is left to the warp-per-SNP kernel (status GT_ITER_DEFER).
+#pragma once
+
+#include "gt_common.cuh"
+#include "gt_contract_tc.cuh"
+#include "gt_contract_tc2.cuh"
+#include "gt_logistic.cuh"
+#include "gt_logistic_thread.cuh"
+
+namespace gtk {
+
+template <int P>
+__global__ void __launch_bounds__(kLtMaxThreads + 32, 1)
+cox_thread_kernel(IterDesignDev T, const uint8_t *__restrict__ geno, long long pitch, int n_snps,
+                  double *__restrict__ out, int *__restrict__ iout, long long ostride,
+                  uint32_t *__restrict__ gperm /* [th_n / 16][ldw] codes in schedule order */, long long ldw,
+                  int maxround) {
+    constexpr int K = P - 1;                              // covariates (Cox has no constant)
+    constexpr int NH = P * (P + 1) / 2;
+    constexpr int XST = (K + 2) & ~1;                     // q (K) | event flag
+    constexpr int XBLK = kLtBlk * XST * 8;
+    constexpr int NF = GT_F_PARAM0 + 6 * P;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned char *smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+    double *sX = (double *)smem;                                   // kLtBuf x [kLtBlk][XST]
+    uint64_t *full = (uint64_t *)(smem + kLtBuf * XBLK), *empty = full + kLtBuf;
+    int *fail = (int *)(empty + kLtBuf);
+    double *sRinv = (double *)(full + 16);                         // [K * K]
+    double *sCmax = sRinv + ((K * K + 1) & ~1);                    // [P] max |x| per column
+    double *sBeta = sCmax + ((P + 1) & ~1);                        // [P][nthr]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nthr = blockDim.x - 32;
+    const int ncw = nthr >> 5;
+    if (tid == 0) {
+        for (int s = 0; s < kLtBuf; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], ncw); }
+        *fail = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    for (int t = tid; t < K * K; t += blockDim.x) sRinv[t] = T.Rinv[t];
+    for (int t = tid; t < P; t += blockDim.x) sCmax[t] = T.colmax[t];
+    __syncthreads();
+    const int nblk = T.th_n / kLtBlk;
+
+    if (warp == ncw) {
+        // ===== producer: the design rows, twice per round, while any marker of the CTA is active =====
+        int it = 0;
+        for (int round = 0; round < maxround; ++round) {
+            for (int b = 0; b < 2 * nblk; ++b, ++it) {
+                const int s = it % kLtBuf;
+                if (it >= kLtBuf && !mbar_wait2(&empty[s], ((it / kLtBuf) & 1) ^ 1, fail)) *fail = 1;
+                if (elect_one()) {
+                    mbar_expect_tx(&full[s], XBLK);
+                    bulk_g2s((unsigned char *)sX + s * XBLK,
+                             (const unsigned char *)T.th_X + (long long)(b % nblk) * XBLK, XBLK, &full[s]);
+                }
+                __syncwarp();
+            }
+            if (!__syncthreads_or(0)) break;
+        }
+        return;
+    }
+
+    // ===== one thread per marker =====
+    const int snp = blockIdx.x * nthr + tid;
+    const bool owner = snp < n_snps;
+    const uint8_t *rowp = geno + (long long)(owner ? snp : 0) * pitch;
+    uint32_t *myw = gperm + (owner ? snp : 0);
+    const int nword = T.th_n / 16;
+    auto write_fail = [&](int status, int nobs, int flip, double maf, double aux, int niter) {
+#pragma unroll 1
+        for (int f = 0; f < NF; ++f) {
+            double v = nan("");
+            if (f == GT_F_MAF) v = maf;
+            if (f == GT_F_AUX) v = aux;
+            out[(long long)f * ostride + snp] = v;
+        }
+        iout[(long long)GT_I_STATUS * ostride + snp] = status;
+        iout[(long long)GT_I_NOBS * ostride + snp] = nobs;
+        iout[(long long)GT_I_FLIP * ostride + snp] = flip;
+        iout[(long long)GT_I_NITER * ostride + snp] = niter;
+    };
+
+    // ---- first sweep: the marker's codes in schedule order; complete cases, MAF, flip ----
+    int nj = 0, sum_g = 0, nev = 0;
+    if (owner) {
+#pragma unroll 1
+        for (int w = 0; w < nword; ++w) {
+            uint32_t word = 0;
+#pragma unroll
+            for (int s = 0; s < 16; ++s) {
+                const int ps = __ldg(T.th_pos + w * 16 + s);            // the same for every lane
+                uint32_t code = 1u;                                      // padding rows: missing
+                if (ps >= 0) code = ((uint32_t)__ldg(rowp + (ps >> 2)) >> (2 * (ps & 3))) & 3u;
+                word |= code << (2 * s);
+                const bool ok = code != 1u;
+                nj += ok ? 1 : 0;
+                sum_g += code == 0u ? 2 : (code == 2u ? 1 : 0);
+                if (ok && __ldg(T.th_X + (long long)(w * 16 + s) * XST + K) != 0.0) nev += 1;
+            }
+            myw[(long long)w * ldw] = word;
+        }
+    }
+    bool active = owner;
+    int status = GT_OK, flip = 0, niter = 0;
+    double maf = nan("");
+    if (owner) {
+        if (nj == 0) { write_fail(GT_ALL_MISSING, 0, 0, nan(""), nan(""), 0); active = false; }
+        else if (!T.raw_mode) {
+            maf = ((double)sum_g / (double)nj) / 2.0;
+            if (maf > 0.5) { maf = 1.0 - maf; flip = 1; }
+            if (T.maf_o != nullptr) { maf = T.maf_o[snp]; flip = T.flip_o[snp]; }
+            if (T.use_maf_t && maf < T.maf_t) { write_fail(GT_MAF_BELOW, nj, flip, maf, maf, 0); active = false; }
+        }
+    }
+    const double g_hom = flip ? 0.0 : 2.0, g_ref = flip ? 2.0 : 0.0;   // codes 00 and 11
+
+    double *myBeta = sBeta + tid;                           // beta[a] at myBeta[a * nthr]
+#pragma unroll
+    for (int a = 0; a < P; ++a) myBeta[a * nthr] = 0.0;
+    // shift of the linear predictor: an upper bound of its maximum (0 at beta = 0, grows by
+    // at most sum_a |step_a| max |x_a| per step); past a drift of 20 the marker is deferred
+    double emax = 0.0, slack = 0.0, llf = 0.0;
+    bool final_eval = false;
+    int it = 0;
+#define GT_H(a, b) H[(a) * P - (a) * ((a) - 1) / 2 + ((b) - (a))]      /* a <= b */
+#define GT_L(i, j) GT_H(j, i)                                           /* i >= j */
+    for (int round = 0; round < maxround; ++round) {
+        // ---- pass 1: total of 1 / S0 over the event times ----
+        double Ttot = 0.0;
+        {
+            double S0 = 0.0;
+            for (int b = 0; b < nblk; ++b, ++it) {
+                const int st = it % kLtBuf;
+                {
+                    const uint32_t fa = smem_u32(&full[st]), fp = (it / kLtBuf) & 1;
+                    int spin = 0;
+                    while (!mbar_try(fa, fp)) if (++spin > (1 << 22)) { *fail = 1; break; }
+                }
+                const double *bx = sX + st * (kLtBlk * XST);
+#pragma unroll 1
+                for (int w16 = 0; w16 < kLtBlk / 16; ++w16) {
+                    const uint32_t word = myw[(long long)(b * (kLtBlk / 16) + w16) * ldw];
+                    const double *xw = bx + w16 * 16 * XST;
+#pragma unroll 4
+                    for (int s = 0; s < 16; ++s) {
+                        const double *xr = xw + s * XST;
+                        const uint32_t code = (word >> (2 * s)) & 3u;
+                        const bool ok = code != 1u;
+                        const double g = code == 0u ? g_hom : (code == 2u ? 1.0 : g_ref);
+                        double e0 = g * myBeta[K * nthr], e1 = 0.0;
+#pragma unroll
+                        for (int a = 0; a < K; ++a) {
+                            if (a & 1) e1 = fma(xr[a], myBeta[a * nthr], e1);
+                            else e0 = fma(xr[a], myBeta[a * nthr], e0);
+                        }
+                        const double e = ok ? lt_exp_neg(emax - (e0 + e1)) : 0.0;
+                        S0 += e;
+                        if (xr[K] != 0.0) Ttot += ok ? lt_rcp(S0) : 0.0;       // event (warp-uniform)
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[st]);
+            }
+        }
+        // ---- pass 2: log-likelihood, score, Hessian ----
+        double H[NH], sc[P], S1[P];
+#pragma unroll
+        for (int i = 0; i < NH; ++i) H[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < P; ++i) { sc[i] = 0.0; S1[i] = 0.0; }
+        double S0 = 0.0, PI = 0.0, ll = 0.0;
+        for (int b = 0; b < nblk; ++b, ++it) {
+            const int st = it % kLtBuf;
+            {
+                const uint32_t fa = smem_u32(&full[st]), fp = (it / kLtBuf) & 1;
+                int spin = 0;
+                while (!mbar_try(fa, fp)) if (++spin > (1 << 22)) { *fail = 1; break; }
+            }
+            const double *bx = sX + st * (kLtBlk * XST);
+#pragma unroll 1
+            for (int w16 = 0; w16 < kLtBlk / 16; ++w16) {
+                const uint32_t word = myw[(long long)(b * (kLtBlk / 16) + w16) * ldw];
+                const double *xw = bx + w16 * 16 * XST;
+#pragma unroll 2
+                for (int s = 0; s < 16; ++s) {
+                    const double *xr = xw + s * XST;
+                    const uint32_t code = (word >> (2 * s)) & 3u;
+                    const bool ok = code != 1u;
+                    const double g = code == 0u ? g_hom : (code == 2u ? 1.0 : g_ref);
+                    double x[P];
+#pragma unroll
+                    for (int a = 0; a < K; ++a) x[a] = xr[a];
+                    x[K] = g;
+                    double e0 = g * myBeta[K * nthr], e1 = 0.0;
+#pragma unroll
+                    for (int a = 0; a < K; ++a) {
+                        if (a & 1) e1 = fma(x[a], myBeta[a * nthr], e1);
+                        else e0 = fma(x[a], myBeta[a * nthr], e0);
+                    }
+                    const double eta = e0 + e1;
+                    const double e = ok ? lt_exp_neg(emax - eta) : 0.0;
+                    S0 += e;
+#pragma unroll
+                    for (int a = 0; a < P; ++a) S1[a] = fma(e, x[a], S1[a]);
+                    const bool ev = xr[K] != 0.0;                       // warp-uniform
+                    double W = e * (Ttot - PI);
+                    if (ev) {
+                        // this sample is an event (W counts its own term): u = S1 / S0
+                        const double inv = ok ? lt_rcp(S0) : 0.0;
+                        PI += inv;
+                        if (final_eval && ok) ll += (eta - emax) - log(S0);
+#pragma unroll
+                        for (int a = 0; a < P; ++a) {
+                            const double ua = S1[a] * inv;
+                            sc[a] += ok ? x[a] : 0.0;
+#pragma unroll
+                            for (int c2 = a; c2 < P; ++c2) GT_H(a, c2) = fma(-ua, S1[c2] * inv, GT_H(a, c2));
+                        }
+                    }
+#pragma unroll
+                    for (int a = 0; a < P; ++a) {
+                        const double wx = W * x[a];
+                        sc[a] -= wx;
+#pragma unroll
+                        for (int c2 = a; c2 < P; ++c2) GT_H(a, c2) = fma(wx, x[c2], GT_H(a, c2));
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[st]);
+        }
+
+        if (active) {
+            const double dn = (double)nj;
+            if (!final_eval) {
+                // Newton step on loglike / nobs with the reference's ridge: (-H / n - ridge... ) as in
+                // gt_coxk.cuh: Hc = H / n with 1e-10 taken off the diagonal, rhs = score / n
+#pragma unroll
+                for (int a = 0; a < P; ++a) {
+#pragma unroll
+                    for (int c2 = a; c2 < P; ++c2) GT_H(a, c2) = GT_H(a, c2) / dn - (a == c2 ? 1e-10 : 0.0);
+                    sc[a] /= dn;
+                }
+            } else llf = ll;
+            // ---- Cholesky in place ----
+            bool okc = true;
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                double d = GT_L(j, j);
+#pragma unroll
+                for (int c = 0; c < j; ++c) d = fma(-GT_L(j, c), GT_L(j, c), d);
+                if (!(d > 0.0)) okc = false;
+                const double sj = sqrt(d), inv = 1.0 / sj;
+                GT_L(j, j) = sj;
+#pragma unroll
+                for (int i = j + 1; i < P; ++i) {
+                    double v = GT_L(i, j);
+#pragma unroll
+                    for (int c = 0; c < j; ++c) v = fma(-GT_L(i, c), GT_L(j, c), v);
+                    GT_L(i, j) = v * inv;
+                }
+            }
+            if (!okc) {
+                write_fail(GT_SINGULAR, nj, flip, maf, nan(""), niter);
+                active = false;
+            } else if (!final_eval) {
+                // step = Hc^-1 score: forward, then back substitution (in sc)
+#pragma unroll
+                for (int i = 0; i < P; ++i) {
+                    double v = sc[i];
+#pragma unroll
+                    for (int c = 0; c < i; ++c) v = fma(-GT_L(i, c), sc[c], v);
+                    sc[i] = v / GT_L(i, i);
+                }
+#pragma unroll
+                for (int i = P - 1; i >= 0; --i) {
+                    double v = sc[i];
+#pragma unroll
+                    for (int c = i + 1; c < P; ++c) v = fma(-GT_L(c, i), sc[c], v);
+                    sc[i] = v / GT_L(i, i);
+                }
+                // convergence is judged on the reference's parameterisation: T step
+                double worst = 0.0, grow = 0.0;
+#pragma unroll
+                for (int i = 0; i < P; ++i) {
+                    double dd = 0.0;
+                    if (i < K) {
+#pragma unroll
+                        for (int a = i; a < K; ++a) dd = fma(sRinv[i * K + a], sc[a], dd);
+                    } else dd = sc[i];
+                    worst = fmax(worst, fabs(dd));
+                    grow = fma(fabs(sc[i]), sCmax[i], grow);
+                    myBeta[i * nthr] += sc[i];
+                }
+                emax += grow; slack += grow;
+                niter += 1;
+                if (!(worst == worst)) { write_fail(GT_NAN_PVALUE, nj, flip, maf, nan(""), niter); active = false; }
+                else if (niter >= T.newton_maxiter) { write_fail(GT_NO_CONVERGENCE, nj, flip, maf, nan(""), niter); active = false; }
+                else if (!(worst > 1e-8)) final_eval = true;
+                else if (slack > 20.0) {
+                    // the bound has drifted: the warp kernel recomputes the exact maximum
+                    iout[(long long)GT_I_STATUS * ostride + snp] = GT_ITER_DEFER;
+                    active = false;
+                }
+            } else {
+                // ---- converged: covariance inv(-H) = Z'Z with Z = Lc^-1 ----
+#pragma unroll
+                for (int j = P - 1; j >= 0; --j) {
+                    const double zjj = 1.0 / GT_L(j, j);
+                    GT_L(j, j) = zjj;
+#pragma unroll
+                    for (int i = P - 1; i > j; --i) {
+                        double v = 0.0;
+#pragma unroll
+                        for (int c = j + 1; c <= i; ++c) v = fma(GT_L(i, c), GT_L(c, j), v);
+                        GT_L(i, j) = -v * zjj;
+                    }
+                }
+                double pv_snp = 0.0;
+#pragma unroll
+                for (int i = 0; i < P; ++i) {
+                    double cf = 0.0, var = 0.0;
+                    if (i < K) {
+#pragma unroll
+                        for (int a = i; a < K; ++a) cf = fma(sRinv[i * K + a], myBeta[a * nthr], cf);
+#pragma unroll
+                        for (int rr = i; rr < P; ++rr) {
+                            double u = 0.0;
+#pragma unroll
+                            for (int a = i; a < K; ++a)
+                                if (a <= rr) u = fma(GT_L(rr, a), sRinv[i * K + a], u);
+                            var = fma(u, u, var);
+                        }
+                    } else {
+                        cf = myBeta[K * nthr];
+                        var = GT_L(K, K) * GT_L(K, K);
+                    }
+                    const double se = sqrt(var), z = cf / se, pval = gt_norm_sf2(z);
+                    double *o = out + (long long)(GT_F_PARAM0 + 6 * i) * ostride + snp;
+                    o[0] = cf; o[ostride] = se; o[2 * ostride] = cf - GT_Z975 * se;
+                    o[3 * ostride] = cf + GT_Z975 * se; o[4 * ostride] = z; o[5 * ostride] = pval;
+                    if (i == K) pv_snp = pval;
+                }
+                if (!T.raw_mode && pv_snp != pv_snp) status = GT_NAN_PVALUE;
+                out[(long long)GT_F_MAF * ostride + snp] = maf;
+                out[(long long)GT_F_AUX * ostride + snp] = nan("");
+                out[(long long)GT_F_STAT * ostride + snp] = (double)nev;
+                out[(long long)GT_F_LLF * ostride + snp] = llf;
+                iout[(long long)GT_I_STATUS * ostride + snp] = status;
+                iout[(long long)GT_I_NOBS * ostride + snp] = nj;
+                iout[(long long)GT_I_FLIP * ostride + snp] = flip;
+                iout[(long long)GT_I_NITER * ostride + snp] = niter;
+                active = false;
+            }
+        }
+        if (!__syncthreads_or(active ? 1 : 0)) break;
+    }
+#undef GT_L
+#undef GT_H
+    if (active) iout[(long long)GT_I_STATUS * ostride + snp] = GT_ITER_DEFER;
+    if (tid == 0 && *fail) printf("cox_thread_kernel: pipeline wait timed out (block %d)\n", blockIdx.x);
+}
+
+}  // namespace gtk

@@ -541,7 +541,7 @@ template <bool PACKED, int NT>
 __global__ void __launch_bounds__(256)
 cox_newton_kernel(IterDesignDev T, const void *__restrict__ geno, long long pitch, int n_snps,
                   double *__restrict__ out, int *__restrict__ iout, long long ostride,
-                  int *__restrict__ next_marker) {
+                  int *__restrict__ next_marker, int only_deferred) {
     extern __shared__ __align__(16) double sm[];
     const int lane = threadIdx.x & 31;
     for (;;) {
@@ -549,6 +549,8 @@ cox_newton_kernel(IterDesignDev T, const void *__restrict__ geno, long long pitc
         if (lane == 0) snp = atomicAdd(next_marker, 1);
         snp = __shfl_sync(GT_FULL, snp, 0);
         if (snp >= n_snps) return;
+        // second pass behind cox_thread_kernel: only the markers it left unfinished
+        if (only_deferred && iout[(long long)GT_I_STATUS * ostride + snp] != -77) continue;
         cox_newton_one<PACKED, NT>(T, geno, pitch, n_snps, out, iout, ostride, snp, sm);
         __syncwarp();
     }

@@ -46,6 +46,11 @@ struct IterDesignDev {
     int newton_maxiter;     // coxph: PHReg.fit(maxiter=100); engine option "cox_maxiter" (tests)
     int n_seg;              // coxph: strata (1 without), blocks seg_start[s] .. seg_start[s + 1) each
     const int *seg_start;   // [n_seg + 1]
+    // coxph, thread-per-SNP kernel (no strata / interaction / tied events): design rows in
+    // descending time, th_n = n rounded up to 256 (padding rows: position -1, zeros)
+    int th_ok, th_n, th_XS;
+    const double *th_X;     // [th_n][th_XS]  q (k) | event flag
+    const int *th_pos;      // [th_n] genotype position
 };
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {

@@ -335,6 +335,61 @@ def test_coxph_packed(engine, ties):
     print("coxph ties={} worst rel err {}".format(ties, worst))
 
 
+def test_coxph_thread_kernel_matches_oracle_and_warp_kernel(engine):
+    """The thread-per-SNP Newton kernel (no strata / interaction / tied event times): every
+    marker against the oracle, and statuses / step counts / values against the warp-per-SNP
+    kernel.  Censored samples share some event times; edge markers: monomorphic (singular),
+    all missing, MAF above one half (flip), MAF under the threshold; the samples are a
+    permuted subset of the file.  With tied event times the engine keeps the warp kernel."""
+    rng = np.random.default_rng(78)
+    n_file, n, n_snps = 1400, 1200, 400
+    C, names = synth_design(rng, n, k_extra=3)
+    C, names = C[:, :-1], names[:-1]
+    pos = rng.permutation(n_file)[:n].astype(np.int32)
+    Gfile = synth_genotypes(rng, n_snps, n_file, missing=0.03, maf_lo=0.02, maf_hi=0.98)
+    Gfile[1] = 0.0
+    Gfile[2] = np.nan
+    Gfile[3] = (rng.random(n_file) < 0.004) * 1.0
+    tte, event = _cox_data(rng, n, C)
+    # censored samples at the time of an event (they belong to its risk set)
+    ev_idx = np.flatnonzero(event == 1)[:40]
+    ce_idx = np.flatnonzero(event == 0)[:40]
+    tte[ce_idx] = tte[ev_idx]
+    assert len(np.unique(tte[event == 1])) == int(event.sum())
+    packed = pack_rows(Gfile)
+    G = Gfile[:, pos]
+    Y = np.column_stack((tte, event))
+    for maf_t in (None, 0.01):
+        engine.set_design("coxph", tte, C, event=event, sample_pos=pos, n_file=n_file, maf_t=maf_t)
+        assert engine.dominant_kernel() == "cox_thread_kernel"
+        try:
+            engine.set_option("thread_iter_min", 64)
+            res = engine.run_packed_host(packed)
+            engine.set_option("thread_iter", 0)
+            ref = engine.run_packed_host(packed)
+        finally:
+            engine.set_option("thread_iter", 1)
+            engine.set_option("thread_iter_min", 4096)
+        oracle = run_oracle("coxph", Y, C, names, G, maf_t=maf_t)
+        problems, worst, n_ok = compare("coxph", res, oracle, names, rtol=LOGIT_TOL)
+        assert not problems, problems[:10]
+        if maf_t is None:
+            assert res.status[1] == 7 and res.status[2] == 1
+        else:
+            assert res.status[1] == 2 and res.status[2] == 1 and res.status[3] == 2
+        assert n_ok >= n_snps - 8
+        assert (res.status == ref.status).all() and (res.niter == ref.niter).all()
+        assert (res.nobs == ref.nobs).all() and (res.flip == ref.flip).all()
+        assert res.flip.sum() > 80
+        ok = res.status == 0
+        np.testing.assert_allclose(res.out[:, ok], ref.out[:, ok], rtol=1e-7, atol=0, equal_nan=True)
+        print("coxph thread kernel, maf_t", maf_t, "worst rel err", worst, "ok", n_ok)
+    # tied event times: the warp-per-SNP kernel (Efron groups) stays in charge
+    tte2 = np.ceil(tte * 50) / 50
+    engine.set_design("coxph", tte2, C, event=event, sample_pos=pos, n_file=n_file)
+    assert engine.dominant_kernel() == "cox_newton_kernel"
+
+
 def test_coxph_interaction_subset_dosage(engine):
     rng = np.random.default_rng(41)
     n_file, n, n_snps = 900, 800, 40
@@ -706,10 +761,10 @@ def test_baseline_configs_full_size_properties(engine, config):
         assert ((p >= 0) & (p <= 1)).all()
     p_snp = np.sort(res.param(len(names))[5])
     assert np.abs(p_snp - (np.arange(n_snps) + 0.5) / n_snps).max() < 0.02
-    # (logistic: calls of at least 4,096 markers run on the thread-per-SNP kernel, smaller
+    # (logistic / Cox: calls of at least 4,096 markers run on the thread-per-SNP kernels, smaller
     # ones on the warp-per-SNP kernel, which sums in another order: keep the sub-range on
     # the same kernel)
-    a, b = n_snps // 2 - 777, n_snps // 2 + (4321 if model == "logistic" else 1234)
+    a, b = n_snps // 2 - 777, n_snps // 2 + (4321 if model in ("logistic", "coxph") else 1234)
     out2, iout2 = engine.run_packed_dev(dev[a:b], b - a)
     sub = engine.fetch(out2, iout2)
     np.testing.assert_array_equal(sub.iout, res.iout[:, a:b])
