@@ -32,14 +32,14 @@ WORKLOADS = {
     "linear": dict(n=100000, k_cov=10, snps=500000, missing=0.01,
                    name="config2: linear GWAS 500k SNPs x 100k samples, 10 "
                         "covariates + intercept, 1% missing genotypes"),
-    # (66,304 markers = two waves of 148 CTAs x 224 markers of the thread-per-SNP IRLS kernel)
-    "logistic": dict(n=50000, k_cov=10, snps=66304, missing=0.0,
+    # (75,776 markers = two waves of 148 CTAs x 256 markers of the thread-per-SNP kernels)
+    "logistic": dict(n=50000, k_cov=10, snps=75776, missing=0.0,
                      name="config3: logistic GWAS 50k samples, 10 covariates "
                           "+ intercept (batched IRLS), SNP shard per step"),
     "linear_gxe": dict(n=100000, k_cov=10, snps=200000, missing=0.01,
                        name="config4: linear GWAS with a SNP x age interaction, "
                             "200k SNPs x 100k samples, 1% missing genotypes"),
-    "coxph": dict(n=20000, k_cov=10, snps=66304, missing=0.0,
+    "coxph": dict(n=20000, k_cov=10, snps=75776, missing=0.0,
                   name="config5: Cox PH (Efron) 20k samples, 10 covariates, "
                        "time/event phenotypes, SNP shard per step"),
 }

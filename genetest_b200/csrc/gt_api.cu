@@ -43,6 +43,7 @@ struct gt_engine {
     int cox_maxiter = 100;     // Newton step limit of the Cox model (statsmodels' default)
     bool use_thread_solve = true;  // thread-per-SNP solve for narrow designs without interaction
     bool use_thread_iter = true;   // thread-per-SNP IRLS for binary outcomes without interaction
+    int thread_fold = 1;           // thread kernels without a producer warp: 256 markers per CTA (option "thread_fold")
     int thread_iter_min = 4096;    // ... for batches of at least this many markers (fewer: warp per SNP)
     DevBuf dIterScratch, dIterT;
     int tc_dbg = 0;
@@ -465,6 +466,7 @@ int gt_engine_set_option(gt_engine *e, const char *name, int value) {
     if (std::strcmp(name, "stream_corrections") == 0) { e->use_stream_corr = value != 0; return 0; }
     if (std::strcmp(name, "thread_solve") == 0) { e->use_thread_solve = value != 0; return 0; }
     if (std::strcmp(name, "thread_iter") == 0) { e->use_thread_iter = value != 0; return 0; }
+    if (std::strcmp(name, "thread_fold") == 0) { e->thread_fold = value != 0; return 0; }
     if (std::strcmp(name, "thread_iter_min") == 0) { e->thread_iter_min = value > 0 ? value : 4096; return 0; }
     if (std::strcmp(name, "cox_maxiter") == 0) { e->cox_maxiter = value > 0 ? value : 100; return 0; }
     if (std::strcmp(name, "host_chunk") == 0) { e->host_chunk = (int)std::max<int64_t>(0, value); return 0; }
@@ -1173,7 +1175,7 @@ static int run_any(gt_engine *e, const void *geno, int64_t pitch, bool packed, i
     }
     return gtk::iter_run(T, e->model, geno, pitch, packed, n_snps, out, iout, ldo, e->stream,
                          (int *)e->dCounter.p, e->timing,
-                         (double *)e->dIterScratch.p, e->use_thread_iter, e->thread_iter_min,
+                         (double *)e->dIterScratch.p, e->use_thread_iter, e->thread_iter_min, e->thread_fold,
                          [&]() { return time_begin(e); }, [&](int s) { time_end(e, s); },
                          e->all_launches, g_err);
 }
@@ -1222,10 +1224,11 @@ static int run_host(gt_engine *e, const void *src, int64_t src_pitch_bytes, int6
         // pay a partial last wave per chunk: keep their chunks large
         chunk = std::max<int64_t>(chunk, e->model == GT_MODEL_LINEAR ? 8192 : 65536);
         // thread-per-SNP IRLS: whole waves of 148 CTAs x 224 markers
-        if (packed && e->use_thread_iter && chunk >= 148 * gtk::kLtMaxThreads &&
+        const int64_t tw = 148 * (int64_t)(e->thread_fold ? gtk::kLtFoldThreads : gtk::kLtMaxThreads);
+        if (packed && e->use_thread_iter && chunk >= tw &&
             ((e->model == GT_MODEL_LOGISTIC && e->T.I == 0 && e->T.p <= 13 && e->T.y_binary) ||
              (e->model == GT_MODEL_COXPH && e->T.th_ok)))
-            chunk = chunk / (148 * gtk::kLtMaxThreads) * (148 * gtk::kLtMaxThreads);
+            chunk = chunk / tw * tw;
         chunk = std::min<int64_t>(chunk, std::max<int64_t>(1024, ((int64_t)512 << 20) / dev_pitch_bytes / 1024 * 1024));
         // whole half-waves of the tcgen05 contraction (148 CTAs x 128 .. 512 SNP rows)
         if (packed && e->model == GT_MODEL_LINEAR && e->use_tc && e->tc_N > 0) {

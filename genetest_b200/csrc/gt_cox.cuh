@@ -225,18 +225,26 @@ static int launch_logistic(const IterDesignDev &T, const void *geno, int64_t pit
 template <int P>
 static int launch_logistic_thread(const IterDesignDev &T, const void *geno, int64_t pitch, int n_snps,
                                   double *out, int32_t *iout, long long ldo, cudaStream_t st,
-                                  double *scratch, long long lds, int maxpass) {
-    // markers per CTA: the batch spread over the 148 SMs (whole warps), at most kLtMaxThreads
-    const int waves = (n_snps + 148 * kLtMaxThreads - 1) / (148 * kLtMaxThreads);
+                                  double *scratch, long long lds, int maxpass, int fold) {
+    // markers per CTA: the batch spread over the 148 SMs (whole warps)
+    const int cap = fold ? kLtFoldThreads : kLtMaxThreads;
+    const int waves = (n_snps + 148 * cap - 1) / (148 * cap);
     int nthr = ((n_snps + 148 * waves - 1) / (148 * waves) + 31) / 32 * 32;
-    nthr = std::max(32, std::min(nthr, kLtMaxThreads));
+    nthr = std::max(32, std::min(nthr, cap));
     const int XSs = std::max(2, (P & ~1));                       // (K + 1) & ~1 with K = P - 1
     const size_t smem = 128 + (size_t)kLtBuf * (kLtBlk * XSs * 8 + kLtBlk * 8) + 128 +
                         (size_t)(((P - 1) * (P - 1) + 1) & ~1) * 8 + (size_t)P * nthr * 8;
-    CK(cudaFuncSetAttribute((const void *)logistic_thread_kernel<P>,
-                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    logistic_thread_kernel<P><<<(n_snps + nthr - 1) / nthr, nthr + 32, smem, st>>>(
-        T, (const uint8_t *)geno, pitch, n_snps, out, iout, ldo, scratch, lds, maxpass);
+    if (fold) {
+        CK(cudaFuncSetAttribute((const void *)logistic_thread_kernel<P, 1>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        logistic_thread_kernel<P, 1><<<(n_snps + nthr - 1) / nthr, nthr, smem, st>>>(
+            T, (const uint8_t *)geno, pitch, n_snps, out, iout, ldo, scratch, lds, maxpass);
+    } else {
+        CK(cudaFuncSetAttribute((const void *)logistic_thread_kernel<P, 0>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        logistic_thread_kernel<P, 0><<<(n_snps + nthr - 1) / nthr, nthr + 32, smem, st>>>(
+            T, (const uint8_t *)geno, pitch, n_snps, out, iout, ldo, scratch, lds, maxpass);
+    }
     CK(cudaGetLastError());
     return 0;
 }
@@ -265,24 +273,32 @@ static int launch_cox(const IterDesignDev &T, const void *geno, int64_t pitch, i
 template <int P>
 static int launch_cox_thread(const IterDesignDev &T, const void *geno, int64_t pitch, int n_snps,
                              double *out, int32_t *iout, long long ldo, cudaStream_t st,
-                             uint32_t *gperm, long long ldw, int maxround) {
-    const int waves = (n_snps + 148 * kLtMaxThreads - 1) / (148 * kLtMaxThreads);
+                             uint32_t *gperm, long long ldw, int maxround, int fold) {
+    const int cap = fold ? kLtFoldThreads : kLtMaxThreads;
+    const int waves = (n_snps + 148 * cap - 1) / (148 * cap);
     int nthr = ((n_snps + 148 * waves - 1) / (148 * waves) + 31) / 32 * 32;
-    nthr = std::max(32, std::min(nthr, kLtMaxThreads));
+    nthr = std::max(32, std::min(nthr, cap));
     const int XST = (P + 1) & ~1;                               // (K + 2) & ~1 with K = P - 1
     const size_t smem = 128 + (size_t)kLtBuf * (kLtBlk * XST * 8) + 128 +
                         (size_t)((((P - 1) * (P - 1) + 1) & ~1) + ((P + 1) & ~1)) * 8 + (size_t)P * nthr * 8;
-    CK(cudaFuncSetAttribute((const void *)cox_thread_kernel<P>,
-                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cox_thread_kernel<P><<<(n_snps + nthr - 1) / nthr, nthr + 32, smem, st>>>(
-        T, (const uint8_t *)geno, pitch, n_snps, out, iout, ldo, gperm, ldw, maxround);
+    if (fold) {
+        CK(cudaFuncSetAttribute((const void *)cox_thread_kernel<P, 1>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cox_thread_kernel<P, 1><<<(n_snps + nthr - 1) / nthr, nthr, smem, st>>>(
+            T, (const uint8_t *)geno, pitch, n_snps, out, iout, ldo, gperm, ldw, maxround);
+    } else {
+        CK(cudaFuncSetAttribute((const void *)cox_thread_kernel<P, 0>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cox_thread_kernel<P, 0><<<(n_snps + nthr - 1) / nthr, nthr + 32, smem, st>>>(
+            T, (const uint8_t *)geno, pitch, n_snps, out, iout, ldo, gperm, ldw, maxround);
+    }
     CK(cudaGetLastError());
     return 0;
 }
 
 static int iter_run(const IterDesignDev &T, int model, const void *geno, int64_t pitch, bool packed,
                     int32_t n_snps, double *out, int32_t *iout, long long ldo, cudaStream_t st, int *counter, bool timing,
-                    double *lt_scratch, bool use_thread, int thread_min,
+                    double *lt_scratch, bool use_thread, int thread_min, int thread_fold,
                     const std::function<int()> &tbegin, const std::function<void(int)> &tend,
                     int64_t &all_launches, std::string &err) {
     (void)timing; (void)err;
@@ -297,7 +313,7 @@ static int iter_run(const IterDesignDev &T, int model, const void *geno, int64_t
             if (use_thread && lt_scratch && T.th_ok && T.p >= 2 && T.p <= 12 && n_snps >= thread_min) {
                 const long long ldw = (n_snps + 31) / 32 * 32;
                 rc = 0;
-#define GT_CT(PP) case PP: rc = launch_cox_thread<PP>(T, geno, pitch, n_snps, out, iout, ldo, st, (uint32_t *)lt_scratch, ldw, 8); break;
+#define GT_CT(PP) case PP: rc = launch_cox_thread<PP>(T, geno, pitch, n_snps, out, iout, ldo, st, (uint32_t *)lt_scratch, ldw, 8, thread_fold); break;
                 switch (T.p) {
                     GT_CT(2) GT_CT(3) GT_CT(4) GT_CT(5) GT_CT(6) GT_CT(7) GT_CT(8) GT_CT(9) GT_CT(10)
                     GT_CT(11) GT_CT(12)
@@ -324,7 +340,7 @@ static int iter_run(const IterDesignDev &T, int model, const void *geno, int64_t
             n_snps >= thread_min) {
             const long long lds = (n_snps + 31) / 32 * 32;
             const int maxpass = 9;
-#define GT_LT(PP) case PP: rc = launch_logistic_thread<PP>(T, geno, pitch, n_snps, out, iout, ldo, st, lt_scratch, lds, maxpass); break;
+#define GT_LT(PP) case PP: rc = launch_logistic_thread<PP>(T, geno, pitch, n_snps, out, iout, ldo, st, lt_scratch, lds, maxpass, thread_fold); break;
             switch (T.p) {
                 GT_LT(2) GT_LT(3) GT_LT(4) GT_LT(5) GT_LT(6) GT_LT(7) GT_LT(8) GT_LT(9) GT_LT(10)
                 GT_LT(11) GT_LT(12) GT_LT(13)

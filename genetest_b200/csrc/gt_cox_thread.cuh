@@ -39,8 +39,9 @@
 
 namespace gtk {
 
-template <int P>
-__global__ void __launch_bounds__(kLtMaxThreads + 32, 1)
+// FOLD = 1: warp 0 issues the bulk copies itself (see logistic_thread_kernel), 256 markers per CTA
+template <int P, int FOLD = 0>
+__global__ void __launch_bounds__(256, 1)
 cox_thread_kernel(IterDesignDev T, const uint8_t *__restrict__ geno, long long pitch, int n_snps,
                   double *__restrict__ out, int *__restrict__ iout, long long ostride,
                   uint32_t *__restrict__ gperm /* [th_n / 16][ldw] codes in schedule order */, long long ldw,
@@ -60,7 +61,7 @@ cox_thread_kernel(IterDesignDev T, const uint8_t *__restrict__ geno, long long p
     double *sCmax = sRinv + ((K * K + 1) & ~1);                    // [P] max |x| per column
     double *sBeta = sCmax + ((P + 1) & ~1);                        // [P][nthr]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int nthr = blockDim.x - 32;
+    const int nthr = blockDim.x - (FOLD ? 0 : 32);
     const int ncw = nthr >> 5;
     if (tid == 0) {
         for (int s = 0; s < kLtBuf; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], ncw); }
@@ -72,7 +73,7 @@ cox_thread_kernel(IterDesignDev T, const uint8_t *__restrict__ geno, long long p
     __syncthreads();
     const int nblk = T.th_n / kLtBlk;
 
-    if (warp == ncw) {
+    if (!FOLD && warp == ncw) {
         // ===== producer: the design rows, twice per round, while any marker of the CTA is active =====
         int it = 0;
         for (int round = 0; round < maxround; ++round) {
@@ -152,7 +153,7 @@ cox_thread_kernel(IterDesignDev T, const uint8_t *__restrict__ geno, long long p
     // at most sum_a |step_a| max |x_a| per step); past a drift of 20 the marker is deferred
     double emax = 0.0, slack = 0.0, llf = 0.0;
     bool final_eval = false;
-    int it = 0;
+    int it = 0, issued = 0;
 #define GT_H(a, b) H[(a) * P - (a) * ((a) - 1) / 2 + ((b) - (a))]      /* a <= b */
 #define GT_L(i, j) GT_H(j, i)                                           /* i >= j */
     for (int round = 0; round < maxround; ++round) {
@@ -162,6 +163,24 @@ cox_thread_kernel(IterDesignDev T, const uint8_t *__restrict__ geno, long long p
             double S0 = 0.0;
             for (int b = 0; b < nblk; ++b, ++it) {
                 const int st = it % kLtBuf;
+            if (FOLD && warp == 0) {
+                // copies of this round up to kLtBuf - 1 blocks ahead (never across its end)
+                const int lim = min(it + kLtBuf - 1, (round + 1) * 2 * nblk - 1);
+                for (; issued <= lim; ++issued) {
+                    const int s2 = issued % kLtBuf;
+                    if (issued >= kLtBuf) {
+                        const uint32_t ea = smem_u32(&empty[s2]), ep = ((issued / kLtBuf) & 1) ^ 1;
+                        int spin = 0;
+                        while (!mbar_try(ea, ep)) if (++spin > (1 << 22)) { *fail = 1; break; }
+                    }
+                    if (elect_one()) {
+                        mbar_expect_tx(&full[s2], XBLK);
+                        bulk_g2s((unsigned char *)sX + s2 * XBLK,
+                                 (const unsigned char *)T.th_X + (long long)(issued % nblk) * XBLK, XBLK, &full[s2]);
+                    }
+                    __syncwarp();
+                }
+            }
                 {
                     const uint32_t fa = smem_u32(&full[st]), fp = (it / kLtBuf) & 1;
                     int spin = 0;
@@ -202,6 +221,24 @@ cox_thread_kernel(IterDesignDev T, const uint8_t *__restrict__ geno, long long p
         double S0 = 0.0, PI = 0.0, ll = 0.0;
         for (int b = 0; b < nblk; ++b, ++it) {
             const int st = it % kLtBuf;
+            if (FOLD && warp == 0) {
+                // copies of this round up to kLtBuf - 1 blocks ahead (never across its end)
+                const int lim = min(it + kLtBuf - 1, (round + 1) * 2 * nblk - 1);
+                for (; issued <= lim; ++issued) {
+                    const int s2 = issued % kLtBuf;
+                    if (issued >= kLtBuf) {
+                        const uint32_t ea = smem_u32(&empty[s2]), ep = ((issued / kLtBuf) & 1) ^ 1;
+                        int spin = 0;
+                        while (!mbar_try(ea, ep)) if (++spin > (1 << 22)) { *fail = 1; break; }
+                    }
+                    if (elect_one()) {
+                        mbar_expect_tx(&full[s2], XBLK);
+                        bulk_g2s((unsigned char *)sX + s2 * XBLK,
+                                 (const unsigned char *)T.th_X + (long long)(issued % nblk) * XBLK, XBLK, &full[s2]);
+                    }
+                    __syncwarp();
+                }
+            }
             {
                 const uint32_t fa = smem_u32(&full[st]), fp = (it / kLtBuf) & 1;
                 int spin = 0;

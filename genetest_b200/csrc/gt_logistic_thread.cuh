@@ -38,7 +38,8 @@ namespace gtk {
 constexpr int GT_ITER_DEFER = -77;      // internal: finish this marker in the warp-per-SNP kernel
 constexpr int kLtBlk = 256;             // samples per shared-memory block
 constexpr int kLtBuf = 4;               // blocks in the ring
-constexpr int kLtMaxThreads = 224;      // markers per CTA (+ the producer warp)
+constexpr int kLtMaxThreads = 224;      // markers per CTA with a producer warp of its own
+constexpr int kLtFoldThreads = 256;     // ... with the copies issued by warp 0 (FOLD): 8 x 32 x 255 registers
 
 
 // ---------------------------------------------------------------------------
@@ -128,8 +129,10 @@ GT_HD double lt_log1p01(double t, double &inv) {   // log(1 + t) and inv = 1 / (
     return big ? lm + GT_LTC(27) : lm;
 }
 
-template <int P>
-__global__ void __launch_bounds__(kLtMaxThreads + 32, 1)
+// FOLD = 1: no producer warp -- warp 0 issues the bulk copies between its own blocks (one block
+// of lookahead less than the ring holds), which makes room for an eighth warp of markers.
+template <int P, int FOLD = 0>
+__global__ void __launch_bounds__(256, 1)
 logistic_thread_kernel(IterDesignDev T, const uint8_t *__restrict__ geno, long long pitch, int n_snps,
                        double *__restrict__ out, int *__restrict__ iout, long long ostride,
                        double *__restrict__ scratch /* [2 P][lds] coef, se of the last solve */, long long lds,
@@ -151,7 +154,7 @@ logistic_thread_kernel(IterDesignDev T, const uint8_t *__restrict__ geno, long l
     double *sRinv = (double *)(full + 16);                         // [K * K]
     double *sBeta = sRinv + ((K * K + 1) & ~1);                    // [P][nthr]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int nthr = blockDim.x - 32;                              // compute threads
+    const int nthr = blockDim.x - (FOLD ? 0 : 32);                 // compute threads
     const int ncw = nthr >> 5;
     if (tid == 0) {
         for (int s = 0; s < kLtBuf; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], ncw); }
@@ -162,7 +165,7 @@ logistic_thread_kernel(IterDesignDev T, const uint8_t *__restrict__ geno, long l
     __syncthreads();
     const int nblk = (T.n_file + kLtBlk - 1) / kLtBlk;
 
-    if (warp == ncw) {
+    if (!FOLD && warp == ncw) {
         // ===== producer: the design rows of one pass after the other, while any marker of the CTA is active =====
         int it = 0;
         for (int pass = 0; pass < maxpass; ++pass) {
@@ -253,6 +256,7 @@ logistic_thread_kernel(IterDesignDev T, const uint8_t *__restrict__ geno, long l
     for (int a = 0; a < P; ++a) myBeta[a * nthr] = 0.0;
     double dev_prev = 0.0, llf = 0.0;
     int it = 0;                                             // blocks consumed (ring position)
+    int issued = 0;                                         // FOLD, warp 0: blocks whose copies are issued
 #define GT_H(a, b) H[(a) * P - (a) * ((a) - 1) / 2 + ((b) - (a))]      /* a <= b */
     for (int pass = 0; pass < maxpass; ++pass) {
         double H[NH], r[P];
@@ -268,6 +272,26 @@ logistic_thread_kernel(IterDesignDev T, const uint8_t *__restrict__ geno, long l
         uint32_t wnext = word_at(0);
         for (int b = 0; b < nblk; ++b, ++it) {
             const int st = it % kLtBuf;
+            if (FOLD && warp == 0) {
+                // copies of this pass up to kLtBuf - 1 blocks ahead (never across the end of the
+                // pass: whether another one follows is only known after it)
+                const int lim = min(it + kLtBuf - 1, (pass + 1) * nblk - 1);
+                for (; issued <= lim; ++issued) {
+                    const int s2 = issued % kLtBuf;
+                    if (issued >= kLtBuf) {
+                        const uint32_t ea = smem_u32(&empty[s2]), ep = ((issued / kLtBuf) & 1) ^ 1;
+                        int spin = 0;
+                        while (!mbar_try(ea, ep)) if (++spin > (1 << 22)) { *fail = 1; break; }
+                    }
+                    if (elect_one()) {
+                        const int bb = issued - pass * nblk;
+                        mbar_expect_tx(&full[s2], XBLK + YBLK);
+                        bulk_g2s((unsigned char *)sX + s2 * XBLK, (const unsigned char *)T.X + (long long)bb * XBLK, XBLK, &full[s2]);
+                        bulk_g2s((unsigned char *)sY + s2 * YBLK, (const unsigned char *)T.y + (long long)bb * YBLK, YBLK, &full[s2]);
+                    }
+                    __syncwarp();
+                }
+            }
             {   // inline wait (a call in this loop would spill the accumulators around it)
                 const uint32_t fa = smem_u32(&full[st]), fp = (it / kLtBuf) & 1;
                 int spin = 0;

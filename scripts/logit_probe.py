@@ -5,6 +5,8 @@ import numpy as np, torch
 from genetest_b200.engine import Engine
 import bench
 eng = Engine(0)
+import os
+eng.set_option("thread_fold", int(os.environ.get("GT_FOLD", "1")))
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 50000
 snps = int(sys.argv[1]) if len(sys.argv) > 1 else 33152
 miss = float(sys.argv[3]) if len(sys.argv) > 3 else 0.0
