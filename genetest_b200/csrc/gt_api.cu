@@ -988,14 +988,22 @@ static int launch_finish(gt_engine *e, const void *g, int64_t pitch, int nb, dou
         // thread-per-SNP streaming corrections (gt_corr_stream.cuh)
         gtk::CorrStreamParams C = e->cs;
         C.n_snps = nb; C.mrec = ml; C.mcount = mc; C.corrT = corr; C.ldc = ldc; C.counts = cnt;
-        const int sm = gtk::kCsBuf * gtk::kCsBlk * gtk::kCsRow * 8 + (gtk::kCsRecRing / 2) * gtk::kCsSnps * 16 + 256;
-        const int cgrid = (nb + gtk::kCsSnps - 1) / gtk::kCsSnps;
+        const int fold = e->thread_fold;
+        const int csn = fold ? gtk::kCsFoldSnps : gtk::kCsSnps;
+        const int sm = gtk::kCsBuf * gtk::kCsBlk * gtk::kCsRow * 8 + (gtk::kCsRecRing / 2) * csn * 16 + 256;
+        const int cgrid = (nb + csn - 1) / csn;
         int cslot = time_begin(e, 1);
 #define GT_CS(N)                                                                              \
     case N:                                                                                   \
-        CK(cudaFuncSetAttribute((const void *)gtk::missing_corr_stream_kernel<N>,             \
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, sm));            \
-        gtk::missing_corr_stream_kernel<N><<<cgrid, gtk::kCsThreads, sm, e->stream>>>(C);     \
+        if (fold) {                                                                           \
+            CK(cudaFuncSetAttribute((const void *)gtk::missing_corr_stream_kernel<N, 1>,      \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, sm));        \
+            gtk::missing_corr_stream_kernel<N, 1><<<cgrid, csn, sm, e->stream>>>(C);          \
+        } else {                                                                              \
+            CK(cudaFuncSetAttribute((const void *)gtk::missing_corr_stream_kernel<N, 0>,      \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, sm));        \
+            gtk::missing_corr_stream_kernel<N, 0><<<cgrid, csn + 32, sm, e->stream>>>(C);     \
+        }                                                                                     \
         break;
         switch (e->cs_nv) {
             GT_CS(1) GT_CS(2) GT_CS(3) GT_CS(4) GT_CS(5) GT_CS(6) GT_CS(7) GT_CS(8) GT_CS(9) GT_CS(10)

@@ -42,6 +42,7 @@ constexpr int kCsRow = 12;              // doubles per row (96 bytes)
 constexpr int kCsRecRing = 16;          // records of a thread's prefetch ring (8 cp.async of 16 B)
 constexpr int kCsSnps = 224;            // markers (threads) per CTA: 7 warps + the producer warp = 256 threads, 255 registers each
 constexpr int kCsThreads = kCsSnps + 32;
+constexpr int kCsFoldSnps = 256;        // FOLD: warp 0 issues the block copies itself, 8 warps of markers
 
 struct CorrStreamParams {
     const double *Ec;         // [n_blocks * kCsBlk][12] design rows (streamed columns only), file order
@@ -64,21 +65,22 @@ struct CorrStreamParams {
 
 __device__ __forceinline__ int cs_tri(int a, int b, int L) { return a * L - a * (a - 1) / 2 + (b - a); }
 
-template <int NV>
-__global__ void __launch_bounds__(kCsThreads, 1)
+template <int NV, int FOLD = 0>
+__global__ void __launch_bounds__(256, 1)
 missing_corr_stream_kernel(const CorrStreamParams P) {
+    constexpr int kSnps = FOLD ? kCsFoldSnps : kCsSnps;
     constexpr int NP = NV * (NV + 1) / 2;
     constexpr int BLKB = kCsBlk * kCsRow * 8;               // bytes of one block
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned char *smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
     unsigned char *sE = smem;                                // kCsBuf blocks
-    unsigned char *sR = smem + kCsBuf * BLKB;                     // [8 pair slots][kCsSnps] x 16 B: record rings
-    uint64_t *full = (uint64_t *)(sR + (kCsRecRing / 2) * kCsSnps * 16), *empty = full + kCsBuf;
+    unsigned char *sR = smem + kCsBuf * BLKB;                     // [8 pair slots][kSnps] x 16 B: record rings
+    uint64_t *full = (uint64_t *)(sR + (kCsRecRing / 2) * kSnps * 16), *empty = full + kCsBuf;
     int *fail = (int *)(empty + kCsBuf);
     double *sZ = (double *)(full + 16);                       // a row of zeros (128-byte aligned: chunk ^ 1 stays inside)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
-        for (int s = 0; s < kCsBuf; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kCsSnps / 32); }
+        for (int s = 0; s < kCsBuf; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kSnps / 32); }
         *fail = 0;
         for (int c = 0; c < 16; ++c) sZ[c] = 0.0;
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -86,7 +88,7 @@ missing_corr_stream_kernel(const CorrStreamParams P) {
     __syncthreads();
     const int nblk = P.n_blocks;
 
-    if (warp == kCsSnps / 32) {
+    if (!FOLD && warp == kSnps / 32) {
         // ===== producer: one bulk copy per block =====
         for (int b = 0; b < nblk; ++b) {
             const int s = b % kCsBuf;
@@ -99,7 +101,7 @@ missing_corr_stream_kernel(const CorrStreamParams P) {
         }
     } else {
         // ===== one thread per marker =====
-        const int snp = blockIdx.x * kCsSnps + tid;
+        const int snp = blockIdx.x * kSnps + tid;
         const bool owner = snp < P.n_snps;
         const int nrec = owner ? P.mcount[snp] : 0;
         const uint2 *recs = P.mrec + (long long)(owner ? snp : 0) * P.rcap;
@@ -114,13 +116,13 @@ missing_corr_stream_kernel(const CorrStreamParams P) {
         const uint32_t ring = smem_u32(sR) + tid * 16;
         auto fetch = [&](int q) {            // records 2 q, 2 q + 1 -> slot q & 7 (reads past the list are unused)
             asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n"
-                         ::"r"(ring + (uint32_t)(q & 7) * (kCsSnps * 16)), "l"(recs + 2 * q) : "memory");
+                         ::"r"(ring + (uint32_t)(q & 7) * (kSnps * 16)), "l"(recs + 2 * q) : "memory");
             asm volatile("cp.async.commit_group;\n" ::: "memory");
         };
         auto rec_at = [&](int r) {           // record r from the ring
             uint2 v;
             asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];\n" : "=r"(v.x), "=r"(v.y)
-                         : "r"(ring + (uint32_t)((r >> 1) & 7) * (kCsSnps * 16) + (uint32_t)(r & 1) * 8));
+                         : "r"(ring + (uint32_t)((r >> 1) & 7) * (kSnps * 16) + (uint32_t)(r & 1) * 8));
             return v;
         };
         // invariant: with record pair q current, pairs up to q + 6 are requested, so that
@@ -182,7 +184,7 @@ missing_corr_stream_kernel(const CorrStreamParams P) {
                 "setp.ne.u32 p, %0, 0;\n\t"
                 "@p cp.async.ca.shared.global [%1], [%2], 16;\n\t"
                 "@p cp.async.commit_group;\n\t}\n"
-                ::"r"((uint32_t)(adv && !(ri & 1))), "r"(ring + (q & 7u) * (kCsSnps * 16)), "l"(recs + 2 * q)
+                ::"r"((uint32_t)(adv && !(ri & 1))), "r"(ring + (q & 7u) * (kSnps * 16)), "l"(recs + 2 * q)
                 : "memory");
         };
         auto accumulate = [&](const double (&v)[12]) {
@@ -195,7 +197,31 @@ missing_corr_stream_kernel(const CorrStreamParams P) {
             }
         };
         int landed = -1;                 // blocks 0 .. landed are known to be in the ring
+        int issued = 0;                  // FOLD, warp 0: blocks whose copies are issued
+        // FOLD: block `issued` reuses the slot of block issued - kCsBuf, which every warp must have
+        // released; only the block this warp needs next is waited for, the lookahead is opportunistic
+        auto try_issue = [&](int b) {
+            while (issued < nblk && issued < b + kCsBuf) {
+                if (issued >= kCsBuf) {
+                    const uint32_t ea = smem_u32(&empty[issued % kCsBuf]);
+                    const uint32_t ep = ((issued / kCsBuf) & 1) ^ 1;
+                    if (!mbar_test(ea, ep)) {
+                        if (issued > b) break;
+                        int spin = 0;
+                        while (!mbar_try(ea, ep)) if (++spin > (1 << 22)) { *fail = 1; break; }
+                    }
+                }
+                if (elect_one()) {
+                    mbar_expect_tx(&full[issued % kCsBuf], BLKB);
+                    bulk_g2s(sE + (issued % kCsBuf) * BLKB, (const unsigned char *)P.Ec + (long long)issued * BLKB,
+                             BLKB, &full[issued % kCsBuf]);
+                }
+                __syncwarp();
+                ++issued;
+            }
+        };
         for (int b = 0; b < nblk; ++b) {
+            if (FOLD && warp == 0) try_issue(b);
             if (landed < b) {
                 if (!mbar_wait2(&full[b % kCsBuf], (b / kCsBuf) & 1, fail)) *fail = 1;
                 landed = b;
@@ -207,6 +233,7 @@ missing_corr_stream_kernel(const CorrStreamParams P) {
             while (__any_sync(GT_FULL, pair < end_b || pairA < end_b)) {
                 // a lane that is done with block b runs ahead into the other blocks of the ring once they have landed
                 if (polled) { ++landed; limit += ppb; polled = false; }
+                if (FOLD && warp == 0 && issued < nblk && issued < b + kCsBuf) try_issue(b);
                 load_next(vB, pairB);
                 accumulate(vA);
                 advance();
