@@ -1062,6 +1062,22 @@ static int launch_finish(gt_engine *e, const void *g, int64_t pitch, int nb, dou
             CK(cudaGetLastError());
             deferred_only = 1;
             e->all_launches += 1;
+        } else if (!D.lean && D.I == 1 && D.p >= 3 && D.p <= 13 && e->use_thread_solve) {
+            // one interaction column: the same kernel with the rows g and g w
+            const int tgrid = (nb + 127) / 128;
+#define GT_ST1(PP)                                                                                  \
+    case PP:                                                                                        \
+        gtk::linear_solve_thread_kernel<PP, 1><<<tgrid, 128, 0, e->stream>>>(D, nb, S, cnt, gs, corr, \
+                                                                             ldc, out, iout, stride); \
+        break;
+            switch (D.p) {
+                GT_ST1(3) GT_ST1(4) GT_ST1(5) GT_ST1(6) GT_ST1(7) GT_ST1(8) GT_ST1(9) GT_ST1(10)
+                GT_ST1(11) GT_ST1(12) GT_ST1(13)
+            }
+#undef GT_ST1
+            CK(cudaGetLastError());
+            deferred_only = 1;
+            e->all_launches += 1;
         }
         if (half) {
             CK(cudaFuncSetAttribute((const void *)gtk::linear_solve_kernel<16>,

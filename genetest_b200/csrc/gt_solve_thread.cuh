@@ -19,15 +19,16 @@ namespace gtk {
 
 constexpr int GT_SOLVE_DEFER = -77;     // internal: finish this marker in linear_solve_kernel
 
-template <int P>
+// NI = 1: one SNP x covariate interaction column (design [Q | g | g w], analysis.py:159-166)
+template <int P, int NI = 0>
 __global__ void __launch_bounds__(128)
 linear_solve_thread_kernel(GtDesignDev D, int n_snps, const double *__restrict__ S,
                            const int *__restrict__ counts, const double *__restrict__ gsum,
                            const double *__restrict__ corrT, long long ldc,
                            double *__restrict__ out, int *__restrict__ iout, long long ostride) {
-    constexpr int K = P - 1;             // covariates (orthonormal basis q)
-    constexpr int L = K + 2;             // base vector [q | y | 1]
-    constexpr int IY = K, I1 = K + 1;
+    constexpr int K = P - 1 - NI;        // covariates (orthonormal basis q)
+    constexpr int L = K + 2 + NI;        // base vector [q | y | 1 | w]
+    constexpr int IY = K, I1 = K + 1, IW = K + 2;
     __shared__ double sFF0[L * L];
     __shared__ double sRinv[K * K + 1];
     for (int t = threadIdx.x; t < L * L; t += blockDim.x) sFF0[t] = D.FF0[t];
@@ -80,7 +81,7 @@ linear_solve_thread_kernel(GtDesignDev D, int n_snps, const double *__restrict__
     }
     const double yy = s0(IY, IY), sy = s0(IY, I1);
     const double *Ssnp = S + (long long)snp * D.NCP;
-    {
+    if constexpr (NI == 0) {
         // g column: g'q (K), g'y, g'1 = sum g, g'g
         double s1y = Ssnp[K], gg = sum_g2_all;
         if (flip) {      // g -> 2 - g on the complete cases (analysis.py:156-157)
@@ -97,8 +98,31 @@ linear_solve_thread_kernel(GtDesignDev D, int n_snps, const double *__restrict__
         }
         GT_A(K, K) = gg;
         vec[K] = s1y;
+    } else {
+        // rows g and g w: S1[c][b] = sum g m_c v_b (S columns c L + b), S2 = sum g^2 m_a m_b
+        // (S columns NCA + {00, 01, 11}); m_0 = 1 (column I1 of v), m_1 = w (column IW)
+        double s2_00 = Ssnp[D.NCA], s2_01 = Ssnp[D.NCA + 1], s2_11 = Ssnp[D.NCA + 2];
+        bool all_zero = false;
+        if (flip) {
+            const double f00 = 4.0 * s0(I1, I1) - 4.0 * Ssnp[I1] + s2_00;
+            const double f01 = 4.0 * s0(I1, IW) - 4.0 * Ssnp[IW] + s2_01;
+            const double f11 = 4.0 * s0(IW, IW) - 4.0 * Ssnp[L + IW] + s2_11;
+            all_zero = f00 == 0.0;
+            s2_00 = all_zero ? 0.0 : f00; s2_01 = all_zero ? 0.0 : f01; s2_11 = all_zero ? 0.0 : f11;
+        }
+        auto s1 = [&](int c, int b) -> double {       // after the flip
+            const double raw = Ssnp[c * L + b];
+            if (!flip) return raw;
+            const int cc = c == 0 ? I1 : IW;
+            const double full = cc <= b ? s0(cc, b) : s0(b, cc);
+            return all_zero ? 0.0 : 2.0 * full - raw;
+        };
+#pragma unroll
+        for (int j = 0; j < K; ++j) { GT_A(K, j) = s1(0, j); GT_A(K + 1, j) = s1(1, j); }
+        GT_A(K, K) = s2_00; GT_A(K + 1, K) = s2_01; GT_A(K + 1, K + 1) = s2_11;
+        vec[K] = s1(0, IY); vec[K + 1] = s1(1, IY);
     }
-    const double gdiag = GT_A(K, K);
+    const double gdiag = NI == 0 ? GT_A(K, K) : GT_A(K, K) + GT_A(K + 1, K + 1);
     // ---- Cholesky A = Lc Lc' (in place) ----
     bool ok = !D.degenerate;
 #pragma unroll
