@@ -320,7 +320,7 @@ int64_t gt_format_rows(int32_t n_rows, int32_t n_cols, const int32_t *col_type,
     if (n_rows <= 0) return 0;
     // Row ranges are formatted by a few host threads, each into its own
     // worst-case slice of `out`; the slices are then closed up in order.
-    int nt = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 8u);
+    int nt = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
     nt = std::max(1, std::min(nt, n_rows / 4096));
     int64_t fixed = 2;                              // worst-case bytes of a row without its strings
     for (int c = 0; c < n_cols; ++c) {
