@@ -147,33 +147,76 @@ static int iter_set_design(const gt_design_desc *d, const std::vector<int> &pos,
         X = host.data(); y = X + n_pad * XSs; Rinv = y + n_pad;
         T.n_slots = (int)ns;
         // ---- schedule of the thread-per-SNP kernel (gt_cox_thread.cuh): the design rows in
-        //      descending time, censored samples of a time point before its event, no padding
-        //      inside; only without strata, interactions and tied events ----
+        //      descending time, stratum by stratum (each padded to whole 256-row blocks), the
+        //      censored samples of a time point before its events; per row the event flag, the
+        //      position inside a group of tied events and the size of that group ----
         T.th_ok = 0;
-        bool tied = !big_first.empty();
-        for (size_t t = 0; t < ns && !tied; ++t)
-            tied = (slot_info[t] & 31) != ((slot_info[t] >> 5) & 31);
-        if (!strata && !tied && I == 0 && !H.degenerate && p >= 2 && p <= 12) {
-            const int XST = (k + 2) & ~1;                 // q (k) | event flag, rounded up to even
-            const size_t nT = ((size_t)n + 255) / 256 * 256;
-            std::vector<double> ht(nT * XST + nT / 2 + 2, 0.0);
-            int *tp = (int *)&ht[nT * XST];
-            for (size_t t = 0; t < nT; ++t) tp[t] = -1;
-            size_t w = 0;
-            for (size_t t = 0; t < ns; ++t) {
-                if (slot_pos[t] < 0) continue;
-                const int row = row_of_pos[slot_pos[t]];
-                for (int j = 0; j < k; ++j) ht[w * XST + j] = H.Q[(size_t)j * n + row];
-                ht[w * XST + k] = (double)((slot_info[t] >> 10) & 1);
-                tp[w] = slot_pos[t];
-                ++w;
+        if (I == 0 && !H.degenerate && p >= 2 && p <= 12) {
+            const int XST = (k + 3) & ~1;                 // q (k) | flags | group size
+            std::vector<double> rowsT;
+            std::vector<int> posT, segblk;
+            auto push_row = [&](int row, int flags, int dsz) {
+                const size_t base = rowsT.size();
+                rowsT.resize(base + XST, 0.0);
+                for (int j = 0; j < k; ++j) rowsT[base + j] = H.Q[(size_t)j * n + row];
+                rowsT[base + k] = (double)flags;
+                rowsT[base + k + 1] = (double)dsz;
+                posT.push_back(pos[row]);
+            };
+            auto pad256 = [&]() {
+                while (posT.size() % 256) { posT.push_back(-1); rowsT.resize(rowsT.size() + XST, 0.0); }
+            };
+            bool any_tied = false;
+            int j0 = 0;
+            segblk.push_back(0);
+            while (j0 < n) {
+                if (strata && j0 > 0 && strata[order[j0]] != strata[order[j0 - 1]]) {
+                    pad256();
+                    segblk.push_back((int)(posT.size() / 256));
+                }
+                int j1 = j0;
+                while (j1 + 1 < n && d->y[order[j1 + 1]] == d->y[order[j0]] &&
+                       (!strata || strata[order[j1 + 1]] == strata[order[j0]])) ++j1;
+                int m = 0;
+                for (int t = j0; t <= j1; ++t) {
+                    if (d->event[order[t]] != 0.0) ++m;
+                    else push_row(order[t], 0, 0);
+                }
+                int idx = 0;
+                for (int t = j0; t <= j1; ++t) {
+                    if (d->event[order[t]] == 0.0) continue;
+                    // 1 event, 2 member of a group of tied events, 4 first / 8 last member
+                    const int fl = 1 | (m >= 2 ? 2 : 0) | (m >= 2 && idx == 0 ? 4 : 0) | (m >= 2 && idx == m - 1 ? 8 : 0);
+                    push_row(order[t], fl, m);
+                    ++idx;
+                }
+                any_tied |= m >= 2;
+                j0 = j1 + 1;
             }
+            pad256();
+            segblk.push_back((int)(posT.size() / 256));
+            const size_t nT = posT.size();
+            const int nblkT = (int)(nT / 256), nsegT = (int)segblk.size() - 1;
+            std::vector<int> ordT;                          // blocks in the order a round consumes them
+            for (int sg = 0; sg < nsegT; ++sg)
+                for (int rep = 0; rep < 2; ++rep)
+                    for (int bb = segblk[sg]; bb < segblk[sg + 1]; ++bb) ordT.push_back(bb);
+            const size_t ints = nT + ordT.size() + segblk.size();
+            std::vector<double> ht(nT * XST + (ints + 1) / 2 + 2, 0.0);
+            std::memcpy(ht.data(), rowsT.data(), nT * XST * 8);
+            int *tp = (int *)&ht[nT * XST];
+            std::memcpy(tp, posT.data(), nT * 4);
+            std::memcpy(tp + nT, ordT.data(), ordT.size() * 4);
+            std::memcpy(tp + nT + ordT.size(), segblk.data(), segblk.size() * 4);
             int rct = upload(bufT, ht.data(), ht.size() * 8, st);
             if (rct) return rct;
             CK(cudaStreamSynchronize(st));
-            T.th_ok = 1; T.th_n = (int)nT; T.th_XS = XST;
+            T.th_ok = 1; T.th_n = (int)nT; T.th_XS = XST; T.th_tied = any_tied ? 1 : 0; T.th_nseg = nsegT;
             T.th_X = (const double *)bufT.p;
             T.th_pos = (const int *)((const double *)bufT.p + nT * XST);
+            T.th_order = T.th_pos + nT;
+            T.th_seg = T.th_order + ordT.size();
+            (void)nblkT;
         }
     }
     int rc = upload(buf, host.data(), host.size() * 8, st);
@@ -269,27 +312,28 @@ static int launch_cox(const IterDesignDev &T, const void *geno, int64_t pitch, i
     return 0;
 }
 
-// thread-per-SNP Newton solver (gt_cox_thread.cuh)
+// thread-per-SNP Newton solver (gt_cox_thread.cuh): warp 0 feeds the ring (no producer warp)
 template <int P>
 static int launch_cox_thread(const IterDesignDev &T, const void *geno, int64_t pitch, int n_snps,
                              double *out, int32_t *iout, long long ldo, cudaStream_t st,
-                             uint32_t *gperm, long long ldw, int maxround, int fold) {
-    const int cap = fold ? kLtFoldThreads : kLtMaxThreads;
+                             uint32_t *gperm, long long ldw, int maxround) {
+    const int cap = kLtFoldThreads;
     const int waves = (n_snps + 148 * cap - 1) / (148 * cap);
     int nthr = ((n_snps + 148 * waves - 1) / (148 * waves) + 31) / 32 * 32;
     nthr = std::max(32, std::min(nthr, cap));
-    const int XST = (P + 1) & ~1;                               // (K + 2) & ~1 with K = P - 1
+    const int XST = (P + 2) & ~1;                               // (K + 3) & ~1 with K = P - 1
     const size_t smem = 128 + (size_t)kLtBuf * (kLtBlk * XST * 8) + 128 +
-                        (size_t)((((P - 1) * (P - 1) + 1) & ~1) + ((P + 1) & ~1)) * 8 + (size_t)P * nthr * 8;
-    if (fold) {
-        CK(cudaFuncSetAttribute((const void *)cox_thread_kernel<P, 1>,
+                        (size_t)((((P - 1) * (P - 1) + 1) & ~1) + ((P + 1) & ~1)) * 8 +
+                        (size_t)(T.th_tied ? 3 : 1) * P * nthr * 8;
+    if (T.th_tied) {
+        CK(cudaFuncSetAttribute((const void *)cox_thread_kernel<P, 1, 1>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        cox_thread_kernel<P, 1><<<(n_snps + nthr - 1) / nthr, nthr, smem, st>>>(
+        cox_thread_kernel<P, 1, 1><<<(n_snps + nthr - 1) / nthr, nthr, smem, st>>>(
             T, (const uint8_t *)geno, pitch, n_snps, out, iout, ldo, gperm, ldw, maxround);
     } else {
-        CK(cudaFuncSetAttribute((const void *)cox_thread_kernel<P, 0>,
+        CK(cudaFuncSetAttribute((const void *)cox_thread_kernel<P, 1, 0>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        cox_thread_kernel<P, 0><<<(n_snps + nthr - 1) / nthr, nthr + 32, smem, st>>>(
+        cox_thread_kernel<P, 1, 0><<<(n_snps + nthr - 1) / nthr, nthr, smem, st>>>(
             T, (const uint8_t *)geno, pitch, n_snps, out, iout, ldo, gperm, ldw, maxround);
     }
     CK(cudaGetLastError());
@@ -313,7 +357,7 @@ static int iter_run(const IterDesignDev &T, int model, const void *geno, int64_t
             if (use_thread && lt_scratch && T.th_ok && T.p >= 2 && T.p <= 12 && n_snps >= thread_min) {
                 const long long ldw = (n_snps + 31) / 32 * 32;
                 rc = 0;
-#define GT_CT(PP) case PP: rc = launch_cox_thread<PP>(T, geno, pitch, n_snps, out, iout, ldo, st, (uint32_t *)lt_scratch, ldw, 8, thread_fold); break;
+#define GT_CT(PP) case PP: rc = launch_cox_thread<PP>(T, geno, pitch, n_snps, out, iout, ldo, st, (uint32_t *)lt_scratch, ldw, 8); break;
                 switch (T.p) {
                     GT_CT(2) GT_CT(3) GT_CT(4) GT_CT(5) GT_CT(6) GT_CT(7) GT_CT(8) GT_CT(9) GT_CT(10)
                     GT_CT(11) GT_CT(12)

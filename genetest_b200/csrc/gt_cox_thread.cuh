@@ -1,7 +1,6 @@
 // K5, thread-per-SNP version: batched Newton solver for the Cox proportional
-// hazards model, FP64, for .bed rows, designs without interaction or strata and
-// without tied event times (Efron's and Breslow's likelihoods coincide then) and
-// at most 12 parameters.
+// hazards model with Efron's tie correction and strata, FP64, for .bed rows,
+// designs without interaction and at most 12 parameters.
 //
 // Restates sm.PHReg(tte, X, status=event, ties="efron").fit() as called by
 // genetest/statistics/models/survival.py:77-82 -- Newton from beta = 0 on
@@ -18,9 +17,15 @@
 // registers and walks the samples twice per Newton step: pass 1 totals inv_t,
 // pass 2 accumulates.  No warp scans, no shuffles, no tensor-core tiles that
 // compute 64 products for the 66 of an 11 x 11 triangle twice over.
-//   * the design rows [q | event flag] (descending time, the same for every
-//     marker) come through a TMA-fed shared-memory ring, read by all lanes at
-//     the same address (broadcast);
+// Tied events (Efron): with F0 / F1 the sums over the d tied events of a time
+// point, term j of the group has den_j = S0 - (j/d) F0 and u_j = (S1 - (j/d) F1)
+// / den_j; the group's totals are gathered by a look-ahead over its rows when
+// its first member comes up, its d terms are added there, and its members then
+// take W_i = e_i (sum of 1/den at or after the group - sum_j (j/d) / den_j).
+// Strata: the sums restart with every stratum (one segment of blocks each).
+//   * the design rows [q | flags | group size] (descending time, the same for
+//     every marker) come through a TMA-fed shared-memory ring, read by all lanes
+//     at the same address (broadcast);
 //   * a first sweep gathers the marker's genotype codes into that order once
 //     and writes them word-major (word w of all markers side by side): the
 //     passes read them coalesced;
@@ -39,8 +44,10 @@
 
 namespace gtk {
 
-// FOLD = 1: warp 0 issues the bulk copies itself (see logistic_thread_kernel), 256 markers per CTA
-template <int P, int FOLD = 0>
+// FOLD = 1: warp 0 issues the bulk copies itself (see logistic_thread_kernel), 256 markers per CTA.
+// TIES = 1: groups of tied events (Efron): a group's totals are gathered by a look-ahead over its
+// rows, its d terms are added at its first member, its members then take the group's weight.
+template <int P, int FOLD = 0, int TIES = 0>
 __global__ void __launch_bounds__(256, 1)
 cox_thread_kernel(IterDesignDev T, const uint8_t *__restrict__ geno, long long pitch, int n_snps,
                   double *__restrict__ out, int *__restrict__ iout, long long ostride,
@@ -48,7 +55,7 @@ cox_thread_kernel(IterDesignDev T, const uint8_t *__restrict__ geno, long long p
                   int maxround) {
     constexpr int K = P - 1;                              // covariates (Cox has no constant)
     constexpr int NH = P * (P + 1) / 2;
-    constexpr int XST = (K + 2) & ~1;                     // q (K) | event flag
+    constexpr int XST = (K + 3) & ~1;                     // q (K) | flags | group size
     constexpr int XBLK = kLtBlk * XST * 8;
     constexpr int NF = GT_F_PARAM0 + 6 * P;
 
@@ -59,10 +66,12 @@ cox_thread_kernel(IterDesignDev T, const uint8_t *__restrict__ geno, long long p
     int *fail = (int *)(empty + kLtBuf);
     double *sRinv = (double *)(full + 16);                         // [K * K]
     double *sCmax = sRinv + ((K * K + 1) & ~1);                    // [P] max |x| per column
-    double *sBeta = sCmax + ((P + 1) & ~1);                        // [P][nthr]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nthr = blockDim.x - (FOLD ? 0 : 32);
     const int ncw = nthr >> 5;
+    double *sBeta = sCmax + ((P + 1) & ~1);                        // [P][nthr]
+    double *sF1 = sBeta + P * nthr;                                // TIES: [P][nthr] sum of e x over a group's events
+    double *sS1g = sF1 + (TIES ? P * nthr : 0);                    // TIES: [P][nthr] S1 at the end of the group
     if (tid == 0) {
         for (int s = 0; s < kLtBuf; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], ncw); }
         *fail = 0;
@@ -72,18 +81,19 @@ cox_thread_kernel(IterDesignDev T, const uint8_t *__restrict__ geno, long long p
     for (int t = tid; t < P; t += blockDim.x) sCmax[t] = T.colmax[t];
     __syncthreads();
     const int nblk = T.th_n / kLtBlk;
+    const int per_round = 2 * nblk;                        // every block twice (totals, then accumulation)
 
     if (!FOLD && warp == ncw) {
-        // ===== producer: the design rows, twice per round, while any marker of the CTA is active =====
+        // ===== producer: the design rows, stratum by stratum twice per round, while any marker is active =====
         int it = 0;
         for (int round = 0; round < maxround; ++round) {
-            for (int b = 0; b < 2 * nblk; ++b, ++it) {
+            for (int b = 0; b < per_round; ++b, ++it) {
                 const int s = it % kLtBuf;
                 if (it >= kLtBuf && !mbar_wait2(&empty[s], ((it / kLtBuf) & 1) ^ 1, fail)) *fail = 1;
                 if (elect_one()) {
                     mbar_expect_tx(&full[s], XBLK);
                     bulk_g2s((unsigned char *)sX + s * XBLK,
-                             (const unsigned char *)T.th_X + (long long)(b % nblk) * XBLK, XBLK, &full[s]);
+                             (const unsigned char *)T.th_X + (long long)__ldg(T.th_order + b) * XBLK, XBLK, &full[s]);
                 }
                 __syncwarp();
             }
@@ -127,7 +137,7 @@ cox_thread_kernel(IterDesignDev T, const uint8_t *__restrict__ geno, long long p
                 const bool ok = code != 1u;
                 nj += ok ? 1 : 0;
                 sum_g += code == 0u ? 2 : (code == 2u ? 1 : 0);
-                if (ok && __ldg(T.th_X + (long long)(w * 16 + s) * XST + K) != 0.0) nev += 1;
+                if (ok && ((int)__ldg(T.th_X + (long long)(w * 16 + s) * XST + K) & 1)) nev += 1;
             }
             myw[(long long)w * ldw] = word;
         }
@@ -147,6 +157,7 @@ cox_thread_kernel(IterDesignDev T, const uint8_t *__restrict__ geno, long long p
     const double g_hom = flip ? 0.0 : 2.0, g_ref = flip ? 2.0 : 0.0;   // codes 00 and 11
 
     double *myBeta = sBeta + tid;                           // beta[a] at myBeta[a * nthr]
+    double *myF1 = sF1 + tid, *myS1g = sS1g + tid;
 #pragma unroll
     for (int a = 0; a < P; ++a) myBeta[a * nthr] = 0.0;
     // shift of the linear predictor: an upper bound of its maximum (0 at beta = 0, grows by
@@ -154,38 +165,65 @@ cox_thread_kernel(IterDesignDev T, const uint8_t *__restrict__ geno, long long p
     double emax = 0.0, slack = 0.0, llf = 0.0;
     bool final_eval = false;
     int it = 0, issued = 0;
+    // FOLD: warp 0 keeps the copies of this round up to kLtBuf - 1 blocks ahead (never across its end)
+    auto feed = [&](int round) {
+        if (!(FOLD && warp == 0)) return;
+        const int lim = min(it + kLtBuf - 1, (round + 1) * per_round - 1);
+        for (; issued <= lim; ++issued) {
+            const int s2 = issued % kLtBuf;
+            if (issued >= kLtBuf) {
+                const uint32_t ea = smem_u32(&empty[s2]), ep = ((issued / kLtBuf) & 1) ^ 1;
+                int spin = 0;
+                while (!mbar_try(ea, ep)) if (++spin > (1 << 22)) { *fail = 1; break; }
+            }
+            if (elect_one()) {
+                mbar_expect_tx(&full[s2], XBLK);
+                bulk_g2s((unsigned char *)sX + s2 * XBLK,
+                         (const unsigned char *)T.th_X + (long long)__ldg(T.th_order + issued % per_round) * XBLK,
+                         XBLK, &full[s2]);
+            }
+            __syncwarp();
+        }
+    };
+    auto wait_block = [&]() {
+        const int st = it % kLtBuf;
+        const uint32_t fa = smem_u32(&full[st]), fp = (it / kLtBuf) & 1;
+        int spin = 0;
+        while (!mbar_try(fa, fp)) if (++spin > (1 << 22)) { *fail = 1; break; }
+        return st;
+    };
+    // linear predictor and exp(eta - emax) of schedule row `row`, read from global memory
+    // (the look-ahead over a group of tied events); returns false for a missing genotype
+    auto row_global = [&](int row, double &e, double (&x)[P]) {
+        const uint32_t code = (myw[(long long)(row >> 4) * ldw] >> (2 * (row & 15))) & 3u;
+        const double *xr = T.th_X + (long long)row * XST;
+        x[K] = code == 0u ? g_hom : (code == 2u ? 1.0 : g_ref);
+        double eta = x[K] * myBeta[K * nthr];
+#pragma unroll
+        for (int a = 0; a < K; ++a) { x[a] = __ldg(xr + a); eta = fma(x[a], myBeta[a * nthr], eta); }
+        const bool ok = code != 1u;
+        e = ok ? lt_exp_neg(emax - eta) : 0.0;
+        return ok;
+    };
 #define GT_H(a, b) H[(a) * P - (a) * ((a) - 1) / 2 + ((b) - (a))]      /* a <= b */
 #define GT_L(i, j) GT_H(j, i)                                           /* i >= j */
     for (int round = 0; round < maxround; ++round) {
-        // ---- pass 1: total of 1 / S0 over the event times ----
+        double H[NH], sc[P];
+#pragma unroll
+        for (int i = 0; i < NH; ++i) H[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < P; ++i) sc[i] = 0.0;
+        double ll = 0.0;
+        for (int seg = 0; seg < T.th_nseg; ++seg) {
+        const int b0 = __ldg(T.th_seg + seg), b1 = __ldg(T.th_seg + seg + 1);
+        // ---- pass 1: total of 1 / den over the event terms of the stratum ----
         double Ttot = 0.0;
         {
-            double S0 = 0.0;
-            for (int b = 0; b < nblk; ++b, ++it) {
-                const int st = it % kLtBuf;
-            if (FOLD && warp == 0) {
-                // copies of this round up to kLtBuf - 1 blocks ahead (never across its end)
-                const int lim = min(it + kLtBuf - 1, (round + 1) * 2 * nblk - 1);
-                for (; issued <= lim; ++issued) {
-                    const int s2 = issued % kLtBuf;
-                    if (issued >= kLtBuf) {
-                        const uint32_t ea = smem_u32(&empty[s2]), ep = ((issued / kLtBuf) & 1) ^ 1;
-                        int spin = 0;
-                        while (!mbar_try(ea, ep)) if (++spin > (1 << 22)) { *fail = 1; break; }
-                    }
-                    if (elect_one()) {
-                        mbar_expect_tx(&full[s2], XBLK);
-                        bulk_g2s((unsigned char *)sX + s2 * XBLK,
-                                 (const unsigned char *)T.th_X + (long long)(issued % nblk) * XBLK, XBLK, &full[s2]);
-                    }
-                    __syncwarp();
-                }
-            }
-                {
-                    const uint32_t fa = smem_u32(&full[st]), fp = (it / kLtBuf) & 1;
-                    int spin = 0;
-                    while (!mbar_try(fa, fp)) if (++spin > (1 << 22)) { *fail = 1; break; }
-                }
+            double S0 = 0.0, F0 = 0.0;
+            int dk = 0;
+            for (int b = b0; b < b1; ++b, ++it) {
+                feed(round);
+                const int st = wait_block();
                 const double *bx = sX + st * (kLtBlk * XST);
 #pragma unroll 1
                 for (int w16 = 0; w16 < kLtBlk / 16; ++w16) {
@@ -205,7 +243,20 @@ cox_thread_kernel(IterDesignDev T, const uint8_t *__restrict__ geno, long long p
                         }
                         const double e = ok ? lt_exp_neg(emax - (e0 + e1)) : 0.0;
                         S0 += e;
-                        if (xr[K] != 0.0) Ttot += ok ? lt_rcp(S0) : 0.0;       // event (warp-uniform)
+                        const int fl = (int)xr[K];                          // warp-uniform
+                        if (TIES && (fl & 2)) {
+                            F0 += e; dk += ok ? 1 : 0;
+                            if (fl & 8) {
+                                const int dsz = (int)xr[K + 1];
+                                const double dinv = dk > 0 ? lt_rcp((double)dk) : 0.0;
+#pragma unroll 1
+                                for (int j = 0; j < dsz; ++j)
+                                    if (j < dk) Ttot += lt_rcp(S0 - ((double)j * dinv) * F0);
+                                F0 = 0.0; dk = 0;
+                            }
+                        } else if (fl & 1) {
+                            Ttot += ok ? lt_rcp(S0) : 0.0;
+                        }
                     }
                 }
                 __syncwarp();
@@ -213,37 +264,14 @@ cox_thread_kernel(IterDesignDev T, const uint8_t *__restrict__ geno, long long p
             }
         }
         // ---- pass 2: log-likelihood, score, Hessian ----
-        double H[NH], sc[P], S1[P];
+        double S1[P];
 #pragma unroll
-        for (int i = 0; i < NH; ++i) H[i] = 0.0;
-#pragma unroll
-        for (int i = 0; i < P; ++i) { sc[i] = 0.0; S1[i] = 0.0; }
-        double S0 = 0.0, PI = 0.0, ll = 0.0;
-        for (int b = 0; b < nblk; ++b, ++it) {
-            const int st = it % kLtBuf;
-            if (FOLD && warp == 0) {
-                // copies of this round up to kLtBuf - 1 blocks ahead (never across its end)
-                const int lim = min(it + kLtBuf - 1, (round + 1) * 2 * nblk - 1);
-                for (; issued <= lim; ++issued) {
-                    const int s2 = issued % kLtBuf;
-                    if (issued >= kLtBuf) {
-                        const uint32_t ea = smem_u32(&empty[s2]), ep = ((issued / kLtBuf) & 1) ^ 1;
-                        int spin = 0;
-                        while (!mbar_try(ea, ep)) if (++spin > (1 << 22)) { *fail = 1; break; }
-                    }
-                    if (elect_one()) {
-                        mbar_expect_tx(&full[s2], XBLK);
-                        bulk_g2s((unsigned char *)sX + s2 * XBLK,
-                                 (const unsigned char *)T.th_X + (long long)(issued % nblk) * XBLK, XBLK, &full[s2]);
-                    }
-                    __syncwarp();
-                }
-            }
-            {
-                const uint32_t fa = smem_u32(&full[st]), fp = (it / kLtBuf) & 1;
-                int spin = 0;
-                while (!mbar_try(fa, fp)) if (++spin > (1 << 22)) { *fail = 1; break; }
-            }
+        for (int i = 0; i < P; ++i) S1[i] = 0.0;
+        double S0 = 0.0, PI = 0.0;
+        double Mg = 0.0, Ag = 0.0;                          // TIES: weight of the current group's members, its sum of 1 / den
+        for (int b = b0; b < b1; ++b, ++it) {
+            feed(round);
+            const int st = wait_block();
             const double *bx = sX + st * (kLtBlk * XST);
 #pragma unroll 1
             for (int w16 = 0; w16 < kLtBlk / 16; ++w16) {
@@ -252,6 +280,50 @@ cox_thread_kernel(IterDesignDev T, const uint8_t *__restrict__ geno, long long p
 #pragma unroll 2
                 for (int s = 0; s < 16; ++s) {
                     const double *xr = xw + s * XST;
+                    const int fl = (int)xr[K];                          // warp-uniform
+                    if (TIES && (fl & 4)) {
+                        // ---- first member of a group of tied events: the group's totals by a
+                        //      look-ahead over its rows, then its d Efron terms ----
+                        const int dsz = (int)xr[K + 1];
+                        const int row0 = (b * (kLtBlk / 16) + w16) * 16 + s;
+                        double S0g = S0, F0 = 0.0;
+                        int dk = 0;
+#pragma unroll
+                        for (int a = 0; a < P; ++a) { myS1g[a * nthr] = S1[a]; myF1[a * nthr] = 0.0; }
+#pragma unroll 1
+                        for (int m = 0; m < dsz; ++m) {
+                            double em, xm[P];
+                            const bool okm = row_global(row0 + m, em, xm);
+                            S0g += em; F0 += em; dk += okm ? 1 : 0;
+#pragma unroll
+                            for (int a = 0; a < P; ++a) {
+                                myS1g[a * nthr] = fma(em, xm[a], myS1g[a * nthr]);
+                                myF1[a * nthr] = fma(em, xm[a], myF1[a * nthr]);
+                            }
+                        }
+                        const double dinv = dk > 0 ? lt_rcp((double)dk) : 0.0;
+                        double Cg = 0.0;
+                        Ag = 0.0;
+#pragma unroll 1
+                        for (int j = 0; j < dsz; ++j) {
+                            if (j < dk) {
+                                const double cj = (double)j * dinv;
+                                const double den = S0g - cj * F0;
+                                const double inv = lt_rcp(den);
+                                Ag += inv; Cg = fma(cj, inv, Cg);
+                                if (final_eval) ll -= log(den);
+                                double u[P];
+#pragma unroll
+                                for (int a = 0; a < P; ++a) u[a] = fma(-cj, myF1[a * nthr], myS1g[a * nthr]) * inv;
+#pragma unroll
+                                for (int a = 0; a < P; ++a)
+#pragma unroll
+                                    for (int c2 = a; c2 < P; ++c2) GT_H(a, c2) = fma(-u[a], u[c2], GT_H(a, c2));
+                            }
+                        }
+                        // members: W_i = e_i (sum of 1 / den over the terms at or after the group - sum_j c_j / den_j)
+                        Mg = (Ttot - PI) - Cg;
+                    }
                     const uint32_t code = (word >> (2 * s)) & 3u;
                     const bool ok = code != 1u;
                     const double g = code == 0u ? g_hom : (code == 2u ? 1.0 : g_ref);
@@ -270,10 +342,18 @@ cox_thread_kernel(IterDesignDev T, const uint8_t *__restrict__ geno, long long p
                     S0 += e;
 #pragma unroll
                     for (int a = 0; a < P; ++a) S1[a] = fma(e, x[a], S1[a]);
-                    const bool ev = xr[K] != 0.0;                       // warp-uniform
                     double W = e * (Ttot - PI);
-                    if (ev) {
-                        // this sample is an event (W counts its own term): u = S1 / S0
+                    if (TIES && (fl & 2)) {
+                        // member of a group of tied events: the group's terms are in already
+                        W = e * Mg;
+                        if (ok) {
+                            if (final_eval) ll += eta - emax;
+#pragma unroll
+                            for (int a = 0; a < P; ++a) sc[a] += x[a];
+                        }
+                        if (fl & 8) PI += Ag;
+                    } else if (fl & 1) {
+                        // an event of its own (W counts its term): u = S1 / S0
                         const double inv = ok ? lt_rcp(S0) : 0.0;
                         PI += inv;
                         if (final_eval && ok) ll += (eta - emax) - log(S0);
@@ -297,6 +377,7 @@ cox_thread_kernel(IterDesignDev T, const uint8_t *__restrict__ geno, long long p
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[st]);
         }
+        }   // strata
 
         if (active) {
             const double dn = (double)nj;

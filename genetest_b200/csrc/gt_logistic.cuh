@@ -46,11 +46,13 @@ struct IterDesignDev {
     int newton_maxiter;     // coxph: PHReg.fit(maxiter=100); engine option "cox_maxiter" (tests)
     int n_seg;              // coxph: strata (1 without), blocks seg_start[s] .. seg_start[s + 1) each
     const int *seg_start;   // [n_seg + 1]
-    // coxph, thread-per-SNP kernel (no strata / interaction / tied events): design rows in
-    // descending time, th_n = n rounded up to 256 (padding rows: position -1, zeros)
-    int th_ok, th_n, th_XS;
-    const double *th_X;     // [th_n][th_XS]  q (k) | event flag
+    // coxph, thread-per-SNP kernel (no interaction): design rows in descending time, stratum by
+    // stratum, each padded to whole 256-row blocks (padding rows: position -1, zeros)
+    int th_ok, th_n, th_XS, th_tied, th_nseg;
+    const double *th_X;     // [th_n][th_XS]  q (k) | flags (1 event, 2 tied, 4 first, 8 last of its group) | group size
     const int *th_pos;      // [th_n] genotype position
+    const int *th_order;    // [2 th_n / 256] blocks in the order one round consumes them
+    const int *th_seg;      // [th_nseg + 1] first block of every stratum
 };
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
