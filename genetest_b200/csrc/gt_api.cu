@@ -518,7 +518,7 @@ int gt_engine_kernel_time(gt_engine *e, double *ms_total, int64_t *launches, int
 const char *gt_engine_dominant_kernel(const gt_engine *e) {
     if (!e) return "";
     if (e->have_design && e->model == GT_MODEL_LINEAR && e->use_tc && e->tc_N > 0) return e->dominant_tc.c_str();
-    if (e->have_design && e->model == GT_MODEL_LOGISTIC && e->use_thread_iter && e->T.I == 0 && e->T.p >= 2 &&
+    if (e->have_design && e->model == GT_MODEL_LOGISTIC && e->use_thread_iter && e->T.I <= 1 && e->T.p >= 2 + e->T.I &&
         e->T.p <= 13 && e->T.y_binary && !e->T.degenerate)
         return "logistic_thread_kernel";       // (calls of at least thread_iter_min .bed markers)
     if (e->have_design && e->model == GT_MODEL_COXPH && e->use_thread_iter && e->T.th_ok)
@@ -1250,7 +1250,7 @@ static int run_host(gt_engine *e, const void *src, int64_t src_pitch_bytes, int6
         // thread-per-SNP IRLS: whole waves of 148 CTAs x 224 markers
         const int64_t tw = 148 * (int64_t)(e->thread_fold ? gtk::kLtFoldThreads : gtk::kLtMaxThreads);
         if (packed && e->use_thread_iter && chunk >= tw &&
-            ((e->model == GT_MODEL_LOGISTIC && e->T.I == 0 && e->T.p <= 13 && e->T.y_binary) ||
+            ((e->model == GT_MODEL_LOGISTIC && e->T.I <= 1 && e->T.p <= 13 && e->T.y_binary) ||
              (e->model == GT_MODEL_COXPH && e->T.th_ok)))
             chunk = chunk / tw * tw;
         chunk = std::min<int64_t>(chunk, std::max<int64_t>(1024, ((int64_t)512 << 20) / dev_pitch_bytes / 1024 * 1024));

@@ -270,14 +270,22 @@ static int launch_logistic_thread(const IterDesignDev &T, const void *geno, int6
                                   double *out, int32_t *iout, long long ldo, cudaStream_t st,
                                   double *scratch, long long lds, int maxpass, int fold) {
     // markers per CTA: the batch spread over the 148 SMs (whole warps)
-    const int cap = fold ? kLtFoldThreads : kLtMaxThreads;
+    const int cap = (fold || T.I == 1) ? kLtFoldThreads : kLtMaxThreads;
     const int waves = (n_snps + 148 * cap - 1) / (148 * cap);
     int nthr = ((n_snps + 148 * waves - 1) / (148 * waves) + 31) / 32 * 32;
     nthr = std::max(32, std::min(nthr, cap));
     const int XSs = std::max(2, (P & ~1));                       // (K + 1) & ~1 with K = P - 1
     const size_t smem = 128 + (size_t)kLtBuf * (kLtBlk * XSs * 8 + kLtBlk * 8) + 128 +
                         (size_t)(((P - 1) * (P - 1) + 1) & ~1) * 8 + (size_t)P * nthr * 8;
-    if (fold) {
+    if (T.I == 1) {
+        // one interaction column: design row [q | g | g w] (always without a producer warp)
+        if constexpr (P >= 3) {
+            CK(cudaFuncSetAttribute((const void *)logistic_thread_kernel<P, 1, 1>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            logistic_thread_kernel<P, 1, 1><<<(n_snps + nthr - 1) / nthr, nthr, smem, st>>>(
+                T, (const uint8_t *)geno, pitch, n_snps, out, iout, ldo, scratch, lds, maxpass);
+        }
+    } else if (fold) {
         CK(cudaFuncSetAttribute((const void *)logistic_thread_kernel<P, 1>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         logistic_thread_kernel<P, 1><<<(n_snps + nthr - 1) / nthr, nthr, smem, st>>>(
@@ -380,7 +388,7 @@ static int iter_run(const IterDesignDev &T, int model, const void *geno, int64_t
         // one thread per marker first, the warp kernel then only finishes what that one deferred
         int deferred = 0;
         rc = 0;
-        if (use_thread && lt_scratch && T.I == 0 && T.p >= 2 && T.p <= 13 && T.y_binary && !T.degenerate &&
+        if (use_thread && lt_scratch && T.I <= 1 && T.p >= 2 + T.I && T.p <= 13 && T.y_binary && !T.degenerate &&
             n_snps >= thread_min) {
             const long long lds = (n_snps + 31) / 32 * 32;
             const int maxpass = 9;

@@ -131,15 +131,16 @@ GT_HD double lt_log1p01(double t, double &inv) {   // log(1 + t) and inv = 1 / (
 
 // FOLD = 1: no producer warp -- warp 0 issues the bulk copies between its own blocks (one block
 // of lookahead less than the ring holds), which makes room for an eighth warp of markers.
-template <int P, int FOLD = 0>
+// NI = 1: one SNP x covariate interaction column (design row [q | g | g w], analysis.py:159-166).
+template <int P, int FOLD = 0, int NI = 0>
 __global__ void __launch_bounds__(256, 1)
 logistic_thread_kernel(IterDesignDev T, const uint8_t *__restrict__ geno, long long pitch, int n_snps,
                        double *__restrict__ out, int *__restrict__ iout, long long ostride,
                        double *__restrict__ scratch /* [2 P][lds] coef, se of the last solve */, long long lds,
                        int maxpass) {
-    constexpr int K = P - 1;
+    constexpr int K = P - 1 - NI;                         // covariates (orthonormal basis q)
     constexpr int NH = P * (P + 1) / 2;
-    constexpr int XS = (K + 1) & ~1;                      // row stride of T.X (I = 0)
+    constexpr int XS = (K + NI + 1) & ~1;                 // row stride of T.X: q (K) | w (NI)
     constexpr int XSs = XS > 0 ? XS : 2;
     constexpr int XBLK = kLtBlk * XSs * 8, YBLK = kLtBlk * 8;
     constexpr int NF = GT_F_PARAM0 + 6 * P;
@@ -317,6 +318,7 @@ logistic_thread_kernel(IterDesignDev T, const uint8_t *__restrict__ geno, long l
 #pragma unroll
                         for (int a = 0; a < K; ++a) x[a] = xr[a];
                         x[K] = g;
+                        if (NI) x[K + 1] = g * xr[K];
                         double eta, mu, li = 0.0;
                         if (pass == 0) {
                             // statsmodels' start for y in {0, 1}: the same constants for every sample
@@ -472,8 +474,9 @@ logistic_thread_kernel(IterDesignDev T, const uint8_t *__restrict__ geno, long l
                             var = fma(u, u, var);
                         }
                     } else {
-                        cf = r[K];
-                        var = GT_L(K, K) * GT_L(K, K);
+                        cf = r[i];
+#pragma unroll
+                        for (int rr = i; rr < P; ++rr) var = fma(GT_L(rr, i), GT_L(rr, i), var);
                     }
                     scratch[(long long)i * lds + snp] = cf;
                     scratch[(long long)(P + i) * lds + snp] = sqrt(var);

@@ -121,10 +121,13 @@ int gt_engine_synchronize(gt_engine *e);
  * (PHReg.fit's maxiter, default 100; reaching it is "Maximum Likelihood
  * optimization failed to converge", survival.py:87-88).  "thread_solve" = 1
  * (default): thread-per-SNP solve of narrow linear designs.  "thread_iter" = 1
- * (default): logistic fits of .bed rows with a binary outcome, no interaction
- * and at most 13 parameters run on the thread-per-SNP IRLS kernel when the
- * call has at least "thread_iter_min" markers (default 4096), the warp-per-SNP
- * kernel finishing what it defers.  "tc_debug": tuning probes of the tcgen05
+ * (default): logistic fits of .bed rows with a binary outcome, at most one
+ * interaction column and at most 13 parameters, and Cox fits without
+ * interaction and at most 12 parameters, run on the thread-per-SNP kernels
+ * when the call has at least "thread_iter_min" markers (default 4096), the
+ * warp-per-SNP kernels finishing what they defer.  "thread_fold" = 1
+ * (default): those kernels and the streaming corrections run without a
+ * producer warp (warp 0 issues the bulk copies), 256 markers per CTA.  "tc_debug": tuning probes of the tcgen05
  * kernel. */
 int gt_engine_set_option(gt_engine *e, const char *name, int value);
 

@@ -252,6 +252,40 @@ def test_logistic_thread_kernel_matches_oracle_and_warp_kernel(engine):
     print("logistic thread kernel worst rel err", worst, "ok", n_ok)
 
 
+def test_logistic_thread_kernel_interaction(engine):
+    """Thread-per-SNP IRLS with one SNP x covariate interaction column (design row
+    [q | g | g w], analysis.py:159-166): against the oracle and the warp-per-SNP kernel, on a
+    permuted subset of the file with missing genotypes and flipped markers."""
+    rng = np.random.default_rng(79)
+    n_file, n, n_snps = 1300, 1100, 240
+    C, names = synth_design(rng, n, k_extra=2)
+    pos = rng.permutation(n_file)[:n].astype(np.int32)
+    Gfile = synth_genotypes(rng, n_snps, n_file, missing=0.02, maf_lo=0.05, maf_hi=0.95)
+    eta = -0.2 + 0.3 * C[:, 0] + 0.2 * np.nan_to_num(Gfile[5, pos]) * C[:, 0]
+    y = (rng.random(n) < 1 / (1 + np.exp(-eta))).astype(float)
+    inter = {"I:age": ["age"]}
+    engine.set_design("logistic", y, C, W=C[:, [0]], sample_pos=pos, n_file=n_file)
+    assert engine.dominant_kernel() == "logistic_thread_kernel"
+    packed = pack_rows(Gfile)
+    try:
+        engine.set_option("thread_iter_min", 64)
+        res = engine.run_packed_host(packed)
+        engine.set_option("thread_iter", 0)
+        ref = engine.run_packed_host(packed)
+    finally:
+        engine.set_option("thread_iter", 1)
+        engine.set_option("thread_iter_min", 4096)
+    oracle = run_oracle("logistic", y[:, None], C, names, Gfile[:, pos], interaction=inter)
+    problems, worst, n_ok = compare("logistic", res, oracle, names, inter_keys=list(inter),
+                                    rtol=LOGIT_TOL)
+    assert not problems, problems[:10]
+    assert n_ok == n_snps
+    assert (res.status == ref.status).all() and (res.niter == ref.niter).all()
+    assert (res.flip == ref.flip).all() and res.flip.sum() > 60
+    np.testing.assert_allclose(res.out, ref.out, rtol=1e-9, atol=0, equal_nan=True)
+    print("logistic thread kernel with interaction: worst rel err", worst)
+
+
 def test_logistic_interaction_subset_and_separation(engine):
     rng = np.random.default_rng(22)
     n_file, n, n_snps = 1200, 1000, 60
