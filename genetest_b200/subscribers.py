@@ -136,12 +136,17 @@ class RowWriter(Subscriber):
         cols = [field if isinstance(field, str)
                 else block.column(field.path, info)
                 for _name, field in self.columns]
-        text = format_rows(cols, keep=block.ok_mask, sep=self.sep).decode()
-        if self._f is not None:
-            self._f.write(text)
+        data = format_rows(cols, keep=block.ok_mask, sep=self.sep)
+        if self._f is not None and hasattr(self._f, "buffer"):
+            # the rows are ASCII already: straight into the file's byte buffer
+            self._f.flush()
+            self._f.buffer.write(data)
+            self._f.buffer.flush()
+        elif self._f is not None:
+            self._f.write(data.decode())
             self._f.flush()
         else:
-            print(text, end="")
+            print(data.decode(), end="")
 
 
 _STAT_COLUMNS = {

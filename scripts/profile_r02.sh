@@ -13,13 +13,13 @@ cap() {  # name, kernel regex, count, command...
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:$regex -c $cnt -o /tmp/$name "$@" > gpurun_out/ncu_$name.log 2>&1
   python profiles/summarise_ncu.py rep /tmp/$name.ncu-rep gpurun_out/${name}.md
 }
-cap r02c_ncu_full_linear "contract_tc2|missing_corr_stream|linear_solve_thread" 3 python scripts/tc_variants.py 151552 0
-python profiles/ncu_stalls.py /tmp/r02c_ncu_full_linear.ncu-rep contract_tc2 25 > gpurun_out/r02c_stalls_contract.txt
-python profiles/ncu_stalls.py /tmp/r02c_ncu_full_linear.ncu-rep missing_corr_stream 25 > gpurun_out/r02c_stalls_corrections.txt
-cap r02c_ncu_full_logistic "logistic_thread" 1 python scripts/logit_probe.py 33152
-python profiles/ncu_stalls.py /tmp/r02c_ncu_full_logistic.ncu-rep logistic_thread 25 > gpurun_out/r02c_stalls_logistic.txt
-cap r02c_ncu_full_cox "cox_thread" 1 python scripts/cox_probe.py 33152
-python profiles/ncu_stalls.py /tmp/r02c_ncu_full_cox.ncu-rep cox_thread 25 > gpurun_out/r02c_stalls_cox.txt
-cap r02c_ncu_full_gxe "contract_tc2" 1 python bench.py --model linear_gxe --steps 1 --warmup 1 --no-side
-python profiles/ncu_stalls.py /tmp/r02c_ncu_full_gxe.ncu-rep contract_tc2 25 > gpurun_out/r02c_stalls_gxe.txt
+cap r02d_ncu_full_linear "contract_tc2|missing_corr_stream|linear_solve_thread" 3 python scripts/tc_variants.py 151552 0
+python profiles/ncu_stalls.py /tmp/r02d_ncu_full_linear.ncu-rep contract_tc2 25 > gpurun_out/r02d_stalls_contract.txt
+python profiles/ncu_stalls.py /tmp/r02d_ncu_full_linear.ncu-rep missing_corr_stream 25 > gpurun_out/r02d_stalls_corrections.txt
+cap r02d_ncu_full_logistic "logistic_thread" 1 python scripts/logit_probe.py 37888
+python profiles/ncu_stalls.py /tmp/r02d_ncu_full_logistic.ncu-rep logistic_thread 25 > gpurun_out/r02d_stalls_logistic.txt
+cap r02d_ncu_full_cox "cox_thread" 1 python scripts/cox_probe.py 37888
+python profiles/ncu_stalls.py /tmp/r02d_ncu_full_cox.ncu-rep cox_thread 25 > gpurun_out/r02d_stalls_cox.txt
+cap r02d_ncu_full_gxe "contract_tc2" 1 python bench.py --model linear_gxe --steps 1 --warmup 1 --no-side
+python profiles/ncu_stalls.py /tmp/r02d_ncu_full_gxe.ncu-rep contract_tc2 25 > gpurun_out/r02d_stalls_gxe.txt
 ls -la gpurun_out | tail -20
