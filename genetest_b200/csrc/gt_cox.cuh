@@ -333,6 +333,19 @@ static int launch_cox_thread(const IterDesignDev &T, const void *geno, int64_t p
     const size_t smem = 128 + (size_t)kLtBuf * (kLtBlk * XST * 8) + 128 +
                         (size_t)((((P - 1) * (P - 1) + 1) & ~1) + ((P + 1) & ~1)) * 8 +
                         (size_t)(T.th_tied ? 3 : 1) * P * nthr * 8;
+    {
+        // the codes of every marker in schedule order, word-major
+        const int row_words = (T.n_file + 15) / 16;
+        int spw = row_words | 1;                                  // odd: the markers of a word hit distinct banks
+        int mpc = 32;
+        while (mpc > 1 && (size_t)mpc * spw * 4 > 200 * 1024) mpc >>= 1;
+        const size_t psm = (size_t)mpc * spw * 4;
+        if (psm > 220 * 1024) return fail(GT_E_UNSUPPORTED, "thread-per-SNP Cox kernel: %d samples per row", T.n_file);
+        CK(cudaFuncSetAttribute((const void *)cox_permute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
+        cox_permute_kernel<<<(n_snps + mpc - 1) / mpc, 256, psm, st>>>(
+            (const uint8_t *)geno, pitch, n_snps, row_words, T.th_pos, T.th_n, gperm, ldw, mpc, spw);
+        CK(cudaGetLastError());
+    }
     if (T.th_tied) {
         CK(cudaFuncSetAttribute((const void *)cox_thread_kernel<P, 1, 1>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

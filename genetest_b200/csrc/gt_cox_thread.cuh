@@ -44,6 +44,40 @@
 
 namespace gtk {
 
+// The genotype codes of `mpc` markers at a time in schedule order: their packed rows are
+// staged in shared memory (coalesced), every thread then builds 16-code words for one marker
+// (lane-fastest over the markers, so that word w of neighbouring markers is written side by
+// side) -- a per-thread gather from global memory would fetch a 32-byte sector per code.
+__global__ void __launch_bounds__(256)
+cox_permute_kernel(const uint8_t *__restrict__ geno, long long pitch, int n_snps, int row_words,
+                   const int *__restrict__ th_pos, int th_n, uint32_t *__restrict__ gperm, long long ldw,
+                   int mpc, int spitch_words) {
+    extern __shared__ __align__(16) uint32_t srow[];        // [mpc][spitch_words]
+    const int snp0 = blockIdx.x * mpc;
+    for (int m = 0; m < mpc; ++m) {
+        const int snp = snp0 + m;
+        if (snp >= n_snps) break;
+        const uint32_t *src = (const uint32_t *)(geno + (long long)snp * pitch);
+        for (int w = threadIdx.x; w < row_words; w += blockDim.x) srow[m * spitch_words + w] = __ldg(src + w);
+    }
+    __syncthreads();
+    const int m = threadIdx.x % mpc, grp = threadIdx.x / mpc, ngrp = blockDim.x / mpc;
+    const int snp = snp0 + m;
+    if (snp >= n_snps) return;
+    const uint8_t *row = (const uint8_t *)(srow + m * spitch_words);
+    const int nword = th_n / 16;
+    for (int ww = grp; ww < nword; ww += ngrp) {
+        uint32_t word = 0;
+#pragma unroll
+        for (int s = 0; s < 16; ++s) {
+            const int ps = __ldg(th_pos + ww * 16 + s);
+            const uint32_t code = ps >= 0 ? ((uint32_t)row[ps >> 2] >> (2 * (ps & 3))) & 3u : 1u;
+            word |= code << (2 * s);
+        }
+        gperm[(long long)ww * ldw + snp] = word;
+    }
+}
+
 // FOLD = 1: warp 0 issues the bulk copies itself (see logistic_thread_kernel), 256 markers per CTA.
 // TIES = 1: groups of tied events (Efron): a group's totals are gathered by a look-ahead over its
 // rows, its d terms are added at its first member, its members then take the group's weight.
@@ -105,7 +139,7 @@ cox_thread_kernel(IterDesignDev T, const uint8_t *__restrict__ geno, long long p
     // ===== one thread per marker =====
     const int snp = blockIdx.x * nthr + tid;
     const bool owner = snp < n_snps;
-    const uint8_t *rowp = geno + (long long)(owner ? snp : 0) * pitch;
+    (void)geno; (void)pitch;
     uint32_t *myw = gperm + (owner ? snp : 0);
     const int nword = T.th_n / 16;
     auto write_fail = [&](int status, int nobs, int flip, double maf, double aux, int niter) {
@@ -122,24 +156,23 @@ cox_thread_kernel(IterDesignDev T, const uint8_t *__restrict__ geno, long long p
         iout[(long long)GT_I_NITER * ostride + snp] = niter;
     };
 
-    // ---- first sweep: the marker's codes in schedule order; complete cases, MAF, flip ----
+    // ---- complete cases, MAF, flip from the codes in schedule order (cox_permute_kernel) ----
     int nj = 0, sum_g = 0, nev = 0;
     if (owner) {
 #pragma unroll 1
         for (int w = 0; w < nword; ++w) {
-            uint32_t word = 0;
+            const uint32_t word = myw[(long long)w * ldw];
+            const uint32_t s1 = word >> 1;
+            const uint32_t hom = ~(word | s1) & 0x55555555u, het = s1 & ~word & 0x55555555u;
+            const uint32_t mis = word & ~s1 & 0x55555555u;
+            nj += 16 - __popc(mis);
+            sum_g += 2 * __popc(hom) + __popc(het);
+            // events among the complete cases: the flags of the 16 rows (the same for every lane)
+            uint32_t evm = 0;
 #pragma unroll
-            for (int s = 0; s < 16; ++s) {
-                const int ps = __ldg(T.th_pos + w * 16 + s);            // the same for every lane
-                uint32_t code = 1u;                                      // padding rows: missing
-                if (ps >= 0) code = ((uint32_t)__ldg(rowp + (ps >> 2)) >> (2 * (ps & 3))) & 3u;
-                word |= code << (2 * s);
-                const bool ok = code != 1u;
-                nj += ok ? 1 : 0;
-                sum_g += code == 0u ? 2 : (code == 2u ? 1 : 0);
-                if (ok && ((int)__ldg(T.th_X + (long long)(w * 16 + s) * XST + K) & 1)) nev += 1;
-            }
-            myw[(long long)w * ldw] = word;
+            for (int s = 0; s < 16; ++s)
+                evm |= (uint32_t)((int)__ldg(T.th_X + (long long)(w * 16 + s) * XST + K) & 1) << (2 * s);
+            nev += __popc(evm & ~mis);
         }
     }
     bool active = owner;
