@@ -953,7 +953,7 @@ static int launch_contract_tc(gt_engine *e, const uint8_t *g, int64_t pitch, int
     }
 #undef GT_TCH
     // tuning probes (option "tc_debug") of the 5 x 16 column instantiation only
-    GT_TCD(5, 4, 1) GT_TCD(5, 4, 2) GT_TCD(5, 4, 6) GT_TCD(5, 4, 14) GT_TCD(5, 4, 61) GT_TCD(5, 4, 63) GT_TCD(5, 4, 128) GT_TCD(5, 4, 256) GT_TCD(5, 4, 512) GT_TCD(5, 4, 768)
+    GT_TCD(5, 4, 1) GT_TCD(5, 4, 2) GT_TCD(5, 4, 6) GT_TCD(5, 4, 14) GT_TCD(5, 4, 61) GT_TCD(5, 4, 63) GT_TCD(5, 4, 128)
 #undef GT_TCD
     switch (NT) {
         GT_TC(1, 4) GT_TC(2, 4) GT_TC(3, 4) GT_TC(4, 4) GT_TC(5, 4) GT_TC(6, 4) GT_TC(7, 2) GT_TC(8, 2)

@@ -132,15 +132,12 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 // x >> 16 as the high half of x * 2^16: an IMAD.HI on the FMA pipe instead of a shift on the
-// ALU pipe, which the expansion loop saturates (LOP3 / SHF / PRMT all issue there)
+// ALU pipe, which the expansion loop saturates (LOP3 / SHF / PRMT all issue there).  (Doing the
+// same to the >> 1 and >> 2 shifts of the flag / selector words measured 3 % slower, and two
+// instead of three A slots 18 % slower.)
 __device__ __forceinline__ uint32_t hi16(uint32_t x) {
     uint32_t r;
     asm("mul.hi.u32 %0, %1, 65536;\n" : "=r"(r) : "r"(x));
-    return r;
-}
-template <int K> __device__ __forceinline__ uint32_t shr_fma(uint32_t x) {
-    uint32_t r;
-    asm("mul.hi.u32 %0, %1, %2;\n" : "=r"(r) : "r"(x), "n"(1u << (32 - K)));
     return r;
 }
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
@@ -185,7 +182,7 @@ contract_tc2_kernel(const __grid_constant__ CUtensorMap gmap, const Tc2Params P)
     constexpr int BSTAGE = N * 128;
     constexpr int BST = Cfg::b_stages(N);
     constexpr int G = Cfg::kGStages;
-    constexpr int S = (DBG & 256) ? 2 : Cfg::a_slots(N);
+    constexpr int S = Cfg::a_slots(N);
     constexpr int EW = Cfg::kExpWarps;
     constexpr int TMEM_NEED = TILES * N + S * TILES * 16;
     constexpr int TMEM_COLS = TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512);
@@ -292,7 +289,7 @@ contract_tc2_kernel(const __grid_constant__ CUtensorMap gmap, const Tc2Params P)
                 // flags of an even word sit on the even bits, those of an odd word on the odd
                 // bits, so that two words share one flag word without any realignment
                 if (!(j & 1)) {
-                    const uint32_t s1 = (DBG & 512) ? shr_fma<1>(wm) : wm >> 1;
+                    const uint32_t s1 = wm >> 1;
                     homf[j] = ~(wm | s1) & 0x55555555u;          // code 00
                     misf[j] = wm & ~s1 & 0x55555555u;            // code 01
                 } else {
@@ -300,7 +297,7 @@ contract_tc2_kernel(const __grid_constant__ CUtensorMap gmap, const Tc2Params P)
                     homf[j] = ~(wm | s1) & 0xaaaaaaaau;
                     misf[j] = s1 & ~wm & 0xaaaaaaaau;
                 }
-                const uint32_t even = w & 0x33333333u, odd = ((DBG & 512) ? shr_fma<2>(w) : (w >> 2)) & 0x33333333u;
+                const uint32_t even = w & 0x33333333u, odd = (w >> 2) & 0x33333333u;
                 a[j * 4 + 0] = prmt(lut, 0u, even);
                 a[j * 4 + 1] = prmt(lut, 0u, hi16(even));
                 a[j * 4 + 2] = prmt(lut, 0u, odd);
