@@ -326,7 +326,8 @@ def measure_side_workload(eng, torch, dist, rank, world, workload, steps,
     breakdown = eng.kernel_breakdown()
     eng.enable_timing(False)
     # end to end with host buffers
-    e2e_snps = min(snps, 65536)
+    # (the iterative models: whole waves of their thread-per-SNP kernels, 148 CTAs x 256 markers)
+    e2e_snps = min(snps, 65536 if base_model(workload) == "linear" else 75776)
     hp = torch.empty((e2e_snps, (n + 3) // 4), dtype=torch.uint8).pin_memory()
     hp.copy_(packed[:e2e_snps, :(n + 3) // 4].cpu())
     ho = torch.empty((eng.n_fields, e2e_snps), dtype=torch.float64).pin_memory()
@@ -612,7 +613,7 @@ def run_ours(args, rank, world, local_rank):
     n_ok = int((status == 0).sum().item())
 
     # ---- end to end through the C ABI with HOST buffers (H2D + D2H inside) ----
-    e2e_snps = min(snps, args.e2e_snps)
+    e2e_snps = min(snps, args.e2e_snps if base_model(workload) == "linear" else max(args.e2e_snps, 75776))
     host_packed = torch.empty((e2e_snps, (n + 3) // 4), dtype=torch.uint8).pin_memory()
     host_packed.copy_(packed[:e2e_snps, :(n + 3) // 4].cpu())
     host_out = torch.empty((eng.n_fields, e2e_snps), dtype=torch.float64).pin_memory()
