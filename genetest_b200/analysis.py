@@ -15,6 +15,7 @@ the subscribers -- there is no other communication.
 """
 
 import itertools
+import os
 import logging
 
 import numpy as np
@@ -52,10 +53,14 @@ def _generate_sample_order(x_samples, geno_samples):
     geno_order = np.array(
         [i for i, s in enumerate(geno_samples) if s in in_x], dtype=int)
     x_order = np.asarray(geno_samples, dtype=object)[geno_order]
-    if pd.Index(x_samples).duplicated().any():
-        raise NotImplementedError(
-            "repeated measurements (duplicated samples) are only used by "
-            "mixedlm, which is outside the B200 hot path")
+    x_index = pd.Index(x_samples)
+    if x_index.duplicated().any():
+        # repeated measurements (mixedlm): one genotype per row of X, in the
+        # order X.loc[x_order] lists them (analysis.py:54-63)
+        counts = x_index.value_counts()
+        geno_order = np.array(
+            [i for i, s in zip(geno_order, x_order) for _ in range(counts[s])],
+            dtype=int)
     return geno_order, x_order
 
 
@@ -66,6 +71,91 @@ def execute_formula(phenotypes, genotypes, formula, test, test_kwargs=None,
     modelspec, subgroups = modelspec_from_formula(formula, test, test_kwargs)
     execute(phenotypes, genotypes, modelspec, subscribers, variant_predicates,
             output_prefix, subgroups, maf_t, cpus, sexual_chromosome)
+
+
+def execute_mixedlm_two_step(phenotypes, genotypes, formula, p_threshold,
+                             output_prefix, test_kwargs=None,
+                             variant_predicates=None, maf_t=None, cpus=None,
+                             sexual_chromosome=False):
+    """The "optimized" MixedLM analysis of the reference's command line
+    (``genetest/scripts/cli.py:183-310``), as a library call:
+
+    1. fit the mixed model once WITHOUT the SNPs (host) and keep the predicted
+       random effect of every sample;
+    2. run a plain linear GWAS ``_random_effects ~ SNPs`` over all the markers
+       -- the B200 hot path -- into ``<prefix>.mixedlm_approximation.txt``;
+    3. refit the real mixed model (host, one marker at a time) only for the
+       markers whose approximate p-value is below ``p_threshold``, into
+       ``<prefix>.txt``.
+
+    Returns the set of marker names that went through step 3."""
+    from . import modelspec as spec
+    from .modelspec import result as analysis_results
+    from .modelspec.predicates import NameFilter
+    from .phenotypes import DataFramePhenotypes
+    from .subscribers import GWASWriter, ResultsMemory, RowWriter
+
+    modelspec, subgroups = modelspec_from_formula(formula, "mixedlm", test_kwargs)
+    if subgroups is not None:
+        raise ValueError("Subgroups are not available for MixedLM optimization")
+    if "SNPs" in modelspec.predictors:
+        del modelspec.predictors[modelspec.predictors.index("SNPs")]
+
+    logger.info("Computing the random effects")
+    memory = ResultsMemory()
+    execute(phenotypes, genotypes, modelspec, subscribers=[memory],
+            output_prefix=output_prefix, subgroups=subgroups, maf_t=maf_t,
+            cpus=cpus, sexual_chromosome=sexual_chromosome)
+    random_effects = memory.results.pop()["MODEL"]["random_effects"]
+    group_col = modelspec.get_translations()[modelspec.outcome["groups"].id]
+
+    old = phenotypes.get_phenotypes()
+    assert "_random_effects" not in old.columns
+    duplicated = old.index.duplicated(keep="first")
+    new = pd.merge(
+        left=old.loc[~duplicated, :].copy(),
+        right=pd.DataFrame({"_random_effects": random_effects}),
+        left_on=group_col, right_index=True)
+
+    spec._reset()
+    new_phenotypes = DataFramePhenotypes(new)
+    assert not new_phenotypes.is_repeated()
+    approx_spec = spec.ModelSpec(outcome=spec.phenotypes._random_effects,
+                                 predictors=[spec.SNPs], test="linear")
+    approximation_fn = output_prefix + ".mixedlm_approximation.txt"
+    r = analysis_results
+    writer = RowWriter(
+        filename=approximation_fn,
+        columns=[("snp", r["SNPs"]["name"]), ("chr", r["SNPs"]["chrom"]),
+                 ("pos", r["SNPs"]["pos"]), ("major", r["SNPs"]["major"]),
+                 ("minor", r["SNPs"]["minor"]), ("maf", r["SNPs"]["maf"]),
+                 ("n", r["MODEL"]["nobs"]), ("p", r["SNPs"]["p_value"]),
+                 ("ll", r["MODEL"]["log_likelihood"]),
+                 ("adj_r2", r["MODEL"]["r_squared_adj"]),
+                 ("approximation", "Yes")],
+        header=True, append=False)
+    logger.info("Executing the optimized MixedLM")
+    execute(new_phenotypes, genotypes, approx_spec, subscribers=[writer],
+            output_prefix=output_prefix + ".mixedlm_approximation",
+            maf_t=maf_t, cpus=cpus, variant_predicates=variant_predicates,
+            sexual_chromosome=sexual_chromosome)
+    if not os.path.isfile(approximation_fn):
+        raise RuntimeError("{}: no such file".format(approximation_fn))
+    approximation = pd.read_csv(approximation_fn, sep="\t")
+    markers = set(approximation.loc[approximation.p < p_threshold, "snp"].values)
+    if len(markers) == 0:
+        logger.info("No marker had a p value < than {}".format(p_threshold))
+        return markers
+
+    spec._reset()
+    logger.info("Executing MixedLM on {:,d} markers".format(len(markers)))
+    execute_formula(phenotypes, genotypes, formula, "mixedlm",
+                    test_kwargs=test_kwargs,
+                    subscribers=[GWASWriter(output_prefix + ".txt", "mixedlm")],
+                    variant_predicates=[NameFilter(extract=markers)],
+                    output_prefix=output_prefix, maf_t=maf_t, cpus=cpus,
+                    sexual_chromosome=sexual_chromosome)
+    return markers
 
 
 def execute(phenotypes, genotypes, modelspec, subscribers=None,
@@ -403,6 +493,8 @@ def _host_fit_loop(genotypes, test, subscribers, y, X, variant_predicates,
         raise RuntimeError("Genotype and phenotype data have "
                            "non-overlapping indices.")
     X = X.copy()
+    unique_samples = ~X.index.duplicated(keep="first")
+    has_duplicates = not unique_samples.all()
     for snp in genotypes.iter_genotypes():
         try:
             if not all([f(snp) for f in variant_predicates]):
@@ -419,11 +511,16 @@ def _host_fit_loop(genotypes, test, subscribers, y, X, variant_predicates,
             messages["failed"].append((snp.variant.name,
                                        "All genotypes are missing"))
             continue
+        # repeated measurements: every sample counts once in the MAF
+        # (analysis.py:74-79, 127-129)
+        for_maf = not_missing
+        if has_duplicates:
+            for_maf = not_missing & unique_samples
         if sample_sex is None:
             maf, minor, major, flip = get_maf(
-                X.loc[not_missing, "SNPs"], snp.coded, snp.reference)
+                X.loc[for_maf, "SNPs"], snp.coded, snp.reference)
         else:
-            ids = X.index[not_missing]
+            ids = X.index[for_maf]
             maf, minor, major, flip = get_sex_maf(
                 X.loc[ids, "SNPs"], sample_sex.reindex(ids), snp.coded,
                 snp.reference)
@@ -484,6 +581,10 @@ def _execute_gwas(genotypes, modelspec, subscribers, y, X, variant_predicates,
 
     # ---- sample alignment (analysis.py:43-65, 97-116) ----
     samples = list(genotypes.get_samples())
+    if X.index.duplicated().any():
+        raise NotImplementedError(
+            "repeated measurements (duplicated samples) are the input of "
+            "mixedlm; the batched {} kernels fit one row per sample".format(model))
     geno_index, sample_order = _generate_sample_order(X.index, samples)
     if geno_index.shape[0] == 0:
         logger.critical("Genotype and phenotype data have non-overlapping "

@@ -11,7 +11,7 @@ Outputs (committed):
 * ``tests/golden/data/*.tsv``    -- the reference's known-answer data tables
   (``genetest/tests/data/statistics/*.txt.bz2``), decompressed verbatim.
 * ``tests/golden/expected.json`` -- every SAS / R / hand number asserted by
-  ``genetest/tests/test_{linear,logistic,coxph}.py``, pulled out of the test
+  ``genetest/tests/test_{linear,logistic,coxph,mixedlm}.py``, pulled out of the test
   sources with ``ast`` (the expected-value expressions are evaluated, the
   "actual" side is recorded as (entity, field, transform)).
 
@@ -31,9 +31,9 @@ REF = "/root/reference/genetest/tests"
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 DATA_FILES = ["linear", "linear_missing", "logistic", "logistic_missing",
-              "coxph", "factors"]
+              "coxph", "factors", "mixedlm"]
 TEST_FILES = {"linear": "test_linear.py", "logistic": "test_logistic.py",
-              "coxph": "test_coxph.py"}
+              "coxph": "test_coxph.py", "mixedlm": "test_mixedlm.py"}
 
 
 class _Inter(object):

@@ -528,3 +528,49 @@ def test_stratified_cox_through_execute(tmp_path):
     # (gwas_one flips to the minor allele; G[0] has MAF 0.3: no flip)
     assert abs(one["SNPs"]["coef"] - o["SNPs"]["coef"]) <= 1e-6 * abs(o["SNPs"]["coef"])
     assert abs(one["MODEL"]["log_likelihood"] - o["MODEL"]["log_likelihood"]) <= 1e-8 * abs(o["MODEL"]["log_likelihood"])
+
+
+def test_mixedlm_two_step(tmp_path):
+    """The "optimized" MixedLM analysis (cli.py:183-310): mixed model without the SNPs on the
+    host, linear GWAS of the predicted random effects on the GPU, the real mixed model only
+    for the markers under the p-value threshold.  Data of the reference's test_mixedlm.py;
+    the markers kept by a threshold of 1 get the R / lme4 numbers of test_mixedlm_gwas, and
+    the approximation file holds the OLS fit of the random effects on each marker."""
+    from genetest_b200.phenotypes import DataFramePhenotypes
+    df = load_table("mixedlm")
+    df.index = df["sampleid"].values
+    snps = ["snp1", "snp2", "snp3", "snp4"]
+    markers = {"snp1": ("3", 1234, "T", "G"), "snp2": ("3", 2345, "C", "A"),
+               "snp3": ("2", 3456, "G", "T"), "snp4": ("22", 4567, "A", "C")}
+    rng = np.random.default_rng(4)
+    pheno = df.drop(snps, axis=1).iloc[rng.permutation(df.shape[0])]
+    geno = df.loc[~df.index.duplicated(), snps]
+    geno = geno.loc[rng.permutation(geno.index.values)]
+    info = pd.DataFrame({"chrom": [markers[s][0] for s in snps], "pos": [markers[s][1] for s in snps],
+                         "a1": [markers[s][2] for s in snps], "a2": [markers[s][3] for s in snps]},
+                        index=snps)
+    formula = ("[outcome=pheno3, groups=sampleid] ~ SNPs + age + var1 + factor(gender) + "
+               "factor(visit)")
+    prefix = str(tmp_path / "two_step")
+    spec._reset()
+    kept = analysis.execute_mixedlm_two_step(
+        DataFramePhenotypes(pheno, repeated_measurements=True), DataFrameReader(geno, info),
+        formula, p_threshold=1.0, output_prefix=prefix)
+    assert kept == set(snps)
+    approx = pd.read_csv(prefix + ".mixedlm_approximation.txt", sep="\t").set_index("snp")
+    assert list(approx.index) == snps and (approx.approximation == "Yes").all()
+    assert (approx.n == 60).all()
+    final = pd.read_csv(prefix + ".txt", sep="\t").set_index("snp")
+    rec = EXPECTED["mixedlm"]["test_mixedlm_gwas"]
+    for c in rec["checks"]:
+        if c["entity"] != "SNPs" or c["field"] not in ("coef", "std_err", "z_value"):
+            continue
+        col = {"coef": "coef", "std_err": "se", "z_value": "z"}[c["field"]]
+        assert abs(final.loc[c["snp"], col] - c["expected"]) < 10.0 ** -min(c["places"], 5), c
+    # a strict threshold keeps only the strongest markers
+    spec._reset()
+    p_sorted = approx.p.sort_values()
+    kept2 = analysis.execute_mixedlm_two_step(
+        DataFramePhenotypes(pheno, repeated_measurements=True), DataFrameReader(geno, info),
+        formula, p_threshold=float(p_sorted.iloc[1]) * 1.0001, output_prefix=prefix + "_b")
+    assert kept2 == set(p_sorted.index[:2])
