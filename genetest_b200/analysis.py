@@ -189,9 +189,8 @@ def execute(phenotypes, genotypes, modelspec, subscribers=None,
         variant_predicates = []
 
     if isinstance(modelspec.outcome, PheWAS):
-        raise NotImplementedError(
-            "pheWAS analyses are outside the B200 hot path (per-SNP "
-            "association loop)")
+        return _execute_phewas(phenotypes, genotypes, modelspec, subscribers,
+                               variant_predicates, output_prefix, subgroups)
 
     data = modelspec.create_data_matrix(phenotypes, genotypes)
     data = data.dropna()            # missing outcome or covariable
@@ -481,6 +480,47 @@ def _dispatch_block(block, subscribers, messages):
                 subscriber.handle(results)
             except KeyError as e:
                 subscribers_module.subscriber_error(e.args[0])
+
+
+def _execute_phewas(phenotypes, genotypes, modelspec, subscribers,
+                    variant_predicates, output_prefix, subgroups):
+    """Phenome-wide scan (``analysis.py:328-452``): the same predictors against
+    every phenotype that is not one of them, one fit each (a batch of one on
+    the engine for the GPU models) -- not a per-SNP loop, so no batching; the
+    reference's worker processes are replaced by a plain loop."""
+    if subgroups:
+        raise NotImplementedError(
+            "Stratified analyses for pheWAS are not supported yet.")
+    if variant_predicates:
+        raise ValueError(
+            "Variant predicates can only be used in the context of GWAS "
+            "analyses.")
+    data = modelspec.create_data_matrix(phenotypes, genotypes)
+    predictors = [i.id for i in modelspec.predictors]
+    if "intercept" in data.columns:
+        predictors.append("intercept")
+    X = data[predictors]
+    fit = modelspec.test().fit
+    translations = modelspec.get_translations()
+    for entity in modelspec.outcome.li:
+        if entity in modelspec.predictors:
+            continue
+        y_data = data[[entity.id]]
+        not_missing = _missing(y_data, X)
+        try:
+            results = fit(y_data[not_missing], X[not_missing])
+        except Exception as e:           # the reference skips the phenotype
+            logger.debug("Exception raised during fitting: {}".format(e))
+            continue
+        results["outcome"] = translations[entity.id]
+        for subscriber in subscribers:
+            try:
+                subscriber.handle(results)
+            except KeyError as e:
+                subscribers_module.subscriber_error(e.args[0])
+    for subscriber in subscribers:
+        subscriber.close()
+    logger.info("PheWAS complete.")
 
 
 def _host_fit_loop(genotypes, test, subscribers, y, X, variant_predicates,

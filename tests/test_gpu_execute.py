@@ -574,3 +574,47 @@ def test_mixedlm_two_step(tmp_path):
         DataFramePhenotypes(pheno, repeated_measurements=True), DataFrameReader(geno, info),
         formula, p_threshold=float(p_sorted.iloc[1]) * 1.0001, output_prefix=prefix + "_b")
     assert kept2 == set(p_sorted.index[:2])
+
+
+def test_phewas_matches_single_fits(tmp_path):
+    """Phenome-wide scan (analysis.py:328-452): the same predictors against every phenotype
+    that is not one of them; each result equals the single fit of that outcome."""
+    df = load_table("linear")
+    rng = np.random.default_rng(8)
+    order = rng.permutation(df.index.values)
+    genotypes = _dataframe_reader(df, order, ["snp1", "snp2"])
+    cols = [c for c in df.columns if not c.startswith("snp")]
+
+    def phenotypes():
+        ph = _DummyPhenotypes()
+        ph.data = df[cols].iloc[rng.permutation(df.shape[0])]
+        return ph
+
+    spec._reset()
+    sub = subscribers.ResultsMemory()
+    modelspec = spec.ModelSpec(outcome=spec.PheWAS(),
+                               predictors=[spec.genotypes.snp1, spec.phenotypes.age],
+                               test="linear")
+    analysis.execute(phenotypes(), genotypes, modelspec, subscribers=[sub])
+    outcomes = sorted(r["outcome"] for r in sub.results)
+    assert outcomes == sorted(c for c in cols if c != "age") and len(outcomes) >= 3
+    for r in sub.results:
+        spec._reset()
+        one = subscribers.ResultsMemory()
+        single = spec.ModelSpec(outcome=spec.phenotypes[r["outcome"]],
+                                predictors=[spec.genotypes.snp1, spec.phenotypes.age],
+                                test="linear")
+        analysis.execute(phenotypes(), genotypes, single, subscribers=[one])
+        want = one.results[0]
+        for col in ("snp1", "age", "intercept"):
+            for fld in ("coef", "std_err", "p_value"):
+                assert r[col][fld] == pytest.approx(want[col][fld], rel=1e-10), (r["outcome"], col, fld)
+        assert r["MODEL"]["nobs"] == want["MODEL"]["nobs"]
+    # GWAS-only options are refused as in the reference
+    spec._reset()
+    with pytest.raises(ValueError):
+        analysis.execute(phenotypes(), genotypes,
+                         spec.ModelSpec(outcome=spec.PheWAS(), predictors=[spec.phenotypes.age],
+                                        test="linear"),
+                         subscribers=[subscribers.ResultsMemory()],
+                         variant_predicates=[lambda g: True])
