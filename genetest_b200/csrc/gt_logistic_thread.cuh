@@ -1,5 +1,6 @@
 // K4, thread-per-SNP version: batched IRLS for the logistic model, FP64, for
-// .bed rows, a binary outcome, no interaction column and at most 13 parameters.
+// .bed rows, a binary outcome, at most one SNP x covariate interaction column
+// and at most 13 parameters.
 //
 // Restates sm.GLM(y, X, family=Binomial()).fit() as called by
 // genetest/statistics/models/logistic.py:38-40 (start mu = (y + .5) / 2, one
@@ -15,14 +16,18 @@
 //     a 13 x 13 symmetric update, and every warp streams the whole design
 //     through L1 for itself);
 //   * all markers of a CTA walk the samples together, so the design rows
-//     [q | y] are read ONCE per CTA: a producer warp bulk-copies them (TMA,
-//     mbarrier complete_tx) into a shared-memory ring and every lane reads the
-//     same address (broadcast, no bank conflicts);
-//   * each thread streams its own packed row with 128-bit loads, two chunks
-//     ahead;
+//     [q | w | y] are read ONCE per CTA: bulk copies (TMA, mbarrier complete_tx,
+//     issued by warp 0 between its own blocks, or by a producer warp) fill a
+//     shared-memory ring and every lane reads the same address (broadcast, no
+//     bank conflicts);
+//   * each thread streams its own packed row word by word, one word ahead (the
+//     eight words of a 32-byte sector hit L1 after the first);
+//   * exp / log / reciprocal are straight-line polynomials for the ranges the
+//     pass needs, and the log-likelihood is summed with compensation (the stop
+//     rule compares deviances to 1e-8 absolute);
 //   * the p x p Cholesky solve, the triangular inverse and the map back to the
 //     reference's parameterisation run fully unrolled in registers.
-// The markers of a warp take their IRLS passes in lockstep; one that needs
+// The markers of a CTA take their IRLS passes in lockstep; one that needs
 // more than `maxpass` passes (perfect separation takes dozens) is handed to the
 // warp-per-SNP kernel (status GT_ITER_DEFER), which is the better shape for a
 // few long-running markers.
