@@ -63,18 +63,16 @@ class PlinkReader(GenotypesReader):
         self.prefix = prefix
         # .fam / .bim: six whitespace-separated fields per line.  One split of the whole file
         # and strided slices of the token list (0.16 s for 262k markers + 100k samples; the
-        # pandas C parser with string columns took 0.5 s); files with another field count go
-        # through pandas.
+        # pandas C parser with string columns took 0.5 s).
         def six_columns(path):
             with open(path) as f:
                 text = f.read()
             tok = text.split()
             n_lines = sum(1 for line in text.splitlines() if line and not line.isspace())
-            if len(tok) == 6 * n_lines:
-                return [tok[j::6] for j in range(6)]
-            tab = pd.read_csv(path, sep=r"\s+", header=None, dtype=object,
-                              keep_default_na=False, na_filter=False, engine="c")
-            return [tab[j].tolist() for j in range(6)]
+            if len(tok) != 6 * n_lines:
+                raise ValueError("{}: every line needs six whitespace-separated "
+                                 "fields".format(path))
+            return [tok[j::6] for j in range(6)]
 
         if os.path.getsize(prefix + ".fam"):
             cols = six_columns(prefix + ".fam")

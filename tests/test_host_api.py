@@ -793,3 +793,24 @@ def test_bgen_reader(tmp_path, layout, bits, compress):
                                       np.isnan(got[3].genotypes))
         # iteration restarts cleanly after a lookup
         assert len(list(r.iter_genotypes())) == m
+
+
+def test_plink_reader_text_tables(tmp_path):
+    """.fam / .bim parsing: any whitespace, blank lines; a line without six fields is an error."""
+    from genetest_b200.genotypes import PlinkReader, PlinkWriter
+    p = str(tmp_path / "c")
+    with PlinkWriter(p) as w:
+        w.write_genotypes(np.array([0, 1, 2, -1, 1]))
+        w.write_genotypes(np.array([2, 2, 0, 0, 1]))
+        w.write_bim([(1, "rs1", 10, "A", "G"), (2, "rs2", 20, "C", "T")])
+        w.write_fam(["a", "b", "c", "d", "e"])
+    want = [("rs1", "1", 10, "A", "G"), ("rs2", "2", 20, "C", "T")]
+    assert PlinkReader(p).variant_table() == want
+    with open(p + ".bim", "w") as f:
+        f.write("1  rs1\t0 10 A G\n\n2\trs2   0\t20\tC\tT\n   \n")
+    r = PlinkReader(p)
+    assert r.variant_table() == want and r.get_samples() == ["a", "b", "c", "d", "e"]
+    with open(p + ".bim", "w") as f:
+        f.write("1 rs1 0 10 A G\n2 rs2 0 20 C\n")
+    with pytest.raises(ValueError):
+        PlinkReader(p)
